@@ -1,0 +1,189 @@
+"""Architecture constants of the Qwen3-TTS-12Hz generation hot path.
+
+Every value mirrors the checkpoint's ``config.json``.  The
+reference never hard-codes these: it reads them through the un-vendored
+``mlx_audio.tts.utils.load_model`` (reference call site: src/qwen3_tts/io.py:111-112),
+so nothing here is a literal inside a kernel -- kernels receive them as arguments.
+
+Three sizes are defined:
+  * ``full()``  -- the 1.7B shape named by BASELINE.json (bench + full-size parity)
+  * ``small()`` -- same head_dim / group structure, fewer and narrower layers (GPU parity)
+  * ``tiny()``  -- seconds on CPU (oracle-vs-cousin tests, golden fixtures)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field, asdict
+from typing import Dict, Tuple
+
+QUANT_GROUP = 64  # config.json "quantization": {"group_size": 64, "bits": 8}
+QUANT_BITS = 8
+
+
+@dataclass
+class TalkerConfig:
+    hidden_size: int = 2048
+    num_layers: int = 28
+    num_heads: int = 16
+    num_kv_heads: int = 8
+    head_dim: int = 128
+    intermediate_size: int = 6144
+    vocab_size: int = 3072          # codec vocabulary of code group 0 (+ control ids)
+    text_vocab_size: int = 151936
+    text_hidden_size: int = 2048
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+    # control ids inside the codec vocabulary
+    codec_pad_id: int = 2148
+    codec_bos_id: int = 2149
+    codec_eos_id: int = 2150
+    codec_think_id: int = 2154
+    codec_nothink_id: int = 2155
+    codec_think_bos_id: int = 2156
+    codec_think_eos_id: int = 2157
+    codec_language_id: Dict[str, int] = field(default_factory=lambda: {
+        "chinese": 2055, "english": 2050, "german": 2053, "italian": 2070, "portuguese": 2071,
+        "spanish": 2054, "japanese": 2058, "korean": 2064, "french": 2061, "russian": 2069})
+    # the nine preset speakers of reference config.py:44-49 (lower-cased at custom.py:166)
+    spk_id: Dict[str, int] = field(default_factory=lambda: {
+        "serena": 3066, "vivian": 3065, "uncle_fu": 3010, "ryan": 3061, "aiden": 2861,
+        "ono_anna": 2873, "sohee": 2864, "eric": 2875, "dylan": 2878})
+
+    @property
+    def q_dim(self) -> int:
+        return self.num_heads * self.head_dim
+
+    @property
+    def kv_dim(self) -> int:
+        return self.num_kv_heads * self.head_dim
+
+
+@dataclass
+class CodePredictorConfig:
+    hidden_size: int = 1024
+    num_layers: int = 5
+    num_heads: int = 16
+    num_kv_heads: int = 8
+    head_dim: int = 128
+    intermediate_size: int = 3072
+    vocab_size: int = 2048
+    num_code_groups: int = 16       # -> 15 embeddings + 15 heads
+    embed_dim: int = 2048           # codec_embedding width == talker hidden
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 1e6
+
+    @property
+    def q_dim(self) -> int:
+        return self.num_heads * self.head_dim
+
+    @property
+    def kv_dim(self) -> int:
+        return self.num_kv_heads * self.head_dim
+
+
+@dataclass
+class CodecConfig:
+    """Speech-tokenizer decoder (12.5 Hz -> 24 kHz)."""
+    num_quantizers: int = 16
+    num_semantic: int = 1
+    codebook_size: int = 2048
+    codebook_dim: int = 256         # vector width of every codebook
+    rvq_out_dim: int = 512          # 1x1 output projections 256 -> 512
+    latent_dim: int = 1024          # pre_conv output / ConvNeXt width
+    tf_hidden: int = 512
+    tf_intermediate: int = 1024
+    tf_heads: int = 16
+    tf_head_dim: int = 64
+    tf_layers: int = 8
+    sliding_window: int = 72
+    tf_rope_theta: float = 1e4
+    tf_rms_eps: float = 1e-5
+    layer_scale: float = 0.01
+    upsampling_ratios: Tuple[int, ...] = (2, 2)
+    upsample_rates: Tuple[int, ...] = (8, 5, 4, 3)
+    decoder_dim: int = 1536
+    chunk_size: int = 300
+    left_context: int = 25
+    # the on-disk cousin trims k-s on BOTH sides of every transposed conv
+    # (qwen3_omni_moe:3319-3331); "right" is the strictly causal alternative.
+    transconv_trim: str = "both"
+    sample_rate: int = 24000
+
+    @property
+    def hop(self) -> int:
+        h = 1
+        for r in self.upsampling_ratios + self.upsample_rates:
+            h *= r
+        return h
+
+    def out_len(self, frames: int) -> int:
+        """Samples produced by ONE vocoder call on `frames` code frames."""
+        n = frames
+        for r in self.upsampling_ratios:
+            n *= r
+        for r in self.upsample_rates:
+            n = (n - 1) * r if self.transconv_trim == "both" else n * r
+        return n
+
+
+@dataclass
+class ModelConfig:
+    tts_model_type: str = "custom_voice"      # custom_voice | voice_design | base
+    talker: TalkerConfig = field(default_factory=TalkerConfig)
+    cp: CodePredictorConfig = field(default_factory=CodePredictorConfig)
+    codec: CodecConfig = field(default_factory=CodecConfig)
+    tts_pad_token_id: int = 151671
+    tts_bos_token_id: int = 151672
+    tts_eos_token_id: int = 151673
+    im_start_id: int = 151644
+    im_end_id: int = 151645
+    assistant_id: int = 77091
+    quant_group: int = QUANT_GROUP
+    quant_bits: int = QUANT_BITS
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+    @classmethod
+    def from_dict(cls, d: dict) -> "ModelConfig":
+        d = dict(d)
+        t = TalkerConfig(**d.pop("talker", {}))
+        c = CodePredictorConfig(**d.pop("cp", {}))
+        k = dict(d.pop("codec", {}))
+        for key in ("upsampling_ratios", "upsample_rates"):
+            if key in k:
+                k[key] = tuple(k[key])
+        return cls(talker=t, cp=c, codec=CodecConfig(**k), **d)
+
+
+def full(tts_model_type: str = "custom_voice") -> ModelConfig:
+    return ModelConfig(tts_model_type=tts_model_type)
+
+
+def _with_small_text_vocab(cfg: ModelConfig) -> ModelConfig:
+    """Reduced text vocabularies keep the special text ids at the top of the table."""
+    v = cfg.talker.text_vocab_size
+    cfg.tts_pad_token_id, cfg.tts_bos_token_id, cfg.tts_eos_token_id = v - 3, v - 2, v - 1
+    cfg.im_start_id, cfg.im_end_id, cfg.assistant_id = v - 6, v - 5, v - 4
+    return cfg
+
+
+def small(tts_model_type: str = "custom_voice") -> ModelConfig:
+    """GPU-parity size: real head_dim/GQA/group structure, 3+2 layers, narrow."""
+    t = TalkerConfig(hidden_size=512, num_layers=3, num_heads=4, num_kv_heads=2, head_dim=128,
+                     intermediate_size=1024, text_vocab_size=4096, text_hidden_size=512)
+    c = CodePredictorConfig(hidden_size=256, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=128,
+                            intermediate_size=512, embed_dim=512)
+    k = CodecConfig(codebook_dim=64, rvq_out_dim=128, latent_dim=256, tf_hidden=128, tf_intermediate=256,
+                    tf_heads=4, tf_head_dim=32, tf_layers=2, decoder_dim=192)
+    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k))
+
+
+def tiny(tts_model_type: str = "custom_voice") -> ModelConfig:
+    """CPU-seconds size used by the golden fixtures."""
+    t = TalkerConfig(hidden_size=128, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=32,
+                     intermediate_size=256, text_vocab_size=1024, text_hidden_size=128)
+    c = CodePredictorConfig(hidden_size=64, num_layers=2, num_heads=4, num_kv_heads=2, head_dim=32,
+                            intermediate_size=128, embed_dim=128)
+    k = CodecConfig(codebook_dim=32, rvq_out_dim=64, latent_dim=64, tf_hidden=64, tf_intermediate=128,
+                    tf_heads=4, tf_head_dim=16, tf_layers=2, decoder_dim=96)
+    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k))
