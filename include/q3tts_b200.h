@@ -1,0 +1,246 @@
+/*
+ * q3tts_b200.h -- C ABI of the B200-native Qwen3-TTS generation hot path.
+ *
+ * This is the drop-in boundary BELOW the two Python callables the reference imports
+ * (`mlx_audio.tts.utils.load_model`, reference src/qwen3_tts/io.py:111-112, and
+ * `mlx_audio.tts.generate.generate_audio`, sessions/custom.py:163-170, design.py:76-81,
+ * clone.py:218-224).  In the reference stack these entry points are MLX graph ops that end in
+ * Metal kernels (un-vendored: mlx==0.30.3 / mlx-audio==0.3.1, pyproject.toml:38-41); each
+ * function below names the MLX op it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - the caller (PyTorch) allocates every buffer, including workspaces; no function allocates,
+ *     frees or synchronises; everything is enqueued on `stream` (a cudaStream_t passed as void*)
+ *     and is CUDA-graph capturable;
+ *   - return value 0 = ok, non-zero = error (message via q3t_last_error()); no C++ exception
+ *     crosses the boundary;
+ *   - activations are fp32 row-major, K/V pages are bf16, weights are "W8 tiles" (below).
+ *
+ * W8 tile format (affine 8-bit, group 64; MLX `quantized_matmul` weights re-laid for HBM streaming)
+ *   matrix [N, K], N % 16 == 0, K % 256 == 0, stored as (N/16)*(K/256) tiles of 4352 bytes ordered
+ *   [row_tile][k_chunk]; a tile = 4096 B of uint8 codes in mma-fragment order + 16 rows x
+ *   {4 bf16 scales, 4 bf16 biases}.  See qwen3_tts_b200/weights.py:pack_w8 for the exact permutation.
+ */
+#ifndef Q3TTS_B200_H
+#define Q3TTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define Q3T_ABI_VERSION 1
+#define Q3T_TILE_BYTES 4352
+#define Q3T_KV_PAGE 16
+
+int q3t_abi_version(void);
+const char* q3t_last_error(void);
+/* number of kernel launches enqueued by this library since load (bench.py "gpu_launches") */
+unsigned long long q3t_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * W8 GEMV  (replaces mx.quantized_matmul, qmv path, M = 1..2 rows per launch)
+ *   y[m, :] = epilogue( W8 . prologue(x[m, :]) )
+ * prologue: RAW            x is [M, K]
+ *           RMSNORM        x is [M, K]; x * rsqrt(mean(x^2)+eps) * norm_w      (mx.fast.rms_norm)
+ *           SWIGLU         x is [M, 2K]; silu(x[:, :K]) * x[:, K:]
+ * gather  : if `gather_idx` != NULL, row m of x is x + gather_idx[m*gather_idx_stride] * gather_row_stride
+ * epilogue: (+ lin_bias[N]) -> act (0 none, 1 SiLU) -> (+ resid[m, :])   ; y may alias resid
+ * ------------------------------------------------------------------------------------------- */
+enum { Q3T_PRO_RAW = 0, Q3T_PRO_RMSNORM = 1, Q3T_PRO_SWIGLU = 2 };
+
+typedef struct {
+    const void* w;            /* W8 tiles */
+    int N, K;
+    const float* lin_bias;    /* [N] or NULL */
+} q3t_w8;
+
+typedef struct {
+    q3t_w8 w;
+    int M;                    /* 1 or 2 */
+    int prologue;
+    const float* x;  long long x_stride;        /* floats between rows */
+    const float* norm_w;  float eps;            /* RMSNORM only */
+    const int* gather_idx;  int gather_idx_stride;  long long gather_row_stride;
+    int act;
+    const float* resid;  long long resid_stride;
+    float* y;  long long y_stride;
+} q3t_gemv_args;
+
+int q3t_w8_gemv(const q3t_gemv_args* a, void* stream);
+
+/* RMSNorm rows: y[m,:] = x[m,:] * rsqrt(mean(x^2)+eps) * w            (mx.fast.rms_norm) */
+int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Paged-KV GQA decode attention with fused per-head q/k RMSNorm + RoPE + KV-page write
+ *   (replaces mx.fast.rms_norm x2, mx.fast.rope x2, cache update, mx.fast.scaled_dot_product_attention)
+ * qkv       [B, (H + 2*Hkv) * D] fp32: q heads, then k heads, then v heads (fused QKV GEMV output)
+ * kv_pool   bf16 pages of ONE layer: [n_pages][2 (k,v)][Hkv][Q3T_KV_PAGE][D]
+ * block_tbl [B, max_pages] int32 page ids;  pos [B] int32 = index of the NEW token (ctx = pos+1)
+ * inv_freq  [D/2] fp32 RoPE inverse frequencies (host-computed exactly as the oracle does)
+ * out       [B, H*D] fp32
+ * work      fp32 workspace >= B*Hkv*nsplit*(H/Hkv)*(D+2); counters: int32 [B*Hkv], zero-initialised once
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* qkv;
+    const float* q_norm_w; const float* k_norm_w; float eps;
+    const float* inv_freq;
+    void* kv_pool;
+    const int* block_tbl; int max_pages;
+    const int* pos;
+    float* out;
+    float* work; int* counters;
+    int B, H, Hkv, D, nsplit;
+} q3t_attn_args;
+
+int q3t_attn_decode(const q3t_attn_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-device sampler (replaces mx.argmax / mx.random.categorical + host-side logits processors)
+ * Order of operations = HF generation: repetition penalty over the set of
+ * previously generated ids, min_new_tokens EOS mask, suppress range (except eos), temperature,
+ * top-k (ties kept), top-p, then argmax (lowest index wins) or inverse-CDF categorical draw.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int do_sample; float temperature; int top_k; float top_p; float repetition_penalty;
+    int min_new_tokens; int suppress_lo, suppress_hi, eos_id;
+    unsigned long long seed;
+} q3t_sampling;
+
+typedef struct {
+    const float* logits; int B, V; long long logits_stride;
+    q3t_sampling sp;
+    unsigned int* seen;       /* [B, ceil(V/32)] bitmask of generated ids (NULL: no penalty, no update) */
+    const int* step;          /* device scalar: frames generated so far (min_new_tokens, RNG counter) */
+    int rng_stream;           /* distinguishes the 16 draws of a frame */
+    const float* uniforms;    /* optional [B] externally supplied uniforms (tests) */
+    int* out; long long out_stride;             /* out[b*out_stride] = chosen id (fixed address) */
+    long long fo_stride, fo_step_stride;        /* addressing of forced/own: [b*fo_stride + step*fo_step_stride] */
+    const int* forced;        /* optional teacher forcing: overrides the choice */
+    int* own;                 /* optional: what the sampler itself picked (before forcing) */
+    int* done;                /* optional [B]: set to 1 when the chosen id == eos_id */
+} q3t_sample_args;
+
+int q3t_sample(const q3t_sample_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Whole-frame enqueue: talker decode step -> sample code0 -> 15 code-predictor passes -> next input
+ *   (replaces the per-frame body of mlx_audio's Model.generate loop; SURVEY 3.1 "HOT LOOP")
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* input_norm; q3t_w8 qkv;
+    const float* q_norm; const float* k_norm;
+    q3t_w8 o;
+    const float* post_norm; q3t_w8 gate_up; q3t_w8 down;
+} q3t_layer;
+
+typedef struct {
+    int hidden, n_layers, n_heads, n_kv_heads, head_dim, inter;
+    float eps;
+    const q3t_layer* layers_host;   /* HOST array [n_layers] */
+    const float* final_norm;
+    const float* inv_freq;          /* [head_dim/2] */
+    void* kv_pool; long long kv_layer_stride_bytes;   /* bf16 pages, per-layer stride */
+    const int* block_tbl; int max_pages;
+    int attn_nsplit;
+} q3t_stack;
+
+typedef struct {
+    int B;
+    /* talker */
+    q3t_stack talker;
+    q3t_w8 codec_head;              /* [V, H] */
+    int talker_vocab;
+    const float* codec_embedding;   /* [V, H] fp32 */
+    q3t_sampling talker_sp;
+    /* code predictor */
+    q3t_stack cp;
+    q3t_w8 cp_proj;                 /* [Hc, H] + bias */
+    const float* const* cp_embeddings_host;   /* HOST array [G-1] of device ptrs [Vc, H] */
+    const float* const* cp_embeddings_dev;    /* the same table in device memory */
+    const q3t_w8* cp_heads_host;    /* HOST array [G-1] */
+    int cp_vocab, n_groups;
+    q3t_sampling cp_sp;
+    /* per-utterance state (device) */
+    float* x;              /* [B, H]  talker residual stream: holds the next input on entry */
+    float* hidden;         /* [B, H]  post-final-norm talker hidden */
+    float* logits;         /* [B, V]  */
+    float* cp_logits;      /* [B, Vc] (per pass; also [G-1, B, Vc] when keep_cp_logits) */
+    int keep_cp_logits;
+    float* xc;             /* [B, Hc] code-predictor residual stream */
+    float* qkv;            /* [B, max(q+2kv dims)] */
+    float* attn;           /* [B, max(H*D)] */
+    float* gu;             /* [B, 2*max(inter)] */
+    float* attn_work; int* attn_counters;
+    int* pos;              /* [B] talker position of the token being fed */
+    int* cp_pos;           /* [G, B] constant table: cp_pos[g][b] = g */
+    int* step;             /* device scalar: frame index */
+    int* cur_codes;        /* [B, G] codes of the frame being generated */
+    int* codes;            /* [B, max_frames, G] int32 */
+    int* own_codes;        /* optional [B, max_frames, G]: un-forced choices (parity tests) */
+    int max_frames;
+    unsigned int* seen;    /* [B, ceil(V/32)] */
+    int* done;             /* [B] */
+    const float* trailing; /* [B, n_trailing, H]; row min(step, n_trailing-1) is added (last row = tts_pad) */
+    int n_trailing;
+    const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
+} q3t_frame_args;
+
+/* one talker forward for the token currently in `x` (prefill token or decode step), logits optional */
+int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream);
+/* everything after the talker logits of a frame + the next talker step */
+int q3t_frame(const q3t_frame_args* f, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Speech-tokenizer decoder operators (replace mx.take/add, mx.conv1d, mx.conv_transpose1d, ...)
+ * Activations are time-major fp32 [B, T, C].
+ * ------------------------------------------------------------------------------------------- */
+/* bit-exact RVQ gather + left-to-right fp32 sum: codes [B, G, T] int32, tables HOST array of G device
+ * ptrs [size, dim]; groups [g_lo, g_hi) summed into out [B, T, dim] */
+int q3t_rvq_gather_sum(const int* codes, const float* const* tables_host, int B, int G, int T, int g_lo, int g_hi,
+                       int dim, int codebook_size, float* out, void* stream);
+
+enum { Q3T_ACT_NONE = 0, Q3T_ACT_SILU = 1, Q3T_ACT_GELU = 2, Q3T_ACT_SNAKE = 3, Q3T_ACT_SWIGLU_PAIR = 4 };
+
+/* Generic causal tap-GEMM:  out[b, t*up + p, co] = epi( bias[co] + sum_{j<taps} sum_ci A[b, t + shift_j, ci] * W[j][p*Cout + co][ci] )
+ *   conv1d (k taps, dilation d): up = 1, shift_j = -(k-1-j)*d          (rows before 0 read as zero)
+ *   conv_transpose1d (k = 2*up): taps = 2 with shifts given by `shift`; N = up*Cout
+ *   linear: taps = 1, shift 0
+ * epilogue: v = acc + bias; v = v * scale[co] (optional); v += resid (optional) ; out_raw = v (optional);
+ *           out_act = act(v) (optional; SNAKE uses act_a = exp(alpha), act_b = 1/(exp(beta)+1e-9) per channel) */
+typedef struct {
+    const float* A; int B, T_in, Cin;          /* [B, T_in, Cin] */
+    const float* W;                            /* [taps][N][Cin], N = up*Cout */
+    const float* bias;                         /* [Cout] or NULL */
+    int taps; int shift[8]; int up; int Cout;
+    int T_out_rows;                            /* GEMM rows per batch item (t range) */
+    const float* scale;                        /* [Cout] or NULL */
+    const float* resid;                        /* [B, T_out_rows*up, Cout] or NULL */
+    float* out_raw;                            /* or NULL */
+    float* out_act; int act; const float* act_a; const float* act_b;
+} q3t_tapgemm_args;
+
+int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream);
+
+/* depthwise causal conv k (weights [C, k]) + LayerNorm over C (ConvNeXt front half) */
+int q3t_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,
+                  float ln_eps, int B, int T, int C, int ksize, float* out, void* stream);
+
+/* sliding-window causal MHA for the codec transformer: qkv [B, T, 3*H*D] (RoPE is applied to q and k IN PLACE
+ * first) -> out [B, T, H*D] */
+int q3t_window_attn(float* qkv, const float* inv_freq, int B, int T, int H, int D, int window, float* out,
+                    void* stream);
+
+/* elementwise SnakeBeta on [rows, C]: a = exp(alpha), b = 1/(exp(beta)+1e-9) precomputed per channel */
+int q3t_snake(const float* x, const float* a, const float* b, long long rows, int C, float* y, void* stream);
+
+/* final: clamp(x, -1, 1) and optional PCM16 conversion */
+int q3t_clamp_pcm16(const float* x, long long n, float* y, int16_t* pcm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q3TTS_B200_H */

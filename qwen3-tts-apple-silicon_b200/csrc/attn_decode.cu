@@ -1,0 +1,230 @@
+// Paged-KV GQA decode attention with fused per-head q/k RMSNorm + RoPE + KV-page write (sm_100a).
+//
+// Replaces, for one new token per sequence: mx.fast.rms_norm (q_norm, k_norm), mx.fast.rope, the KV
+// cache update and mx.fast.scaled_dot_product_attention of the reference stack
+// (cousin arithmetic: transformers qwen3/modeling_qwen3.py:222-291).
+//
+// grid = (kv_head, split, batch); 128 threads.  A CTA owns one KV head (its `REP` query heads share every
+// K/V byte it streams) and one contiguous slice of the context, so the KV pages are read exactly once
+// per step.  Each half-warp streams one token at a time with 128-bit loads (16 lanes x 8 bf16 = one
+// 256 B row); scores are reduced with 4 xor-shuffles; softmax is online in fp32.  Slices are merged by
+// the last CTA to arrive (fixed split order => deterministic, no float atomics).
+#include "common.cuh"
+#include "../../include/q3tts_b200.h"
+
+namespace q3t {
+
+struct AttnParams {
+    const float* qkv; const float* q_norm_w; const float* k_norm_w; float eps;
+    const float* inv_freq;
+    __nv_bfloat16* kv_pool;
+    const int* block_tbl; int max_pages;
+    const int* pos;
+    float* out; float* work; int* counters;
+    int B, H, Hkv, nsplit;
+};
+
+template <int EPL> struct KvVec;
+template <> struct KvVec<8> { using T = uint4; };
+template <> struct KvVec<4> { using T = uint2; };
+template <> struct KvVec<2> { using T = uint32_t; };
+
+template <int EPL>
+__device__ __forceinline__ void load_bf16_row(const __nv_bfloat16* p, float (&o)[EPL]) {
+    typename KvVec<EPL>::T raw = *reinterpret_cast<const typename KvVec<EPL>::T*>(p);
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < EPL / 2; ++i) { o[2 * i] = bf16lo(u[i]); o[2 * i + 1] = bf16hi(u[i]); }
+}
+
+template <int D, int REP>
+__global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
+    constexpr int E = D / 32;     // elements per lane in the prep stage
+    constexpr int EPL = D / 16;   // elements per sub-lane in the streaming stage
+    constexpr int PSTR = D + 2;   // partial record: acc[D], m, l
+    __shared__ float q_s[REP][D];
+    __shared__ float part_s[8][REP][PSTR];
+    __shared__ int is_last;
+
+    const int kvh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pos = p.pos[b], ctx = pos + 1;
+    int chunk = (ctx + p.nsplit - 1) / p.nsplit;
+    chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
+    const int s0 = split * chunk, s1 = min(ctx, s0 + chunk);
+    const bool owner = (pos >= s0 && pos < s1);
+    const int* btbl = p.block_tbl + (size_t)b * p.max_pages;
+    const size_t page_elems = (size_t)2 * p.Hkv * Q3T_KV_PAGE * D;
+    const size_t head_off = (size_t)kvh * Q3T_KV_PAGE * D;
+    const size_t v_off = (size_t)p.Hkv * Q3T_KV_PAGE * D;
+    const int qkv_dim = (p.H + 2 * p.Hkv) * D;
+    const float* row = p.qkv + (size_t)b * qkv_dim;
+
+    // ---- stage 1: q (REP heads), k, v of the new token: RMSNorm + RoPE ------------------------
+    if (s0 < s1) {
+        for (int vi = warp; vi < REP + 2; vi += 4) {
+            const bool is_q = vi < REP, is_k = vi == REP;
+            if (!is_q && !owner) continue;
+            const float* src = is_q ? row + (size_t)(kvh * REP + vi) * D
+                                    : (is_k ? row + (size_t)(p.H + kvh) * D : row + (size_t)(p.H + p.Hkv + kvh) * D);
+            float x[E];
+#pragma unroll
+            for (int e = 0; e < E; ++e) x[e] = src[lane * E + e];
+            if (is_q || is_k) {
+                float ss = 0.f;
+#pragma unroll
+                for (int e = 0; e < E; ++e) ss += x[e] * x[e];
+                ss = warp_sum(ss);
+                const float rstd = rsqrtf(ss / (float)D + p.eps);
+                const float* nw = is_q ? p.q_norm_w : p.k_norm_w;
+#pragma unroll
+                for (int e = 0; e < E; ++e) x[e] = nw[lane * E + e] * (x[e] * rstd);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float other = __shfl_xor_sync(0xffffffffu, x[e], 16);
+                    const float ang = (float)pos * p.inv_freq[(lane & 15) * E + e];
+                    float sn, cs;
+                    sincosf(ang, &sn, &cs);
+                    x[e] = (lane < 16) ? (x[e] * cs - other * sn) : (x[e] * cs + other * sn);
+                }
+            }
+            if (is_q) {
+                const float sc = rsqrtf((float)D);
+#pragma unroll
+                for (int e = 0; e < E; ++e) q_s[vi][lane * E + e] = x[e] * sc;
+            } else {
+                __nv_bfloat16* dst = p.kv_pool + (size_t)btbl[pos / Q3T_KV_PAGE] * page_elems + head_off +
+                                     (is_k ? 0 : v_off) + (size_t)(pos % Q3T_KV_PAGE) * D + lane * E;
+#pragma unroll
+                for (int e = 0; e < E; ++e) dst[e] = __float2bfloat16_rn(x[e]);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2: stream the slice --------------------------------------------------------------
+    const int hw = lane >> 4, sl = lane & 15, hwid = warp * 2 + hw;
+    float m_run[REP], l_run[REP], acc[REP][EPL], qr[REP][EPL];
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+        m_run[r] = -INFINITY; l_run[r] = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { acc[r][e] = 0.f; qr[r][e] = (s0 < s1) ? q_s[r][sl * EPL + e] : 0.f; }
+    }
+    for (int tok = s0 + hwid; tok < s1; tok += 16) {
+        const int tok2 = tok + 8;
+        const bool has2 = tok2 < s1;
+        const __nv_bfloat16* kp = p.kv_pool + (size_t)btbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
+                                  (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
+        const __nv_bfloat16* kp2 = has2 ? p.kv_pool + (size_t)btbl[tok2 / Q3T_KV_PAGE] * page_elems + head_off +
+                                              (size_t)(tok2 % Q3T_KV_PAGE) * D + sl * EPL
+                                        : kp;
+        float k0[EPL], v0[EPL], k1[EPL], v1[EPL];
+        load_bf16_row<EPL>(kp, k0);
+        load_bf16_row<EPL>(kp + v_off, v0);
+        load_bf16_row<EPL>(kp2, k1);
+        load_bf16_row<EPL>(kp2 + v_off, v1);
+#pragma unroll
+        for (int r = 0; r < REP; ++r) {
+            float sa = 0.f, sb = 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { sa = fmaf(qr[r][e], k0[e], sa); sb = fmaf(qr[r][e], k1[e], sb); }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o);
+            }
+            if (!has2) sb = -INFINITY;
+            const float mn = fmaxf(m_run[r], fmaxf(sa, sb));
+            const float corr = __expf(m_run[r] - mn);   // exp(-inf) = 0 on the first token
+            const float pa = __expf(sa - mn), pb = __expf(sb - mn);
+            l_run[r] = l_run[r] * corr + pa + pb;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) acc[r][e] = fmaf(pb, v1[e], fmaf(pa, v0[e], acc[r][e] * corr));
+            m_run[r] = mn;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) part_s[hwid][r][sl * EPL + e] = acc[r][e];
+        if (sl == 0) { part_s[hwid][r][D] = m_run[r]; part_s[hwid][r][D + 1] = l_run[r]; }
+    }
+    __syncthreads();
+
+    // ---- stage 3: merge the 8 half-warps, publish the slice partial ---------------------------
+    float* wbase = p.work + ((size_t)(b * p.Hkv + kvh) * p.nsplit) * REP * PSTR;
+    for (int i = tid; i < REP * D; i += 128) {
+        const int r = i / D, d = i % D;
+        float M = -INFINITY;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) M = fmaxf(M, part_s[h][r][D]);
+        float L = 0.f, A = 0.f;
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+            const float mh = part_s[h][r][D];
+            const float w = (mh == -INFINITY) ? 0.f : __expf(mh - M);
+            L = fmaf(part_s[h][r][D + 1], w, L);
+            A = fmaf(part_s[h][r][d], w, A);
+        }
+        float* rec = wbase + ((size_t)split * REP + r) * PSTR;
+        rec[d] = A;
+        if (d == 0) { rec[D] = M; rec[D + 1] = L; }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int prev = atomicAdd(p.counters + b * p.Hkv + kvh, 1);
+        is_last = (prev == p.nsplit - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int i = tid; i < REP * D; i += 128) {
+        const int r = i / D, d = i % D;
+        float M = -INFINITY;
+        for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, __ldcg(wbase + ((size_t)s * REP + r) * PSTR + D));
+        float L = 0.f, A = 0.f;
+        for (int s = 0; s < p.nsplit; ++s) {
+            const float* rec = wbase + ((size_t)s * REP + r) * PSTR;
+            const float ms = __ldcg(rec + D);
+            const float w = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+            L = fmaf(__ldcg(rec + D + 1), w, L);
+            A = fmaf(__ldcg(rec + d), w, A);
+        }
+        p.out[(size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d] = A / L;
+    }
+    if (tid == 0) p.counters[b * p.Hkv + kvh] = 0;   // re-arm for the next launch / graph replay
+}
+
+template <int D, int REP>
+static int launch_attn_t(const AttnParams& p, cudaStream_t stream) {
+    dim3 grid(p.Hkv, p.nsplit, p.B);
+    attn_decode_kernel<D, REP><<<grid, 128, 0, stream>>>(p);
+    Q3T_CHECK_LAUNCH("attn_decode");
+    return 0;
+}
+
+int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream) {
+    Q3T_REQUIRE(a->H % a->Hkv == 0, "attn_decode: H % Hkv");
+    Q3T_REQUIRE(a->nsplit >= 1 && a->nsplit <= 64, "attn_decode: nsplit in [1,64]");
+    AttnParams p;
+    p.qkv = a->qkv; p.q_norm_w = a->q_norm_w; p.k_norm_w = a->k_norm_w; p.eps = a->eps; p.inv_freq = a->inv_freq;
+    p.kv_pool = (__nv_bfloat16*)a->kv_pool; p.block_tbl = a->block_tbl; p.max_pages = a->max_pages; p.pos = a->pos;
+    p.out = a->out; p.work = a->work; p.counters = a->counters; p.B = a->B; p.H = a->H; p.Hkv = a->Hkv;
+    p.nsplit = a->nsplit;
+    const int rep = a->H / a->Hkv;
+    if (a->D == 128 && rep == 2) return launch_attn_t<128, 2>(p, stream);
+    if (a->D == 128 && rep == 1) return launch_attn_t<128, 1>(p, stream);
+    if (a->D == 128 && rep == 4) return launch_attn_t<128, 4>(p, stream);
+    if (a->D == 64 && rep == 2) return launch_attn_t<64, 2>(p, stream);
+    if (a->D == 64 && rep == 1) return launch_attn_t<64, 1>(p, stream);
+    Q3T_REQUIRE(false, "attn_decode: unsupported (head_dim, H/Hkv); built for D in {64,128}, rep in {1,2,4}");
+    return 2;
+}
+
+}  // namespace q3t
+
+extern "C" int q3t_attn_decode(const q3t_attn_args* a, void* stream) {
+    return q3t::launch_attn_decode(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Builds libq3tts_b200.so (sm_100a only) next to the Python package.  nvcc cross-compiles without a GPU.
+set -euo pipefail
+here="$(cd "$(dirname "$0")" && pwd)"
+out="$here/../qwen3_tts_b200/libq3tts_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+ARCH=(-gencode arch=compute_100a,code=sm_100a)
+FLAGS=("${ARCH[@]}" -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177)
+objs=(); pids=()
+mkdir -p "$here/build"
+for f in glue w8_gemv attn_decode sampler engine codec; do
+  src="$here/$f.cu"; obj="$here/build/$f.o"
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$here/common.cuh" -nt "$obj" ] || [ "$here/../../include/q3tts_b200.h" -nt "$obj" ]; then
+    "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" &
+    pids+=($!)
+  fi
+  objs+=("$obj")
+done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
+"$NVCC" "${ARCH[@]}" -shared --cudart static -o "$out" "${objs[@]}"
+echo "built $out"

@@ -1,0 +1,77 @@
+// Shared device/host helpers for the sm_100a kernels of the Qwen3-TTS hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace q3t {
+
+// ---- error plumbing (no exception crosses the C ABI) -----------------------------------------
+extern thread_local char g_err[512];
+extern unsigned long long g_launches;
+
+#define Q3T_CHECK_LAUNCH(name)                                                        \
+    do {                                                                              \
+        cudaError_t e__ = cudaGetLastError();                                         \
+        if (e__ != cudaSuccess) {                                                     \
+            snprintf(q3t::g_err, sizeof(q3t::g_err), "%s: %s", name, cudaGetErrorString(e__)); \
+            return 1;                                                                 \
+        }                                                                             \
+        ++q3t::g_launches;                                                            \
+    } while (0)
+
+#define Q3T_REQUIRE(cond, msg)                                                        \
+    do {                                                                              \
+        if (!(cond)) { snprintf(q3t::g_err, sizeof(q3t::g_err), "%s:%d: %s", __FILE__, __LINE__, msg); return 2; } \
+    } while (0)
+
+// ---- warp / block reductions --------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum; `red` is a shared float[32]; result broadcast to every thread.  Deterministic.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    float r = (lane < nw) ? red[lane] : -INFINITY;
+    r = warp_max(r);
+    return r;
+}
+
+// ---- streaming loads: weights are read exactly once per step -> do not allocate in L1 --------------
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+
+}  // namespace q3t

@@ -1,0 +1,162 @@
+// Frame orchestration of the generation hot loop: every kernel of a talker step / a whole frame is
+// enqueued from C++ on one stream (CUDA-graph capturable; no host round trip between the 16 sampled
+// codes of a frame).  Replaces the per-frame body of mlx_audio's `Model.generate` loop
+// (cousin driver transformers qwen3_omni_moe/modeling_qwen3_omni_moe.py:3243-3279).
+#include "common.cuh"
+#include "../../include/q3tts_b200.h"
+
+namespace q3t {
+
+int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream);
+int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream);
+int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
+
+// ---- small kernels --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      float* __restrict__ y, int H, float eps) {
+    __shared__ float red[32];
+    const float* xr = x + (size_t)blockIdx.x * H;
+    float* yr = y + (size_t)blockIdx.x * H;
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { const float v = xr[i]; ss += v * v; }
+    const float tot = block_sum(ss, red);
+    const float rstd = rsqrtf(tot / (float)H + eps);
+    for (int i = threadIdx.x; i < H; i += blockDim.x) yr[i] = w[i] * (xr[i] * rstd);
+}
+
+__global__ void advance_kernel(int* pos, int B, int* step) {
+    const int i = threadIdx.x;
+    if (i < B) pos[i] += 1;
+    if (step && i == 0) *step += 1;
+}
+
+// next talker input: emb_talker[c0] + sum_{g=1..G-1} emb_cp[g-1][c_g] summed sequentially in
+// fp32, then + trailing_text[min(step, n-1)]; also archives the frame's codes.
+__global__ void __launch_bounds__(256) next_input_kernel(const float* __restrict__ codec_emb,
+                                                         const float* const* __restrict__ cp_emb, const int* cur_codes,
+                                                         int G, int H, const float* __restrict__ trailing,
+                                                         int n_trailing, const int* step_p, float* x, int* codes,
+                                                         int max_frames) {
+    const int b = blockIdx.x, step = *step_p;
+    const int* cc = cur_codes + b * G;
+    const int trow = step < n_trailing - 1 ? step : n_trailing - 1;
+    const float* tr = trailing + ((size_t)b * n_trailing + trow) * H;
+    for (int i = threadIdx.x; i < H; i += blockDim.x) {
+        float acc = codec_emb[(size_t)cc[0] * H + i];
+        for (int g = 1; g < G; ++g) acc = acc + cp_emb[g - 1][(size_t)cc[g] * H + i];
+        x[(size_t)b * H + i] = acc + tr[i];
+    }
+    if (threadIdx.x < G && step < max_frames) codes[((size_t)b * max_frames + step) * G + threadIdx.x] = cc[threadIdx.x];
+}
+
+int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, cudaStream_t s) {
+    rmsnorm_kernel<<<M, 256, 0, s>>>(x, w, y, H, eps);
+    Q3T_CHECK_LAUNCH("rmsnorm");
+    return 0;
+}
+
+#define Q3T_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+// y[b0..b0+M) rows through one W8 matrix, two rows per launch
+static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
+                     const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
+                     float* y, long long ys, cudaStream_t s) {
+    for (int b0 = 0; b0 < B; b0 += 2) {
+        q3t_gemv_args a;
+        memset(&a, 0, sizeof(a));
+        a.w = w; a.M = (B - b0) >= 2 ? 2 : 1; a.prologue = prologue;
+        a.x = x + (gidx ? 0 : b0 * xs); a.x_stride = gidx ? 0 : xs; a.norm_w = norm_w; a.eps = eps;
+        a.gather_idx = gidx ? gidx + (long long)b0 * gidx_stride : nullptr; a.gather_idx_stride = gidx_stride;
+        a.gather_row_stride = grow; a.act = act;
+        a.resid = resid ? resid + b0 * rs : nullptr; a.resid_stride = rs;
+        a.y = y + b0 * ys; a.y_stride = ys;
+        Q3T_TRY(launch_w8_gemv(&a, s));
+    }
+    return 0;
+}
+
+// one token through a dense Qwen3 stack; x [B, hidden] is updated in place (residual stream)
+static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x, const int* pos, cudaStream_t s) {
+    const int B = f->B, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim;
+    const int qkvd = qd + 2 * kvd;
+    for (int l = 0; l < st.n_layers; ++l) {
+        const q3t_layer& L = st.layers_host[l];
+        Q3T_TRY(gemv_rows(L.qkv, B, Q3T_PRO_RMSNORM, x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->qkv,
+                          qkvd, s));
+        q3t_attn_args a;
+        memset(&a, 0, sizeof(a));
+        a.qkv = f->qkv; a.q_norm_w = L.q_norm; a.k_norm_w = L.k_norm; a.eps = st.eps; a.inv_freq = st.inv_freq;
+        a.kv_pool = (char*)st.kv_pool + (long long)l * st.kv_layer_stride_bytes;
+        a.block_tbl = st.block_tbl; a.max_pages = st.max_pages; a.pos = pos; a.out = f->attn; a.work = f->attn_work;
+        a.counters = f->attn_counters; a.B = B; a.H = st.n_heads; a.Hkv = st.n_kv_heads; a.D = st.head_dim;
+        a.nsplit = st.attn_nsplit;
+        Q3T_TRY(launch_attn_decode(&a, s));
+        Q3T_TRY(gemv_rows(L.o, B, Q3T_PRO_RAW, f->attn, qd, nullptr, 0.f, nullptr, 0, 0, 0, x, hid, x, hid, s));
+        Q3T_TRY(gemv_rows(L.gate_up, B, Q3T_PRO_RMSNORM, x, hid, L.post_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->gu,
+                          2 * st.inter, s));
+        Q3T_TRY(gemv_rows(L.down, B, Q3T_PRO_SWIGLU, f->gu, 2 * st.inter, nullptr, 0.f, nullptr, 0, 0, 0, x, hid, x, hid,
+                          s));
+    }
+    return 0;
+}
+
+static int talker_step(const q3t_frame_args* f, int want_logits, int bump_step, cudaStream_t s) {
+    const q3t_stack& t = f->talker;
+    Q3T_REQUIRE(f->B >= 1 && f->B <= 1024, "talker_step: batch out of range");
+    Q3T_TRY(stack_forward(f, t, f->x, f->pos, s));
+    Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
+    if (want_logits)
+        Q3T_TRY(gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr,
+                          0, f->logits, f->talker_vocab, s));
+    advance_kernel<<<1, 1024, 0, s>>>(f->pos, f->B, bump_step ? f->step : nullptr);
+    Q3T_CHECK_LAUNCH("advance");
+    return 0;
+}
+
+static int sample_into(const q3t_frame_args* f, const float* logits, int V, const q3t_sampling& sp, unsigned int* seen,
+                       int g, int* done, cudaStream_t s) {
+    q3t_sample_args a;
+    memset(&a, 0, sizeof(a));
+    const int G = f->n_groups;
+    a.logits = logits; a.B = f->B; a.V = V; a.logits_stride = V; a.sp = sp; a.seen = seen; a.step = f->step;
+    a.rng_stream = g; a.out = f->cur_codes + g; a.out_stride = G;
+    a.fo_stride = (long long)f->max_frames * G; a.fo_step_stride = G;
+    a.forced = f->forced_codes ? f->forced_codes + g : nullptr;
+    a.own = f->own_codes ? f->own_codes + g : nullptr;
+    a.done = done;
+    return launch_sample(&a, s);
+}
+
+static int frame(const q3t_frame_args* f, cudaStream_t s) {
+    const q3t_stack& c = f->cp;
+    const int B = f->B, G = f->n_groups, H = f->talker.hidden, Hc = c.hidden;
+    // code 0 from the talker logits
+    Q3T_TRY(sample_into(f, f->logits, f->talker_vocab, f->talker_sp, f->seen, 0, f->done, s));
+    // code predictor: position 0 = projected talker hidden, position 1 = projected embedding of code 0
+    Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, f->hidden, H, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->xc, Hc, s));
+    Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
+    for (int g = 0; g < G - 1; ++g) {
+        const float* table = g == 0 ? f->codec_embedding : f->cp_embeddings_host[g - 1];
+        Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, table, 0, nullptr, 0.f, f->cur_codes + g, G, H, 0, nullptr, 0, f->xc,
+                          Hc, s));
+        Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
+        float* lg = f->keep_cp_logits ? f->cp_logits + (size_t)g * B * f->cp_vocab : f->cp_logits;
+        Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
+                          nullptr, 0, lg, f->cp_vocab, s));
+        Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));
+    }
+    next_input_kernel<<<B, 256, 0, s>>>(f->codec_embedding, f->cp_embeddings_dev, f->cur_codes, G, H, f->trailing,
+                                        f->n_trailing, f->step, f->x, f->codes, f->max_frames);
+    Q3T_CHECK_LAUNCH("next_input");
+    return talker_step(f, 1, 1, s);
+}
+
+}  // namespace q3t
+
+extern "C" int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, void* stream) {
+    return q3t::launch_rmsnorm(x, w, y, M, H, eps, (cudaStream_t)stream);
+}
+extern "C" int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream) {
+    return q3t::talker_step(f, want_logits, 0, (cudaStream_t)stream);
+}
+extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) { return q3t::frame(f, (cudaStream_t)stream); }

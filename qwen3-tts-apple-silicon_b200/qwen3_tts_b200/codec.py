@@ -1,0 +1,218 @@
+"""Host side of the speech-tokenizer decoder (RVQ codes -> 24 kHz waveform) on B200.
+
+Weight re-layout for the tap-GEMM operator happens once at load; every arithmetic op is a kernel of
+libq3tts_b200.so (csrc/codec.cu).  Structure follows the cousin `Code2Wav` forward + `chunked_decode`
+(transformers qwen3_omni_moe/modeling_qwen3_omni_moe.py:3766-3790) with the Qwen3-TTS front end
+(split-RVQ decode, pre-conv, in/out projections).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+from .config import ModelConfig
+from .weights import WeightStore
+
+
+class _Tap:
+    """One tap-GEMM layer: W [taps, N, Cin] + bias + shifts."""
+
+    def __init__(self, W: torch.Tensor, bias: Optional[torch.Tensor], shifts: List[int], up: int, cout: int,
+                 rows_delta: int = 0):
+        self.W, self.bias, self.shifts, self.up, self.cout, self.rows_delta = W.contiguous(), bias, shifts, up, cout, rows_delta
+        self.taps, self.cin = W.shape[0], W.shape[2]
+
+
+class CodecDecoder:
+    def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda"):
+        self.lib = L.load()
+        self.cfg, self.k, self.dev = cfg, cfg.codec, torch.device(device)
+        k = self.k
+        w: Dict[str, torch.Tensor] = {n: t.to(self.dev, torch.float32) for n, t in ws.fp.items() if n.startswith("codec.")}
+        self.w = w
+
+        def conv(name: str, dilation: int = 1) -> _Tap:
+            W = w[name + ".weight"]                      # [Cout, Cin, k]
+            ks = W.shape[2]
+            return _Tap(W.permute(2, 0, 1), w[name + ".bias"], [-(ks - 1 - j) * dilation for j in range(ks)], 1, W.shape[0])
+
+        def tconv(name: str, stride: int) -> _Tap:
+            W = w[name + ".weight"]                      # [Cin, Cout, k]
+            cin, cout, ks = W.shape
+            t0 = W[:, :, :stride].permute(2, 1, 0).reshape(stride * cout, cin)
+            if ks == stride:
+                return _Tap(t0[None], w[name + ".bias"], [0], stride, cout)
+            assert ks == 2 * stride
+            t1 = W[:, :, stride:].permute(2, 1, 0).reshape(stride * cout, cin)
+            if k.transconv_trim == "both":               # out[q*s+p] = x[q+1] W[p] + x[q] W[p+s]   (cousin :3319-3331)
+                return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [1, 0], stride, cout, rows_delta=-1)
+            return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [0, -1], stride, cout)
+
+        def lin(W: torch.Tensor, bias: Optional[torch.Tensor] = None) -> _Tap:
+            return _Tap(W[None], bias, [0], 1, W.shape[0])
+
+        def snake(name: str):
+            return (torch.exp(w[name + ".alpha"]).contiguous(), (1.0 / (torch.exp(w[name + ".beta"]) + 1e-9)).contiguous())
+
+        # RVQ tables: embed_sum / clamp(usage, 1e-5)  (mimi:1191-1195), one per quantizer
+        self.tables = []
+        for grp, nq in (("semantic", k.num_semantic), ("acoustic", k.num_quantizers - k.num_semantic)):
+            for i in range(nq):
+                p = f"codec.rvq.{grp}.codebooks.{i}"
+                self.tables.append((w[p + ".embed_sum"] / w[p + ".cluster_usage"].clamp(min=1e-5)[:, None]).contiguous())
+        self._tab_ptrs = (L.vp * len(self.tables))(*[t.data_ptr() for t in self.tables])
+        self.rvq_sem = lin(w["codec.rvq.semantic.out_proj.weight"])
+        self.rvq_ac = lin(w["codec.rvq.acoustic.out_proj.weight"])
+        self.pre_conv = conv("codec.pre_conv")
+        self.tf_in = lin(w["codec.tf.in_proj.weight"], w["codec.tf.in_proj.bias"])
+        self.tf_layers = []
+        for i in range(k.tf_layers):
+            p = f"codec.tf.layers.{i}"
+            gu = torch.stack([w[p + ".gate_proj.weight"], w[p + ".up_proj.weight"]], 1).reshape(-1, k.tf_hidden)
+            self.tf_layers.append(dict(
+                n1=w[p + ".input_norm.weight"].contiguous(),
+                qkv=lin(torch.cat([w[p + ".q_proj.weight"], w[p + ".k_proj.weight"], w[p + ".v_proj.weight"]], 0)),
+                o=lin(w[p + ".o_proj.weight"]), s1=w[p + ".attn_scale"].contiguous(),
+                n2=w[p + ".post_norm.weight"].contiguous(), gu=lin(gu), down=lin(w[p + ".down_proj.weight"]),
+                s2=w[p + ".mlp_scale"].contiguous()))
+        self.tf_norm = w["codec.tf.norm.weight"].contiguous()
+        self.tf_out = lin(w["codec.tf.out_proj.weight"], w["codec.tf.out_proj.bias"])
+        self.tf_inv_freq = (1.0 / (k.tf_rope_theta ** (torch.arange(0, k.tf_head_dim, 2, dtype=torch.float32) /
+                                                      k.tf_head_dim))).to(self.dev)
+        self.ups = []
+        for i, r in enumerate(k.upsampling_ratios):
+            p = f"codec.up.{i}"
+            self.ups.append(dict(tconv=tconv(p + ".tconv", r), dw_w=w[p + ".cnx.dw.weight"].reshape(k.latent_dim, -1).contiguous(),
+                                 dw_b=w[p + ".cnx.dw.bias"], ln_w=w[p + ".cnx.ln.weight"], ln_b=w[p + ".cnx.ln.bias"],
+                                 pw1=lin(w[p + ".cnx.pw1.weight"], w[p + ".cnx.pw1.bias"]),
+                                 pw2=lin(w[p + ".cnx.pw2.weight"], w[p + ".cnx.pw2.bias"]), gamma=w[p + ".cnx.gamma"]))
+        self.conv_in = conv("codec.dec.conv_in")
+        self.blocks = []
+        for i, r in enumerate(k.upsample_rates):
+            p = f"codec.dec.blocks.{i}"
+            units = []
+            for j, d in enumerate((1, 3, 9)):
+                u = f"{p}.units.{j}"
+                units.append(dict(s1=snake(u + ".snake1"), c1=conv(u + ".conv1", d), s2=snake(u + ".snake2"),
+                                  c2=conv(u + ".conv2")))
+            self.blocks.append(dict(snake=snake(p + ".snake"), tconv=tconv(p + ".tconv", r), units=units))
+        self.snake_out = snake("codec.dec.snake_out")
+        self.conv_out = conv("codec.dec.conv_out")
+
+    # ---- operator wrappers ---------------------------------------------------------------------------------
+    def _tap(self, layer: _Tap, A: torch.Tensor, scale=None, resid=None, want_raw=True, act=L.ACT_NONE, act_ab=None):
+        """A [B, T, Cin] -> (raw [B, rows*up, Cout] or None, act or None)."""
+        B, T, Cin = A.shape
+        assert Cin == layer.cin and A.is_contiguous()
+        rows = T + layer.rows_delta
+        N = layer.up * layer.cout
+        a = L.TapGemmArgs()
+        a.A, a.B, a.T_in, a.Cin = A.data_ptr(), B, T, Cin
+        a.W, a.bias, a.taps = layer.W.data_ptr(), L.ptr(layer.bias), layer.taps
+        for i, s in enumerate(layer.shifts):
+            a.shift[i] = s
+        a.up, a.Cout, a.T_out_rows = layer.up, layer.cout, rows
+        a.scale, a.resid = L.ptr(scale), L.ptr(resid)
+        raw = torch.empty(B, rows * layer.up, layer.cout, device=self.dev, dtype=torch.float32) if want_raw else None
+        out_act = None
+        if act != L.ACT_NONE:
+            shape = (B, rows, N // 2) if act == L.ACT_SWIGLU_PAIR else (B, rows * layer.up, layer.cout)
+            out_act = torch.empty(*shape, device=self.dev, dtype=torch.float32)
+        a.out_raw, a.out_act, a.act = L.ptr(raw), L.ptr(out_act), act
+        if act_ab is not None:
+            a.act_a, a.act_b = act_ab[0].data_ptr(), act_ab[1].data_ptr()
+        L.check(self.lib.q3t_tapgemm(C.byref(a), L.stream_ptr()), "tapgemm")
+        return raw, out_act
+
+    def _rmsnorm(self, x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
+        y = torch.empty_like(x)
+        L.check(self.lib.q3t_rmsnorm(x.data_ptr(), w.data_ptr(), y.data_ptr(), x.numel() // x.shape[-1], x.shape[-1],
+                                     eps, L.stream_ptr()), "rmsnorm")
+        return y
+
+    def rvq_sums(self, codes: torch.Tensor):
+        """codes [B, G, T] int -> (semantic sum [B,T,dim], acoustic sum [B,T,dim]); bit-exact gather + fp32 adds."""
+        k = self.k
+        codes = codes.to(self.dev, torch.int32).contiguous()
+        B, G, T = codes.shape
+        outs = []
+        for lo, hi in ((0, k.num_semantic), (k.num_semantic, k.num_quantizers)):
+            o = torch.empty(B, T, k.codebook_dim, device=self.dev, dtype=torch.float32)
+            L.check(self.lib.q3t_rvq_gather_sum(codes.data_ptr(), self._tab_ptrs, B, G, T, lo, hi, k.codebook_dim,
+                                                k.codebook_size, o.data_ptr(), L.stream_ptr()), "rvq_gather_sum")
+            outs.append(o)
+        return outs
+
+    # ---- one vocoder call -----------------------------------------------------------------------------------
+    def forward(self, codes: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
+        """codes [B, 16, T] -> wav [B, out_len(T)] fp32 in [-1, 1]."""
+        k = self.k
+        sem, ac = self.rvq_sums(codes)
+        y, _ = self._tap(self.rvq_sem, sem)
+        x, _ = self._tap(self.rvq_ac, ac, resid=y)                        # [B, T, 512]
+        x, _ = self._tap(self.pre_conv, x)                                # [B, T, 1024]
+        if stages is not None:
+            stages["pre_conv"] = x
+        h, _ = self._tap(self.tf_in, x)
+        B, T, _ = h.shape
+        for ly in self.tf_layers:
+            n = self._rmsnorm(h, ly["n1"], k.tf_rms_eps)
+            qkv, _ = self._tap(ly["qkv"], n)
+            a = torch.empty(B, T, k.tf_heads * k.tf_head_dim, device=self.dev, dtype=torch.float32)
+            L.check(self.lib.q3t_window_attn(qkv.data_ptr(), self.tf_inv_freq.data_ptr(), B, T, k.tf_heads, k.tf_head_dim,
+                                             k.sliding_window, a.data_ptr(), L.stream_ptr()), "window_attn")
+            h, _ = self._tap(ly["o"], a, scale=ly["s1"], resid=h)
+            n = self._rmsnorm(h, ly["n2"], k.tf_rms_eps)
+            _, g = self._tap(ly["gu"], n, want_raw=False, act=L.ACT_SWIGLU_PAIR)
+            h, _ = self._tap(ly["down"], g, scale=ly["s2"], resid=h)
+        h = self._rmsnorm(h, self.tf_norm, k.tf_rms_eps)
+        x, _ = self._tap(self.tf_out, h)                                  # [B, T, 1024]
+        if stages is not None:
+            stages["transformer"] = x
+        for up in self.ups:
+            x, _ = self._tap(up["tconv"], x)
+            Bn, Tn, Cn = x.shape
+            n = torch.empty_like(x)
+            L.check(self.lib.q3t_dwconv_ln(x.data_ptr(), up["dw_w"].data_ptr(), up["dw_b"].data_ptr(), up["ln_w"].data_ptr(),
+                                           up["ln_b"].data_ptr(), 1e-6, Bn, Tn, Cn, up["dw_w"].shape[1], n.data_ptr(),
+                                           L.stream_ptr()), "dwconv_ln")
+            _, g = self._tap(up["pw1"], n, want_raw=False, act=L.ACT_GELU)
+            x, _ = self._tap(up["pw2"], g, scale=up["gamma"], resid=x)
+        if stages is not None:
+            stages["upsample"] = x
+        # vocoder: every conv writes the SnakeBeta of its consumer in its epilogue
+        _, act = self._tap(self.conv_in, x, want_raw=False, act=L.ACT_SNAKE, act_ab=self.blocks[0]["snake"])
+        for bi, blk in enumerate(self.blocks):
+            u, act = self._tap(blk["tconv"], act, act=L.ACT_SNAKE, act_ab=blk["units"][0]["s1"])
+            for ui, unit in enumerate(blk["units"]):
+                _, a2 = self._tap(unit["c1"], act, want_raw=False, act=L.ACT_SNAKE, act_ab=unit["s2"])
+                if ui + 1 < len(blk["units"]):
+                    nxt = blk["units"][ui + 1]["s1"]
+                elif bi + 1 < len(self.blocks):
+                    nxt = self.blocks[bi + 1]["snake"]
+                else:
+                    nxt = self.snake_out
+                want_raw = ui + 1 < len(blk["units"]) or stages is not None
+                u2, act = self._tap(unit["c2"], a2, resid=u, want_raw=True, act=L.ACT_SNAKE, act_ab=nxt)
+                u = u2
+            if stages is not None:
+                stages[f"block{bi}"] = u
+        wav, _ = self._tap(self.conv_out, act)                              # [B, n, 1]
+        out = torch.empty(wav.shape[0], wav.shape[1], device=self.dev, dtype=torch.float32)
+        L.check(self.lib.q3t_clamp_pcm16(wav.data_ptr(), wav.numel(), out.data_ptr(), 0, L.stream_ptr()), "clamp")
+        return out
+
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """Chunked decode (300-frame chunks, 25 frames of left context; cousin :3780-3790). codes [B,16,T] -> [B, n]."""
+        k = self.k
+        wavs, start, T = [], 0, codes.shape[-1]
+        while start < T:
+            end = min(start + k.chunk_size, T)
+            ctx = k.left_context if start - k.left_context > 0 else start
+            wav = self.forward(codes[..., start - ctx:end])
+            wavs.append(wav[:, ctx * k.hop:])
+            start = end
+        return torch.cat(wavs, -1)

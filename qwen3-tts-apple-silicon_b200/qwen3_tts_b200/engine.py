@@ -1,0 +1,300 @@
+"""Host side of the B200 generation engine: owns device memory (weights, paged KV, state), builds the
+C-ABI argument blocks once, captures the talker step and the whole frame into CUDA graphs and replays
+them.  PyTorch is plumbing here (allocations, streams, graphs); every arithmetic kernel lives in
+libq3tts_b200.so.
+
+Mirrors what `mlx_audio`'s Qwen3-TTS `Model` does between `load_model` and the end of `generate`
+(reference call sites: src/qwen3_tts/io.py:111-112, sessions/custom.py:163-170).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import lib as L
+from .config import ModelConfig
+from .weights import WeightStore, pack_w8, quantize_w8
+
+
+def _rope_inv_freq(head_dim: int, theta: float, device) -> torch.Tensor:
+    # identical expression to the oracle (fp32 pow on the host)
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    return inv.to(device)
+
+
+class _Keep:
+    """Keeps every tensor referenced by a ctypes struct alive."""
+
+    def __init__(self):
+        self.t: List[torch.Tensor] = []
+
+    def __call__(self, t: torch.Tensor) -> int:
+        assert t.is_cuda and t.is_contiguous()
+        self.t.append(t)
+        return t.data_ptr()
+
+
+class TalkerEngine:
+    """Talker + code predictor on one GPU for a fixed batch of `B` lock-step sequences."""
+
+    def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", batch: int = 1, max_frames: int = 512,
+                 max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1):
+        self.lib = L.load()
+        self.cfg, self.dev, self.B = cfg, torch.device(device), batch
+        self.max_frames, self.max_ctx, self.max_trailing = max_frames, max_ctx, max_trailing
+        self.keep = _Keep()
+        t, c = cfg.talker, cfg.cp
+        self.G = c.num_code_groups
+        dev = self.dev
+        f32 = dict(device=dev, dtype=torch.float32)
+        i32 = dict(device=dev, dtype=torch.int32)
+
+        # ---- weights -------------------------------------------------------------------------
+        self.w_bytes = 0
+
+        def fp(name):
+            return ws.fp[name].to(dev, torch.float32).contiguous()
+
+        def w8(names: Sequence[str], bias_name: Optional[str] = None) -> L.W8:
+            trips = [ws.q[n] for n in names]
+            q = torch.cat([x[0] for x in trips], 0).to(dev)
+            s = torch.cat([x[1] for x in trips], 0).to(dev)
+            b = torch.cat([x[2] for x in trips], 0).to(dev)
+            blob = pack_w8(q, s, b)
+            self.w_bytes += blob.numel()
+            o = L.W8()
+            o.w, o.N, o.K = self.keep(blob), q.shape[0], q.shape[1]
+            o.lin_bias = self.keep(fp(bias_name)) if bias_name else 0
+            return o
+
+        def stack(prefix: str, sc, n_pages: int, pages_per_seq: int, nsplit: int) -> Tuple[L.Stack, object]:
+            layers = (L.Layer * sc.num_layers)()
+            for i in range(sc.num_layers):
+                p = f"{prefix}.layers.{i}"
+                ly = layers[i]
+                ly.input_norm = self.keep(fp(p + ".input_norm.weight"))
+                ly.qkv = w8([p + ".q_proj", p + ".k_proj", p + ".v_proj"])
+                ly.q_norm = self.keep(fp(p + ".q_norm.weight"))
+                ly.k_norm = self.keep(fp(p + ".k_norm.weight"))
+                ly.o = w8([p + ".o_proj"])
+                ly.post_norm = self.keep(fp(p + ".post_norm.weight"))
+                ly.gate_up = w8([p + ".gate_proj", p + ".up_proj"])
+                ly.down = w8([p + ".down_proj"])
+            st = L.Stack()
+            st.hidden, st.n_layers, st.n_heads, st.n_kv_heads = sc.hidden_size, sc.num_layers, sc.num_heads, sc.num_kv_heads
+            st.head_dim, st.inter, st.eps = sc.head_dim, sc.intermediate_size, sc.rms_norm_eps
+            st.layers_host = C.cast(layers, C.POINTER(L.Layer))
+            st.final_norm = self.keep(fp(prefix + ".norm.weight"))
+            st.inv_freq = self.keep(_rope_inv_freq(sc.head_dim, sc.rope_theta, dev))
+            layer_elems = n_pages * 2 * sc.num_kv_heads * L.KV_PAGE * sc.head_dim
+            pool = torch.zeros(sc.num_layers * layer_elems, device=dev, dtype=torch.bfloat16)
+            st.kv_pool = self.keep(pool)
+            st.kv_layer_stride_bytes = layer_elems * 2
+            tbl = torch.arange(self.B * pages_per_seq, **i32).reshape(self.B, pages_per_seq).contiguous()
+            st.block_tbl, st.max_pages, st.attn_nsplit = self.keep(tbl), pages_per_seq, nsplit
+            return st, layers
+
+        pps = (max_ctx + L.KV_PAGE - 1) // L.KV_PAGE
+        self.talker_stack, self._tl = stack("talker", t, self.B * pps, pps, attn_nsplit)
+        cp_pps = (self.G + 1 + L.KV_PAGE - 1) // L.KV_PAGE
+        self.cp_stack, self._cl = stack("cp", c, self.B * cp_pps, cp_pps, 1)
+
+        fa = L.FrameArgs()
+        self.fa = fa
+        fa.B = self.B
+        fa.talker, fa.cp = self.talker_stack, self.cp_stack
+        fa.codec_head = w8(["talker.codec_head"])
+        fa.talker_vocab = t.vocab_size
+        self.codec_embedding = fp("talker.codec_embedding")
+        fa.codec_embedding = self.keep(self.codec_embedding)
+        fa.cp_proj = w8(["cp.proj"], "cp.proj.bias")
+        self.cp_embeddings = [fp(f"cp.embeddings.{g}") for g in range(self.G - 1)]
+        self._cp_emb_host = (L.vp * (self.G - 1))(*[self.keep(e) for e in self.cp_embeddings])
+        fa.cp_embeddings_host = C.cast(self._cp_emb_host, C.POINTER(L.vp))
+        self._cp_emb_dev = torch.tensor([e.data_ptr() for e in self.cp_embeddings], device=dev, dtype=torch.int64)
+        fa.cp_embeddings_dev = self.keep(self._cp_emb_dev)
+        self._cp_heads = (L.W8 * (self.G - 1))(*[w8([f"cp.heads.{g}"]) for g in range(self.G - 1)])
+        fa.cp_heads_host = C.cast(self._cp_heads, C.POINTER(L.W8))
+        fa.cp_vocab, fa.n_groups = c.vocab_size, self.G
+        # text side (prefill only)
+        self.text_embedding = fp("talker.text_embedding")
+        self.tp_fc1 = w8(["talker.text_projection.fc1"], "talker.text_projection.fc1.bias")
+        self.tp_fc2 = w8(["talker.text_projection.fc2"], "talker.text_projection.fc2.bias")
+
+        # ---- state -------------------------------------------------------------------------------
+        B, H, Hc, V, Vc, G = self.B, t.hidden_size, c.hidden_size, t.vocab_size, c.vocab_size, self.G
+        self.x = torch.zeros(B, H, **f32)
+        self.hidden = torch.zeros(B, H, **f32)
+        self.logits = torch.zeros(B, V, **f32)
+        self.cp_logits = torch.zeros((G - 1) if keep_cp_logits else 1, B, Vc, **f32)
+        self.xc = torch.zeros(B, Hc, **f32)
+        qkvd = max(t.q_dim + 2 * t.kv_dim, c.q_dim + 2 * c.kv_dim)
+        self.qkv = torch.zeros(B, qkvd, **f32)
+        self.attn = torch.zeros(B, max(t.q_dim, c.q_dim), **f32)
+        self.gu = torch.zeros(B, 2 * max(t.intermediate_size, c.intermediate_size), **f32)
+        rep = max(t.num_heads // t.num_kv_heads, c.num_heads // c.num_kv_heads)
+        self.attn_work = torch.zeros(B * max(t.num_kv_heads, c.num_kv_heads) * max(attn_nsplit, 1) * rep *
+                                     (max(t.head_dim, c.head_dim) + 2), **f32)
+        self.attn_counters = torch.zeros(B * max(t.num_kv_heads, c.num_kv_heads), **i32)
+        self.pos = torch.zeros(B, **i32)
+        self.cp_pos = torch.arange(G + 1, **i32).repeat_interleave(B).contiguous()
+        self.step = torch.zeros(1, **i32)
+        self.cur_codes = torch.zeros(B, G, **i32)
+        self.codes = torch.zeros(B, max_frames, G, **i32)
+        self.own_codes = torch.zeros(B, max_frames, G, **i32)
+        self.forced = torch.zeros(B, max_frames, G, **i32)
+        self.seen = torch.zeros(B, (V + 31) // 32, device=dev, dtype=torch.int32)
+        self.done = torch.zeros(B, **i32)
+        self.trailing = torch.zeros(B, max_trailing, H, **f32)
+        fa.x, fa.hidden, fa.logits, fa.cp_logits = map(self.keep, (self.x, self.hidden, self.logits, self.cp_logits))
+        fa.keep_cp_logits = int(keep_cp_logits)
+        fa.xc, fa.qkv, fa.attn, fa.gu = map(self.keep, (self.xc, self.qkv, self.attn, self.gu))
+        fa.attn_work, fa.attn_counters = self.keep(self.attn_work), self.keep(self.attn_counters)
+        fa.pos, fa.cp_pos, fa.step = self.keep(self.pos), self.keep(self.cp_pos), self.keep(self.step)
+        fa.cur_codes, fa.codes, fa.own_codes = self.keep(self.cur_codes), self.keep(self.codes), self.keep(self.own_codes)
+        fa.max_frames = max_frames
+        fa.seen, fa.done = self.keep(self.seen), self.keep(self.done)
+        fa.trailing, fa.n_trailing = self.keep(self.trailing), max_trailing
+        fa.forced_codes = 0
+        self.set_sampling()
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+        self.use_graphs = True
+        self.launches_per_frame = None
+
+    # ---- configuration ---------------------------------------------------------------------------
+    def set_sampling(self, do_sample: bool = False, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
+                     repetition_penalty: float = 1.05, min_new_tokens: int = 2, seed: int = 0,
+                     cp_do_sample: Optional[bool] = None, cp_temperature: float = 0.9, cp_top_k: int = 50,
+                     cp_top_p: float = 1.0):
+        """Greedy parity definition: argmax after the suppress mask, penalty 1.0, no
+        min_new_tokens.  Sampling defaults follow SURVEY App. A."""
+        t = self.cfg.talker
+        sp = self.fa.talker_sp
+        sp.do_sample = int(do_sample)
+        sp.temperature, sp.top_k, sp.top_p = temperature, top_k, top_p
+        sp.repetition_penalty = repetition_penalty if do_sample else 1.0
+        sp.min_new_tokens = min_new_tokens if do_sample else 0
+        sp.suppress_lo, sp.suppress_hi, sp.eos_id = t.vocab_size - 1024, t.vocab_size, t.codec_eos_id
+        sp.seed = seed
+        cs = self.fa.cp_sp
+        cs.do_sample = int(do_sample if cp_do_sample is None else cp_do_sample)
+        cs.temperature, cs.top_k, cs.top_p, cs.repetition_penalty = cp_temperature, cp_top_k, cp_top_p, 1.0
+        cs.min_new_tokens, cs.suppress_lo, cs.suppress_hi, cs.eos_id, cs.seed = 0, -1, -1, -1, seed + 1
+        self._graphs = {}
+
+    def set_forced(self, forced: Optional[torch.Tensor]):
+        """Teacher forcing for parity tests: forced [B, T, G] int."""
+        if forced is None:
+            self.fa.forced_codes = 0
+        else:
+            T = forced.shape[1]
+            self.forced.zero_()
+            self.forced[:, :T] = forced.to(self.dev, torch.int32)
+            self.fa.forced_codes = self.forced.data_ptr()
+        self._graphs = {}
+
+    # ---- embeddings for the prefill (W8 GEMVs, two rows per launch) ------------------------------------
+    def text_embed(self, ids: torch.Tensor) -> torch.Tensor:
+        """P(ids) = fc2(silu(fc1(text_embedding[ids]))) -> [n, H] on device."""
+        ids = ids.to(self.dev).long().reshape(-1)
+        e = self.text_embedding[ids].contiguous()
+        n, Ht = e.shape
+        h = torch.empty(n, Ht, device=self.dev, dtype=torch.float32)
+        o = torch.empty(n, self.cfg.talker.hidden_size, device=self.dev, dtype=torch.float32)
+        self._gemv_rows(self.tp_fc1, e, h, act=L.ACT_SILU)
+        self._gemv_rows(self.tp_fc2, h, o)
+        return o
+
+    def _gemv_rows(self, w: L.W8, x: torch.Tensor, y: torch.Tensor, act: int = 0, prologue: int = 0,
+                   norm_w: Optional[torch.Tensor] = None, eps: float = 0.0, resid: Optional[torch.Tensor] = None):
+        n = x.shape[0]
+        s = L.stream_ptr()
+        for r in range(0, n, 2):
+            a = L.GemvArgs()
+            a.w, a.M, a.prologue = w, min(2, n - r), prologue
+            a.x, a.x_stride = x[r:].data_ptr(), x.stride(0)
+            a.norm_w, a.eps = L.ptr(norm_w), eps
+            a.act = act
+            if resid is not None:
+                a.resid, a.resid_stride = resid[r:].data_ptr(), resid.stride(0)
+            a.y, a.y_stride = y[r:].data_ptr(), y.stride(0)
+            L.check(self.lib.q3t_w8_gemv(C.byref(a), s), "w8_gemv")
+
+    # ---- generation --------------------------------------------------------------------------------
+    def reset(self):
+        for t in (self.pos, self.step, self.seen, self.done, self.codes, self.own_codes, self.attn_counters):
+            t.zero_()
+
+    def _talker_step(self, want_logits: bool):
+        L.check(self.lib.q3t_talker_step(C.byref(self.fa), int(want_logits), L.stream_ptr()), "talker_step")
+
+    def _frame(self):
+        L.check(self.lib.q3t_frame(C.byref(self.fa), L.stream_ptr()), "frame")
+
+    def _ensure_graphs(self):
+        """Capture the talker step (with / without logits) and the whole frame once.  The warm-up run
+        mutates state, so this is only called right before a reset()."""
+        if self._graphs or not self.use_graphs:
+            return
+        fns = {"step": lambda: self._talker_step(False), "step_logits": lambda: self._talker_step(True),
+               "frame": self._frame}
+        for fn in fns.values():          # warm-up outside capture (lazy module load, func attributes)
+            fn()
+        torch.cuda.synchronize()
+        self.reset()
+        for key, fn in fns.items():
+            n0 = self.lib.q3t_launch_count()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = g
+            if key == "frame":
+                self.launches_per_frame = int(self.lib.q3t_launch_count() - n0)
+        torch.cuda.synchronize()
+
+    def _run(self, key: str):
+        if self.use_graphs:
+            self._graphs[key].replay()
+        elif key == "frame":
+            self._frame()
+        else:
+            self._talker_step(key == "step_logits")
+
+    def prefill(self, embeds: torch.Tensor, lengths: Optional[Sequence[int]] = None,
+                trailing: Optional[torch.Tensor] = None):
+        """embeds [B, Lmax, H] (RIGHT-aligned when lengths differ); trailing [B, n_tr, H] whose last row is the
+        tts_pad embedding (rows past n_tr repeat it).  v1 prefill feeds one token per talker step."""
+        B, Lmax, H = embeds.shape
+        assert B == self.B
+        embeds = embeds.to(self.dev, torch.float32)
+        lengths = list(lengths) if lengths is not None else [Lmax] * B
+        assert max(lengths) == Lmax and Lmax + self.max_frames <= self.max_ctx
+        self._ensure_graphs()
+        self.reset()
+        if trailing is None:
+            trailing = torch.zeros(B, 1, H)
+        n_tr = trailing.shape[1]
+        assert n_tr <= self.max_trailing, "raise max_trailing for streaming text"
+        tr = trailing.to(self.dev, torch.float32)
+        self.trailing[:, :n_tr] = tr
+        self.trailing[:, n_tr:] = tr[:, -1:]
+        off = torch.tensor([Lmax - l for l in lengths], device=self.dev, dtype=torch.int32)
+        for tkn in range(Lmax):
+            self.pos.copy_((tkn - off).clamp_(min=0))
+            self.x.copy_(embeds[:, tkn])
+            self._run("step_logits" if tkn == Lmax - 1 else "step")
+        self.pos.copy_(torch.tensor(lengths, device=self.dev, dtype=torch.int32))
+
+    def generate(self, n_frames: int, check_every: int = 16) -> torch.Tensor:
+        """Runs up to n_frames frames (stops early once every sequence sampled EOS). Returns codes [B, T, G]."""
+        assert n_frames <= self.max_frames
+        for f in range(n_frames):
+            self._run("frame")
+            if check_every and (f + 1) % check_every == 0 and f + 1 < n_frames:
+                if bool(self.done.all().item()):
+                    n_frames = f + 1
+                    break
+        return self.codes[:, :n_frames]

@@ -1,0 +1,239 @@
+"""`Model` = the object `load_model(path)` returns and `generate_audio(model=...)` drives.
+
+Keeps the reference's surface: `load_model(path).generate(text, voice / instruct / ref_audio, ...)` yields
+result objects carrying `audio`, `sample_rate`, ... (SURVEY.md 8b "Output contract"); the three session
+kinds of the reference map to `tts_model_type`:
+    custom_voice  sessions/custom.py:163-170   generate(text, voice=<speaker>, instruct=<emotion>, speed=)
+    voice_design  sessions/design.py:76-81     generate(text, instruct=<voice description>)
+    base          sessions/clone.py:218-224    generate(text, ref_audio=<wav path>, ref_text=)
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import time
+import wave
+from dataclasses import dataclass
+from typing import Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import config as cfgmod
+from .codec import CodecDecoder
+from .config import ModelConfig
+from .engine import TalkerEngine
+from .weights import WeightStore, make_weights
+
+
+@dataclass
+class GenerationResult:
+    audio: np.ndarray               # float32 mono in [-1, 1]
+    sample_rate: int
+    samples: int
+    segment_idx: int
+    token_count: int                # frames generated (12.5 Hz)
+    audio_duration: float
+    processing_time_seconds: float
+    real_time_factor: float         # audio seconds / wall seconds (RTFx)
+    codes: Optional[np.ndarray] = None
+
+
+class ByteTokenizer:
+    """Stand-in text front end: the Qwen2 BPE vocabulary files are not available offline, so text
+    is mapped byte-wise into the text vocabulary.  A real `tokenizer.json` in the model directory replaces it."""
+
+    def __init__(self, cfg: ModelConfig):
+        self.cfg = cfg
+
+    def encode(self, text: str) -> List[int]:
+        v = self.cfg.talker.text_vocab_size
+        return [(b * 2654435761 + 17) % max(v - 16, 1) for b in text.encode("utf-8")]
+
+
+def _load_tokenizer(path: Optional[str], cfg: ModelConfig):
+    if path:
+        tj = os.path.join(path, "tokenizer.json")
+        if os.path.exists(tj):
+            from tokenizers import Tokenizer
+            tok = Tokenizer.from_file(tj)
+
+            class _T:
+                def encode(self, text):
+                    return tok.encode(text, add_special_tokens=False).ids
+            return _T()
+    return ByteTokenizer(cfg)
+
+
+class Model:
+    def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", model_path: Optional[str] = None,
+                 max_frames: int = 2048, max_ctx: int = 4096, batch: int = 1, max_trailing: int = 1024):
+        if not torch.cuda.is_available():
+            raise RuntimeError("qwen3_tts_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.sample_rate = cfg.codec.sample_rate
+        self.device = device
+        self.engine = TalkerEngine(cfg, ws, device, batch=batch, max_frames=max_frames, max_ctx=max_ctx,
+                                   max_trailing=max_trailing)
+        self.codec = CodecDecoder(cfg, ws, device)
+        self.tokenizer = _load_tokenizer(model_path, cfg)
+
+    # ---- prompt assembly (mirrors oracle.OracleModel.build_prefill) -------------------------
+    def chat_ids(self, text: str) -> List[int]:
+        """<|im_start|>assistant\\n{text}<|im_end|>\\n<|im_start|>assistant\\n  ->  ids[:3] prefix, ids[-5:] tail."""
+        c = self.cfg
+        nl = self.tokenizer.encode("\n")[:1] or [10]
+        return [c.im_start_id, c.assistant_id, nl[0]] + list(self.tokenizer.encode(text)) + \
+               [c.im_end_id, nl[0], c.im_start_id, c.assistant_id, nl[0]]
+
+    def instruct_ids(self, instruct: str) -> List[int]:
+        c = self.cfg
+        nl = self.tokenizer.encode("\n")[:1] or [10]
+        user = self.tokenizer.encode("user")[:1] or [11]
+        return [c.im_start_id, user[0], nl[0]] + list(self.tokenizer.encode(instruct)) + [c.im_end_id, nl[0]]
+
+    def build_prefill(self, text_ids: Sequence[int], instruct_ids: Optional[Sequence[int]] = None,
+                      speaker: Optional[str] = None, language: Optional[str] = None,
+                      speaker_vec: Optional[torch.Tensor] = None, streaming: bool = False):
+        e, t, cfg = self.engine, self.cfg.talker, self.cfg
+        dev = e.dev
+        ids = torch.as_tensor(list(text_ids), dtype=torch.long, device=dev)
+        special = e.text_embed(torch.tensor([cfg.tts_pad_token_id, cfg.tts_bos_token_id, cfg.tts_eos_token_id]))
+        pad, bos, eos = special[0], special[1], special[2]
+        cemb = lambda lst: e.codec_embedding[torch.as_tensor(lst, dtype=torch.long, device=dev)]
+        if language is not None and language.lower() in t.codec_language_id:
+            prefix = [t.codec_think_id, t.codec_think_bos_id, t.codec_language_id[language.lower()], t.codec_think_eos_id]
+        else:
+            prefix = [t.codec_nothink_id, t.codec_think_bos_id, t.codec_think_eos_id]
+        parts = [cemb(prefix)]
+        if speaker_vec is not None:
+            parts.append(speaker_vec.to(dev, torch.float32).view(1, -1))
+        elif speaker is not None:
+            parts.append(cemb([t.spk_id[speaker.lower()]]))
+        parts.append(cemb([t.codec_pad_id, t.codec_bos_id]))
+        codec_seq = torch.cat(parts, 0)
+        n = codec_seq.shape[0]
+        # one batched projection of every text-side id used below
+        body_ids = ids[3:-5]
+        segs = []
+        if instruct_ids is not None and len(instruct_ids):
+            segs.append(e.text_embed(torch.as_tensor(list(instruct_ids), dtype=torch.long)))
+        head = e.text_embed(ids[:3])
+        mid = torch.cat([pad.expand(n - 2, -1), bos[None]], 0) + codec_seq[:-1]
+        segs += [head, mid]
+        body_e = e.text_embed(body_ids) if len(body_ids) else torch.zeros(0, t.hidden_size, device=dev)
+        if not streaming:
+            body = torch.cat([body_e, eos[None]], 0) + cemb([t.codec_pad_id] * (len(body_ids) + 1))
+            tail = pad[None] + cemb([t.codec_bos_id])
+            segs += [body, tail]
+            trailing = pad[None]
+        else:
+            segs.append(body_e[:1] + codec_seq[-1:])
+            trailing = torch.cat([body_e[1:], eos[None], pad[None]], 0)
+        return torch.cat(segs, 0), trailing
+
+    # ---- low-level: ids -> codes -> wav -----------------------------------------------------------------------
+    def generate_codes(self, prefill: torch.Tensor, trailing: torch.Tensor, max_frames: int) -> torch.Tensor:
+        """prefill [L, H], trailing [n, H] -> codes [T, 16] (int32, trimmed at EOS)."""
+        e = self.engine
+        e.prefill(prefill[None], None, trailing[None])
+        codes = e.generate(max_frames)[0]
+        eos = (codes[:, 0] == self.cfg.talker.codec_eos_id).nonzero()
+        if eos.numel():
+            codes = codes[: int(eos[0, 0])]
+        return codes
+
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """codes [T, 16] -> wav [n] on device."""
+        if codes.shape[0] == 0:
+            return torch.zeros(0, device=self.engine.dev)
+        return self.codec.decode(codes.t()[None].contiguous())[0]
+
+    # ---- the reference-facing surface ------------------------------------------------------------------------------
+    def generate(self, text: str, voice: Optional[str] = None, instruct: Optional[str] = None, speed: float = 1.0,
+                 lang_code: str = "auto", ref_audio: Optional[str] = None, ref_text: Optional[str] = None,
+                 temperature: Optional[float] = None, top_k: int = 50, top_p: float = 1.0,
+                 repetition_penalty: float = 1.05, max_tokens: int = 1200, seed: int = 0, verbose: bool = False,
+                 **kwargs) -> Iterator[GenerationResult]:
+        """One utterance -> one result (the reference consumes only audio_000.wav, io.py:156).
+        `speed` is accepted and ignored exactly like an unknown library kwarg; `temperature=0`
+        or `None` with greedy=True selects the greedy parity path."""
+        t0 = time.perf_counter()
+        mode = self.cfg.tts_model_type
+        greedy = kwargs.pop("greedy", False) or (temperature is not None and temperature <= 0)
+        self.engine.set_sampling(do_sample=not greedy, temperature=temperature or 0.9, top_k=top_k, top_p=top_p,
+                                 repetition_penalty=repetition_penalty, seed=seed)
+        language = None if lang_code in (None, "auto") else lang_code
+        speaker, speaker_vec, streaming, ref_codes = None, None, False, None
+        ins = self.instruct_ids(instruct) if instruct else None
+        if mode == "custom_voice":
+            if voice is not None and voice.lower() not in self.cfg.talker.spk_id:
+                raise ValueError(f"unknown speaker '{voice}'")
+            speaker = voice
+        elif mode == "base" and ref_audio is not None:
+            ref_codes, speaker_vec = self._reference_prompt(ref_audio)
+            streaming = True
+        ids = self.chat_ids(text)
+        prefill, trailing = self.build_prefill(ids, ins, speaker, language, speaker_vec, streaming)
+        max_frames = min(max_tokens, self.engine.max_frames)
+        codes = self.generate_codes(prefill, trailing, max_frames)
+        wav = self.decode(codes)
+        audio = wav.float().cpu().numpy()
+        dt = time.perf_counter() - t0
+        dur = audio.shape[0] / self.sample_rate
+        yield GenerationResult(audio=audio, sample_rate=self.sample_rate, samples=int(audio.shape[0]), segment_idx=0,
+                               token_count=int(codes.shape[0]), audio_duration=dur, processing_time_seconds=dt,
+                               real_time_factor=(dur / dt if dt > 0 else 0.0), codes=codes.cpu().numpy())
+
+    def _reference_prompt(self, ref_audio: str):
+        """Voice-cloning prompt.  The speech-tokenizer ENCODER and the ECAPA speaker encoder are 'next' rows
+        (SURVEY 8f-2/3); until they exist the reference clip is reduced to a deterministic synthetic code
+        prompt + speaker vector derived from the file contents (BASELINE.json config 3 does the same)."""
+        with open(ref_audio, "rb") as f:
+            digest = hashlib.sha256(f.read()).digest()
+        g = torch.Generator().manual_seed(int.from_bytes(digest[:8], "little") & 0x7fffffff)
+        n_ref = 38
+        codes = torch.randint(0, self.cfg.codec.codebook_size, (n_ref, self.cfg.cp.num_code_groups), generator=g)
+        vec = torch.randn(self.cfg.talker.hidden_size, generator=g) * 0.02
+        return codes, vec
+
+
+def write_wav(path: str, audio: np.ndarray, sample_rate: int) -> None:
+    """Mono PCM16 WAV (what `save_audio_file` moves out of the temp dir, reference io.py:156-160)."""
+    pcm = np.clip(np.asarray(audio, dtype=np.float32), -1.0, 1.0)
+    pcm = np.round(pcm * 32767.0).astype("<i2")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(sample_rate)
+        w.writeframes(pcm.tobytes())
+
+
+_MODE_BY_FOLDER = {"customvoice": "custom_voice", "voicedesign": "voice_design", "base": "base"}
+
+
+def load_model(model_path: str, device: str = "cuda", **kw) -> Model:
+    """Drop-in for `mlx_audio.tts.utils.load_model(model_path)` (reference io.py:111-112).
+
+    Reads `<model_path>/config.json` when present.  Real `mlx-community/*-8bit` safetensors are a 'next' row
+    (SURVEY 8f-1): a directory holding `model.safetensors` raises ValueError (which the reference reports as
+    "Failed to load model", io.py:115-117); a directory without weights gets seeded random-init weights of the
+    architecture its config/folder names (the offline parity/benchmark set-up)."""
+    if not os.path.isdir(model_path):
+        raise OSError(f"model directory not found: {model_path}")
+    if os.path.exists(os.path.join(model_path, "model.safetensors")) or \
+            os.path.exists(os.path.join(model_path, "model.safetensors.index.json")):
+        raise ValueError("loading MLX-quantised safetensors is not implemented yet in the B200 backend")
+    cj = os.path.join(model_path, "config.json")
+    meta = {}
+    if os.path.exists(cj):
+        with open(cj) as f:
+            meta = json.load(f)
+    folder = os.path.basename(os.path.normpath(model_path)).lower().replace("-", "")
+    mode = meta.get("tts_model_type") or next((v for k, v in _MODE_BY_FOLDER.items() if k in folder), "custom_voice")
+    size = meta.get("b200_size", "full")
+    cfg = ModelConfig.from_dict(meta["b200_config"]) if "b200_config" in meta else getattr(cfgmod, size)(mode)
+    cfg.tts_model_type = mode
+    ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False)
+    return Model(cfg, ws, device, model_path=model_path, **kw)
