@@ -399,6 +399,30 @@ def codec_transformer(w, cfg, x):
     return rms_norm(x, w["codec.tf.norm.weight"], k.tf_rms_eps)
 
 
+def convnext_block(w, p: str, x: torch.Tensor) -> torch.Tensor:
+    """qwen3_omni_moe:3334-3366.  x [B, C, T]."""
+    y = causal_conv1d(x, w[p + ".dw.weight"], w[p + ".dw.bias"], groups=x.shape[1])
+    y = F.layer_norm(y.transpose(1, 2), (x.shape[1],), w[p + ".ln.weight"], w[p + ".ln.bias"], 1e-6)
+    y = F.gelu(y @ w[p + ".pw1.weight"].T + w[p + ".pw1.bias"])      # exact-erf GELU (:3345)
+    y = y @ w[p + ".pw2.weight"].T + w[p + ".pw2.bias"]
+    return x + (w[p + ".gamma"] * y).transpose(1, 2)
+
+
+def decoder_block(w, cfg, p: str, x: torch.Tensor, rate: int) -> torch.Tensor:
+    """qwen3_omni_moe:3686-3727: SnakeBeta -> transposed conv (k = 2r, stride r) -> 3 dilated residual units."""
+    k = cfg.codec
+    x = snake_beta(x, w[p + ".snake.alpha"], w[p + ".snake.beta"])
+    x = causal_tconv1d(x, w[p + ".tconv.weight"], w[p + ".tconv.bias"], rate, k.transconv_trim)
+    for j, d in enumerate((1, 3, 9)):
+        u = f"{p}.units.{j}"
+        y = snake_beta(x, w[u + ".snake1.alpha"], w[u + ".snake1.beta"])
+        y = causal_conv1d(y, w[u + ".conv1.weight"], w[u + ".conv1.bias"], dilation=d)
+        y = snake_beta(y, w[u + ".snake2.alpha"], w[u + ".snake2.beta"])
+        y = causal_conv1d(y, w[u + ".conv2.weight"], w[u + ".conv2.bias"])
+        x = x + y
+    return x
+
+
 def codec_forward(w, cfg, codes: torch.Tensor, stages: Optional[dict] = None) -> torch.Tensor:
     """One vocoder call: codes [B, 16, T] -> wav [B, 1, out_len(T)] (qwen3_omni_moe:3766-3778 with the
     Qwen3-TTS front end: split-RVQ decode -> causal conv k3 -> in-proj -> transformer -> out-proj)."""
@@ -415,26 +439,12 @@ def codec_forward(w, cfg, codes: torch.Tensor, stages: Optional[dict] = None) ->
     for i, r in enumerate(k.upsampling_ratios):
         p = f"codec.up.{i}"
         x = causal_tconv1d(x, w[p + ".tconv.weight"], w[p + ".tconv.bias"], r, k.transconv_trim)
-        res = x
-        y = causal_conv1d(x, w[p + ".cnx.dw.weight"], w[p + ".cnx.dw.bias"], groups=x.shape[1])
-        y = F.layer_norm(y.transpose(1, 2), (x.shape[1],), w[p + ".cnx.ln.weight"], w[p + ".cnx.ln.bias"], 1e-6)
-        y = F.gelu(y @ w[p + ".cnx.pw1.weight"].T + w[p + ".cnx.pw1.bias"])      # exact-erf GELU (:3345)
-        y = y @ w[p + ".cnx.pw2.weight"].T + w[p + ".cnx.pw2.bias"]
-        x = res + (w[p + ".cnx.gamma"] * y).transpose(1, 2)
+        x = convnext_block(w, p + ".cnx", x)
     if stages is not None:
         stages["upsample"] = x
     x = causal_conv1d(x, w["codec.dec.conv_in.weight"], w["codec.dec.conv_in.bias"])
     for i, r in enumerate(k.upsample_rates):
-        p = f"codec.dec.blocks.{i}"
-        x = snake_beta(x, w[p + ".snake.alpha"], w[p + ".snake.beta"])
-        x = causal_tconv1d(x, w[p + ".tconv.weight"], w[p + ".tconv.bias"], r, k.transconv_trim)
-        for j, d in enumerate((1, 3, 9)):
-            u = f"{p}.units.{j}"
-            y = snake_beta(x, w[u + ".snake1.alpha"], w[u + ".snake1.beta"])
-            y = causal_conv1d(y, w[u + ".conv1.weight"], w[u + ".conv1.bias"], dilation=d)
-            y = snake_beta(y, w[u + ".snake2.alpha"], w[u + ".snake2.beta"])
-            y = causal_conv1d(y, w[u + ".conv2.weight"], w[u + ".conv2.bias"])
-            x = x + y
+        x = decoder_block(w, cfg, f"codec.dec.blocks.{i}", x, r)
         if stages is not None:
             stages[f"block{i}"] = x
     x = snake_beta(x, w["codec.dec.snake_out.alpha"], w["codec.dec.snake_out.beta"])

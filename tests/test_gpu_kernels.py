@@ -1,0 +1,245 @@
+"""GPU parity of the individual kernels against the CPU oracle, called through the C ABI (ctypes)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from oracle import qwen3_tts_oracle as O
+from qwen3_tts_b200 import lib as L
+from qwen3_tts_b200.weights import dequantize_w8, pack_w8, quantize_w8
+
+pytestmark = pytest.mark.gpu
+
+
+def _w8(n, k, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    w = torch.randn(n, k, generator=g) * 0.02
+    q, s, b = quantize_w8(w)
+    wd = dequantize_w8(q, s, b)
+    o = L.W8()
+    blob = pack_w8(q.to(dev), s.to(dev), b.to(dev))
+    o.w, o.N, o.K = blob.data_ptr(), n, k
+    return o, blob, wd
+
+
+@pytest.mark.parametrize("n,k", [(2048, 2048), (4096, 2048), (12288, 2048), (2048, 6144), (3072, 2048), (1024, 256),
+                                 (1024, 1024), (6144, 1024), (1024, 3072), (16, 256), (2064, 512)])
+@pytest.mark.parametrize("m", [1, 2])
+def test_w8_gemv_raw(cuda, n, k, m):
+    lib = L.load()
+    o, blob, wd = _w8(n, k, n + k, cuda)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(m, k, generator=g) * torch.rand(1, generator=g) * 3
+    ref = (x.double() @ wd.double().T)
+    xd = x.to(cuda)
+    y = torch.full((m, n), float("nan"), device=cuda)
+    a = L.GemvArgs()
+    a.w, a.M, a.prologue = o, m, L.PRO_RAW
+    a.x, a.x_stride, a.y, a.y_stride = xd.data_ptr(), k, y.data_ptr(), n
+    L.check(lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()), "gemv")
+    torch.cuda.synchronize()
+    err = (y.cpu().double() - ref).abs().max() / ref.abs().max()
+    assert err < 2e-6, f"rel err {err}"
+
+
+def test_w8_gemv_prologues_epilogues(cuda):
+    lib = L.load()
+    n, k = 2048, 1024
+    o, blob, wd = _w8(n, k, 3, cuda)
+    g = torch.Generator().manual_seed(11)
+    # RMSNorm prologue + bias + residual
+    x = torch.randn(2, k, generator=g)
+    nw = 1 + 0.1 * torch.randn(k, generator=g)
+    bias = torch.randn(n, generator=g)
+    resid = torch.randn(2, n, generator=g)
+    ref = O.rms_norm(x, nw, 1e-6).double() @ wd.double().T + bias.double() + resid.double()
+    xd, nwd, bd, rd = x.to(cuda), nw.to(cuda), bias.to(cuda), resid.to(cuda)
+    o.lin_bias = bd.data_ptr()
+    a = L.GemvArgs()
+    a.w, a.M, a.prologue = o, 2, L.PRO_RMSNORM
+    a.x, a.x_stride, a.norm_w, a.eps = xd.data_ptr(), k, nwd.data_ptr(), 1e-6
+    a.resid, a.resid_stride, a.y, a.y_stride = rd.data_ptr(), n, rd.data_ptr(), n     # in place on the residual
+    L.check(lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()), "gemv")
+    torch.cuda.synchronize()
+    assert (rd.cpu().double() - ref).abs().max() / ref.abs().max() < 3e-6
+    # SwiGLU prologue + SiLU epilogue
+    o.lin_bias = 0
+    gu = torch.randn(1, 2 * k, generator=g)
+    ref = torch.nn.functional.silu(((torch.nn.functional.silu(gu[:, :k]) * gu[:, k:]).double() @ wd.double().T))
+    gud = gu.to(cuda)
+    y = torch.empty(1, n, device=cuda)
+    a = L.GemvArgs()
+    a.w, a.M, a.prologue, a.act = o, 1, L.PRO_SWIGLU, L.ACT_SILU
+    a.x, a.x_stride, a.y, a.y_stride = gud.data_ptr(), 2 * k, y.data_ptr(), n
+    L.check(lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()), "gemv")
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 3e-6
+    # gather prologue (embedding row picked on device) with a zero row
+    table = torch.randn(50, k, generator=g)
+    table[7] = 0
+    idx = torch.tensor([33, 7], dtype=torch.int32)
+    ref = table[idx.long()].double() @ wd.double().T
+    td, idd = table.to(cuda), idx.to(cuda)
+    y = torch.empty(2, n, device=cuda)
+    a = L.GemvArgs()
+    a.w, a.M, a.prologue = o, 2, L.PRO_RAW
+    a.x, a.x_stride, a.gather_idx, a.gather_idx_stride, a.gather_row_stride = td.data_ptr(), 0, idd.data_ptr(), 1, k
+    a.y, a.y_stride = y.data_ptr(), n
+    L.check(lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()), "gemv")
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 3e-6
+    assert (y[1] == 0).all()
+
+
+def test_w8_gemv_rejects_bad_shapes(cuda):
+    lib = L.load()
+    a = L.GemvArgs()
+    a.w.N, a.w.K, a.M = 24, 256, 1
+    assert lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()) != 0
+    assert b"N%16" in lib.q3t_last_error()
+    a.w.N, a.M = 32, 3
+    assert lib.q3t_w8_gemv(C.byref(a), L.stream_ptr()) != 0
+
+
+def _attn_ref(qkv, qn, kn, eps, theta, H, Hkv, D, kcache, vcache, pos):
+    """fp32 reference for one new token; kcache/vcache [pos, Hkv, D] already rounded to bf16."""
+    q = qkv[: H * D].view(H, D)
+    k = qkv[H * D:(H + Hkv) * D].view(Hkv, D)
+    v = qkv[(H + Hkv) * D:].view(Hkv, D)
+    cos, sin = O.rope_cos_sin(torch.tensor([pos]), D, theta)
+    q = O.apply_rope(O.rms_norm(q, qn, eps)[None], cos, sin)[0]
+    k = O.apply_rope(O.rms_norm(k, kn, eps)[None], cos, sin)[0]
+    k, v = k.bfloat16().float(), v.bfloat16().float()
+    K = torch.cat([kcache, k[None]], 0).repeat_interleave(H // Hkv, 1)
+    V = torch.cat([vcache, v[None]], 0).repeat_interleave(H // Hkv, 1)
+    s = torch.einsum("hd,shd->hs", q, K) * D ** -0.5
+    return torch.einsum("hs,shd->hd", torch.softmax(s, -1), V).reshape(-1), k, v
+
+
+@pytest.mark.parametrize("pos,nsplit", [(0, 1), (0, 16), (5, 4), (16, 16), (17, 1), (250, 16), (1000, 16), (1000, 3)])
+def test_attn_decode(cuda, pos, nsplit):
+    lib = L.load()
+    H, Hkv, D, B, theta, eps = 4, 2, 128, 2, 1e6, 1e-6
+    g = torch.Generator().manual_seed(pos * 31 + nsplit)
+    max_pages = (pos + 1 + 15) // 16 + 1
+    n_pages = B * max_pages
+    pool = torch.zeros(n_pages, 2, Hkv, 16, D, dtype=torch.bfloat16)
+    perm = torch.randperm(n_pages, generator=g).int().reshape(B, max_pages)      # scattered pages
+    kc = torch.randn(B, pos, Hkv, D, generator=g).bfloat16()
+    vc = torch.randn(B, pos, Hkv, D, generator=g).bfloat16()
+    for b in range(B):
+        for t in range(pos):
+            pool[perm[b, t // 16], 0, :, t % 16] = kc[b, t]
+            pool[perm[b, t // 16], 1, :, t % 16] = vc[b, t]
+    qkv = torch.randn(B, (H + 2 * Hkv) * D, generator=g)
+    qn = 1 + 0.1 * torch.randn(D, generator=g)
+    kn = 1 + 0.1 * torch.randn(D, generator=g)
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    d = lambda t: t.to(cuda).contiguous()
+    pool_d, perm_d, qkv_d, qn_d, kn_d, inv_d = map(d, (pool, perm, qkv, qn, kn, inv))
+    pos_d = torch.full((B,), pos, dtype=torch.int32, device=cuda)
+    out = torch.full((B, H * D), float("nan"), device=cuda)
+    work = torch.zeros(B * Hkv * nsplit * (H // Hkv) * (D + 2), device=cuda)
+    cnt = torch.zeros(B * Hkv, dtype=torch.int32, device=cuda)
+    a = L.AttnArgs()
+    a.qkv, a.q_norm_w, a.k_norm_w, a.eps, a.inv_freq = qkv_d.data_ptr(), qn_d.data_ptr(), kn_d.data_ptr(), eps, inv_d.data_ptr()
+    a.kv_pool, a.block_tbl, a.max_pages, a.pos = pool_d.data_ptr(), perm_d.data_ptr(), max_pages, pos_d.data_ptr()
+    a.out, a.work, a.counters = out.data_ptr(), work.data_ptr(), cnt.data_ptr()
+    a.B, a.H, a.Hkv, a.D, a.nsplit = B, H, Hkv, D, nsplit
+    for _ in range(2):   # second launch checks the counters re-arm themselves
+        L.check(lib.q3t_attn_decode(C.byref(a), L.stream_ptr()), "attn")
+    torch.cuda.synchronize()
+    assert int(cnt.abs().sum()) == 0
+    pool_h = pool_d.cpu()
+    for b in range(B):
+        ref, k_new, v_new = _attn_ref(qkv[b], qn, kn, eps, theta, H, Hkv, D, kc[b].float(), vc[b].float(), pos)
+        err = (out[b].cpu() - ref).abs().max() / ref.abs().max()
+        assert err < 2e-5, f"b={b} rel err {err}"
+        pg = perm[b, pos // 16]
+        # the new K/V row landed in its page (bf16): allow one bf16 ulp for rounding-boundary cases
+        assert (pool_h[pg, 0, :, pos % 16].float() - k_new).abs().max() <= 2 ** -7 * k_new.abs().max()
+        assert torch.equal(pool_h[pg, 1, :, pos % 16].float(), v_new)
+
+
+def _sample(lib, cuda, logits, sp, seen=None, step=0, uniforms=None):
+    B, V = logits.shape
+    lg = logits.to(cuda).contiguous()
+    out = torch.full((B,), -1, dtype=torch.int32, device=cuda)
+    done = torch.zeros(B, dtype=torch.int32, device=cuda)
+    st = torch.tensor([step], dtype=torch.int32, device=cuda)
+    a = L.SampleArgs()
+    a.logits, a.B, a.V, a.logits_stride, a.sp = lg.data_ptr(), B, V, V, sp
+    a.seen = 0 if seen is None else seen.data_ptr()
+    a.step = st.data_ptr()
+    un = None if uniforms is None else uniforms.to(cuda)
+    a.uniforms = 0 if un is None else un.data_ptr()
+    a.out, a.out_stride, a.done = out.data_ptr(), 1, done.data_ptr()
+    L.check(lib.q3t_sample(C.byref(a), L.stream_ptr()), "sample")
+    torch.cuda.synchronize()
+    return out.cpu(), done.cpu()
+
+
+def test_sampler_greedy_masks_and_ties(cuda):
+    lib = L.load()
+    V = 3072
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(4, V, generator=g)
+    logits[0, 2900] = 50.0                 # inside the suppressed range -> must be ignored
+    logits[1, 2150] = 60.0                 # eos is exempt from suppression
+    logits[2, 100] = logits[2, 200] = 40.0  # tie -> lowest index
+    logits[3, 2150] = 60.0                 # eos but min_new_tokens forbids it at step 0
+    sp = L.Sampling()
+    sp.do_sample, sp.repetition_penalty, sp.suppress_lo, sp.suppress_hi, sp.eos_id = 0, 1.0, V - 1024, V, 2150
+    out, done = _sample(lib, cuda, logits, sp)
+    osp = O.SamplingParams(suppress_lo=V - 1024, suppress_hi=V, eos_id=2150)
+    ref = [O.draw(O.process_logits(logits[b], osp, (), 0), osp) for b in range(4)]
+    assert out.tolist() == ref and out[1] == 2150 and out[2] == 100 and done.tolist() == [0, 1, 0, 1]
+    sp.min_new_tokens = 2
+    out, done = _sample(lib, cuda, logits[3:], sp, step=0)
+    osp.min_new_tokens = 2
+    assert out.tolist() == [O.draw(O.process_logits(logits[3], osp, (), 0), osp)] and done.tolist() == [0]
+
+
+def test_sampler_repetition_penalty_set_semantics(cuda):
+    lib = L.load()
+    V = 2048
+    g = torch.Generator().manual_seed(1)
+    logits = torch.randn(2, V, generator=g)
+    logits[0, 5], logits[0, 9] = 10.0, 9.9       # 5 was generated before: 10/1.05 < 9.9 -> 9 wins
+    logits[1, 5], logits[1, 9] = -0.001, -0.00101  # negative scores are multiplied
+    hist = [5, 5, 77]
+    seen = torch.zeros(2, V // 32, dtype=torch.int32)
+    for h in hist:
+        seen[:, h // 32] |= 1 << (h % 32)
+    sp = L.Sampling()
+    sp.do_sample, sp.repetition_penalty, sp.suppress_lo, sp.suppress_hi, sp.eos_id = 0, 1.05, -1, -1, -1
+    seen_d = seen.to(cuda)
+    out, _ = _sample(lib, cuda, logits, sp, seen=seen_d)
+    osp = O.SamplingParams(repetition_penalty=1.05)
+    ref = [O.draw(O.process_logits(logits[b], osp, hist, 3), osp) for b in range(2)]
+    assert out.tolist() == ref
+    s2 = seen_d.cpu()
+    for b in range(2):   # the chosen id was added to the set
+        assert (int(s2[b, out[b] // 32]) >> (int(out[b]) % 32)) & 1
+
+
+@pytest.mark.parametrize("top_k,top_p,temp", [(50, 1.0, 0.9), (50, 0.8, 0.9), (0, 0.9, 1.0), (1, 1.0, 1.0), (5, 0.5, 2.0)])
+def test_sampler_stochastic_with_shared_uniforms(cuda, top_k, top_p, temp):
+    lib = L.load()
+    V, B = 2048, 64
+    g = torch.Generator().manual_seed(top_k + 3)
+    logits = torch.randn(B, V, generator=g) * 3
+    logits[:, 10] = logits[:, 20]                # a tie inside the candidate set
+    u = torch.rand(B, generator=g)
+    sp = L.Sampling()
+    sp.do_sample, sp.temperature, sp.top_k, sp.top_p, sp.repetition_penalty = 1, temp, top_k, top_p, 1.0
+    sp.suppress_lo, sp.suppress_hi, sp.eos_id = -1, -1, -1
+    out, _ = _sample(lib, cuda, logits, sp, uniforms=u)
+    osp = O.SamplingParams(do_sample=True, temperature=temp, top_k=top_k, top_p=top_p)
+    mism = 0
+    for b in range(B):
+        s = O.process_logits(logits[b], osp, (), 0)
+        ref = O.draw(s, osp, float(u[b]))
+        assert torch.isfinite(s[out[b]]), "sampled a filtered id"
+        mism += int(ref != int(out[b]))
+    assert mism <= 1, f"{mism} draws differ (only CDF-boundary rounding may differ)"

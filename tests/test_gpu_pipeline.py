@@ -1,0 +1,182 @@
+"""GPU parity of the whole hot path (talker decode -> code predictor -> codec) against the CPU oracle."""
+import pytest
+import torch
+
+from oracle import qwen3_tts_oracle as O
+from qwen3_tts_b200 import config as Cfg
+from qwen3_tts_b200.weights import make_weights
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 1e-2          # BASELINE.json: logits within 1e-2 relative
+WAV_SNR_DB = 40.0          # BASELINE.json: waveform SNR >= 40 dB
+
+
+def _text_ids(cfg, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    body = torch.randint(0, cfg.talker.text_vocab_size - 16, (n,), generator=g).tolist()
+    return [cfg.im_start_id, cfg.assistant_id, 10] + body + [cfg.im_end_id, 10, cfg.im_start_id, cfg.assistant_id, 10]
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+
+
+@pytest.fixture(scope="module")
+def small_setup(cuda):
+    from qwen3_tts_b200.model import Model
+    cfg = Cfg.small("custom_voice")
+    ws = make_weights(cfg, seed=0, head_std=0.2)
+    model = Model(cfg, ws, "cuda", max_frames=64, max_ctx=256, max_trailing=64)
+    oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
+    return cfg, ws, model, oracle
+
+
+def test_prefill_embeddings_match(small_setup):
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 12, 1)
+    for kwargs in (dict(speaker="ryan", language="english", instruct_ids=[5, 6, 7, 8]), dict(streaming=True),
+                   dict(speaker_vec=torch.randn(cfg.talker.hidden_size) * 0.02, streaming=True, language="korean")):
+        pre_o, tr_o = oracle.build_prefill(ids, **kwargs)
+        pre_d, tr_d = model.build_prefill(ids, **kwargs)
+        assert pre_d.shape == pre_o.shape and tr_d.shape == tr_o.shape
+        assert _rel(pre_d.cpu(), pre_o) < 1e-5 and _rel(tr_d.cpu(), tr_o) < 1e-5
+
+
+def test_teacher_forced_logits_and_argmax(small_setup):
+    """Primary parity gate: feed the oracle's codes, compare per-step logits and argmax."""
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 10, 2)
+    pre, tr = oracle.build_prefill(ids, speaker="serena", language="english")
+    n = 12
+    codes_o, rec = oracle.generate(pre, tr, n, record=True)
+    e = model.engine
+    e2 = type(e)(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=256, keep_cp_logits=True)
+    e2.set_sampling(do_sample=False)
+    e2.set_forced(codes_o[None])
+    e2.use_graphs = False
+    e2.prefill(pre[None], None, tr[None])
+    tl, cl = [], []
+    for f in range(n):
+        tl.append(e2.logits[0].clone())
+        e2._run("frame")
+        cl.append(e2.cp_logits[:, 0].clone())
+    torch.cuda.synchronize()
+    own = e2.own_codes[0, :n].cpu()
+    for f in range(n):
+        assert _rel(tl[f].cpu(), rec["talker_logits"][f]) < LOGIT_RTOL, f"talker logits frame {f}"
+        assert _rel(cl[f].cpu(), rec["cp_logits"][f]) < LOGIT_RTOL, f"cp logits frame {f}"
+    own_o = torch.tensor(rec["own_codes"])
+    assert torch.equal(own.long(), own_o), "teacher-forced argmax differs"
+    assert torch.equal(e2.codes[0, :n].cpu().long(), codes_o)
+
+
+def test_free_running_greedy_codes_bit_exact(small_setup):
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 14, 3)
+    pre, tr = oracle.build_prefill(ids, speaker="ryan", language="english", instruct_ids=[9, 8, 7])
+    n = 24
+    codes_o, rec = oracle.generate(pre, tr, n, record=True)
+    model.engine.set_sampling(do_sample=False)
+    codes_d = model.generate_codes(pre.cuda(), tr.cuda(), n).cpu().long()
+    eps = 1e-4    # equality is asserted up to the first frame whose oracle top-1/top-2 margin is below eps
+    safe = n
+    for f, m in enumerate(rec["margins"]):
+        if m < eps:
+            safe = f
+            break
+    assert safe >= 8, "test set-up: margins too small to say anything"
+    assert torch.equal(codes_d[:safe], codes_o[:safe]), f"greedy codes differ before frame {safe}"
+
+
+def test_streaming_trailing_text_and_graph_replay_equals_eager(small_setup):
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 9, 4)
+    pre, tr = oracle.build_prefill(ids, streaming=True, speaker_vec=torch.randn(cfg.talker.hidden_size) * 0.02)
+    n = 14     # longer than the trailing text: exercises the switch to tts_pad
+    codes_o = oracle.generate(pre, tr, n)
+    e = model.engine
+    e.set_sampling(do_sample=False)
+    e.use_graphs = True
+    a = model.generate_codes(pre.cuda(), tr.cuda(), n).cpu().long()
+    e.use_graphs = False
+    b = model.generate_codes(pre.cuda(), tr.cuda(), n).cpu().long()
+    e.use_graphs = True
+    assert torch.equal(a, b), "graph replay and eager launch disagree"
+    assert torch.equal(a[:6], codes_o[:6])
+
+
+def test_batch2_rows_are_independent(cuda):
+    from qwen3_tts_b200.engine import TalkerEngine
+    cfg = Cfg.small("voice_design")
+    ws = make_weights(cfg, seed=5, head_std=0.2)
+    oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
+    pa, ta = oracle.build_prefill(_text_ids(cfg, 6, 5), instruct_ids=[1, 2, 3])
+    pb, tb = oracle.build_prefill(_text_ids(cfg, 11, 6), instruct_ids=[4, 5])
+    La, Lb = pa.shape[0], pb.shape[0]
+    Lm = max(La, Lb)
+    emb = torch.zeros(2, Lm, cfg.talker.hidden_size)
+    emb[0, Lm - La:], emb[1, Lm - Lb:] = pa, pb           # right-aligned
+    e = TalkerEngine(cfg, ws, "cuda", batch=2, max_frames=32, max_ctx=128)
+    e.set_sampling(do_sample=False)
+    e.prefill(emb, [La, Lb], torch.stack([ta, tb]))
+    codes = e.generate(8).cpu().long()
+    assert torch.equal(codes[0, :4], oracle.generate(pa, ta, 4))
+    assert torch.equal(codes[1, :4], oracle.generate(pb, tb, 4))
+
+
+def test_rvq_gather_is_bit_exact(small_setup):
+    cfg, ws, model, oracle = small_setup
+    g = torch.Generator().manual_seed(7)
+    for T in (1, 37):
+        codes = torch.randint(0, cfg.codec.codebook_size, (3, 16, T), generator=g)
+        codes[0, :, 0] = 0
+        codes[1, :, -1] = cfg.codec.codebook_size - 1
+        _, sums = O.rvq_decode(ws.fp, cfg, codes, split=True)
+        sem, ac = model.codec.rvq_sums(codes)
+        assert torch.equal(sem.cpu(), sums[0]) and torch.equal(ac.cpu(), sums[1])
+
+
+def _snr_db(x, ref):
+    return float(10 * torch.log10(ref.double().pow(2).sum() / (x.double() - ref.double()).pow(2).sum().clamp_min(1e-30)))
+
+
+def test_codec_stages_and_waveform_snr(small_setup):
+    cfg, ws, model, oracle = small_setup
+    g = torch.Generator().manual_seed(8)
+    codes = torch.randint(0, cfg.codec.codebook_size, (2, 16, 21), generator=g)
+    so, sd = {}, {}
+    wav_o = O.codec_forward(ws.fp, cfg, codes, so)[:, 0]
+    wav_d = model.codec.forward(codes, sd).cpu()
+    assert wav_d.shape == wav_o.shape == (2, cfg.codec.out_len(21))
+    for k in so:
+        assert _rel(sd[k].cpu().transpose(1, 2), so[k]) < 1e-3, k
+    assert _snr_db(wav_d, wav_o) >= WAV_SNR_DB
+    assert float(wav_d.abs().max()) <= 1.0
+
+
+def test_codec_chunked_decode_matches_oracle(small_setup):
+    cfg, ws, model, oracle = small_setup
+    g = torch.Generator().manual_seed(9)
+    old = cfg.codec.chunk_size, cfg.codec.left_context
+    cfg.codec.chunk_size, cfg.codec.left_context = 16, 5       # several chunks at a CPU-friendly size
+    try:
+        codes = torch.randint(0, cfg.codec.codebook_size, (1, 16, 45), generator=g)
+        wav_o = O.codec_chunked_decode(ws.fp, cfg, codes)[:, 0]
+        wav_d = model.codec.decode(codes).cpu()
+        assert wav_d.shape == wav_o.shape
+        assert _snr_db(wav_d, wav_o) >= WAV_SNR_DB
+    finally:
+        cfg.codec.chunk_size, cfg.codec.left_context = old
+
+
+def test_generate_audio_writes_audio_000_wav(small_setup, tmp_path):
+    """The reference's output contract (io.py:156-158): <output_path>/audio_000.wav, mono, 24 kHz."""
+    import wave
+    from mlx_audio.tts.generate import generate_audio
+    cfg, ws, model, oracle = small_setup
+    generate_audio(model=model, text="Hello there", voice="ryan", instruct="Normal tone", speed=1.0,
+                   output_path=str(tmp_path), max_tokens=5, greedy=True)
+    with wave.open(str(tmp_path / "audio_000.wav")) as w:
+        assert w.getframerate() == 24000 and w.getnchannels() == 1 and w.getsampwidth() == 2
+        assert w.getnframes() == cfg.codec.out_len(5)

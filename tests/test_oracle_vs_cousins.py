@@ -1,0 +1,259 @@
+"""Pins the CPU oracle against the structurally identical classes that ship with transformers 5.5 (the only
+independent implementation of this arithmetic available offline).  The reference's own tests hold
+no golden vectors for the hot path ("parity unpinned"), so these cross-checks are what anchors the oracle:
+
+  (i)   dense Qwen3 decoder stack (talker layers)            vs  transformers Qwen3Model
+  (ii)  code-predictor stack + heads, incl. KV-cached steps  vs  Qwen3OmniMoeTalkerCodePredictorModelForConditionalGeneration
+  (iii) codec transformer / ConvNeXt / decoder blocks        vs  Qwen3OmniMoeCode2Wav* classes
+  (iv)  split RVQ decode                                     vs  MimiSplitResidualVectorQuantizer
+  (v)   sampler                                              vs  HF logits processors
+"""
+import pytest
+import torch
+
+from oracle import qwen3_tts_oracle as O
+from qwen3_tts_b200 import config as Cfg
+from qwen3_tts_b200.weights import make_weights
+
+tf = pytest.importorskip("transformers")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    cfg = Cfg.tiny()
+    return cfg, make_weights(cfg, seed=0)
+
+
+def _copy_layers(dst_layers, w, prefix, n):
+    with torch.no_grad():
+        for i in range(n):
+            p, l = f"{prefix}.layers.{i}", dst_layers[i]
+            l.input_layernorm.weight.copy_(w[p + ".input_norm.weight"])
+            l.post_attention_layernorm.weight.copy_(w[p + ".post_norm.weight"])
+            a = l.self_attn
+            a.q_proj.weight.copy_(w[p + ".q_proj.weight"]); a.k_proj.weight.copy_(w[p + ".k_proj.weight"])
+            a.v_proj.weight.copy_(w[p + ".v_proj.weight"]); a.o_proj.weight.copy_(w[p + ".o_proj.weight"])
+            a.q_norm.weight.copy_(w[p + ".q_norm.weight"]); a.k_norm.weight.copy_(w[p + ".k_norm.weight"])
+            l.mlp.gate_proj.weight.copy_(w[p + ".gate_proj.weight"]); l.mlp.up_proj.weight.copy_(w[p + ".up_proj.weight"])
+            l.mlp.down_proj.weight.copy_(w[p + ".down_proj.weight"])
+
+
+def test_talker_stack_matches_qwen3model(tiny):
+    cfg, ws = tiny
+    t = cfg.talker
+    from transformers import Qwen3Config, Qwen3Model
+    hc = Qwen3Config(vocab_size=32, hidden_size=t.hidden_size, intermediate_size=t.intermediate_size,
+                     num_hidden_layers=t.num_layers, num_attention_heads=t.num_heads, num_key_value_heads=t.num_kv_heads,
+                     head_dim=t.head_dim, rms_norm_eps=t.rms_norm_eps, rope_parameters={"rope_type": "default",
+                                                                                        "rope_theta": t.rope_theta},
+                     attention_bias=False, tie_word_embeddings=False)
+    hc._attn_implementation = "eager"
+    m = Qwen3Model(hc).eval()
+    _copy_layers(m.layers, ws.fp, "talker", t.num_layers)
+    with torch.no_grad():
+        m.norm.weight.copy_(ws.fp["talker.norm.weight"])
+    x = torch.randn(1, 9, t.hidden_size, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = m(inputs_embeds=x).last_hidden_state[0]
+    st = O.DecoderStack(ws.fp, "talker", t.num_layers, t.num_heads, t.num_kv_heads, t.head_dim, t.rms_norm_eps, t.rope_theta)
+    got = st.forward(x[0, :5])                       # prefill 5 ...
+    got = torch.cat([got] + [st.forward(x[0, i:i + 1]) for i in range(5, 9)])   # ... then 4 cached decode steps
+    assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+
+
+def test_code_predictor_matches_cousin(tiny):
+    cfg, ws = tiny
+    c = cfg.cp
+    from transformers.models.qwen3_omni_moe import configuration_qwen3_omni_moe as CC, modeling_qwen3_omni_moe as MM
+    hc = CC.Qwen3OmniMoeTalkerCodePredictorConfig(
+        vocab_size=c.vocab_size, hidden_size=c.hidden_size, intermediate_size=c.intermediate_size,
+        num_hidden_layers=c.num_layers, num_attention_heads=c.num_heads, num_key_value_heads=c.num_kv_heads,
+        head_dim=c.head_dim, rms_norm_eps=c.rms_norm_eps, num_code_groups=c.num_code_groups,
+        rope_parameters={"rope_type": "default", "rope_theta": c.rope_theta})
+    hc._attn_implementation = "eager"
+    m = MM.Qwen3OmniMoeTalkerCodePredictorModelForConditionalGeneration(hc).eval()
+    _copy_layers(m.model.layers, ws.fp, "cp", c.num_layers)
+    with torch.no_grad():
+        m.model.norm.weight.copy_(ws.fp["cp.norm.weight"])
+        for g in range(c.num_code_groups - 1):
+            m.lm_head[g].weight.copy_(ws.fp[f"cp.heads.{g}.weight"])
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 2, c.hidden_size, generator=g)
+    st = O.DecoderStack(ws.fp, "cp", c.num_layers, c.num_heads, c.num_kv_heads, c.head_dim, c.rms_norm_eps, c.rope_theta)
+    with torch.no_grad():
+        out = m(inputs_embeds=x, use_cache=True)                      # 2-token prefill -> lm_head[0]
+    h = st.forward(x[0])[-1]
+    assert torch.allclose(h @ ws.fp["cp.heads.0.weight"].T, out.logits[0, -1], rtol=1e-4, atol=1e-5)
+    past = out.past_key_values
+    for step in range(1, 4):                                           # cached single-token steps -> lm_head[step]
+        xi = torch.randn(1, 1, c.hidden_size, generator=g)
+        with torch.no_grad():
+            # the cousin embeds ids itself in the generation stage; bypass it to feed identical vectors
+            o = m.model(inputs_embeds=xi, past_key_values=past, use_cache=True)
+            ref = m.lm_head[step](o.last_hidden_state)[0, -1]
+            past = o.past_key_values
+        h = st.forward(xi[0])[-1]
+        assert torch.allclose(h @ ws.fp[f"cp.heads.{step}.weight"].T, ref, rtol=1e-4, atol=1e-5)
+
+
+def _c2w_cfg(cfg):
+    from transformers.models.qwen3_omni_moe import configuration_qwen3_omni_moe as CC
+    k = cfg.codec
+    hc = CC.Qwen3OmniMoeCode2WavConfig(
+        codebook_size=k.codebook_size, hidden_size=k.tf_hidden, num_attention_heads=k.tf_heads,
+        num_key_value_heads=k.tf_heads, sliding_window=k.sliding_window, intermediate_size=k.tf_intermediate,
+        layer_scale_initial_scale=k.layer_scale, rms_norm_eps=k.tf_rms_eps, num_hidden_layers=k.tf_layers,
+        num_quantizers=k.num_quantizers, upsample_rates=k.upsample_rates, upsampling_ratios=k.upsampling_ratios,
+        decoder_dim=k.decoder_dim, rope_parameters={"rope_type": "default", "rope_theta": k.tf_rope_theta})
+    hc._attn_implementation = "eager"
+    return hc
+
+
+def test_codec_transformer_matches_cousin(tiny):
+    cfg, ws = tiny
+    w, k = ws.fp, cfg.codec
+    assert k.tf_heads * k.tf_head_dim == k.tf_hidden   # the cousin ties head_dim to hidden/heads
+    from transformers.models.qwen3_omni_moe import modeling_qwen3_omni_moe as MM
+    m = MM.Qwen3OmniMoeCode2WavTransformerModel(_c2w_cfg(cfg)).eval()
+    with torch.no_grad():
+        for i, l in enumerate(m.layers):
+            p = f"codec.tf.layers.{i}"
+            l.input_layernorm.weight.copy_(w[p + ".input_norm.weight"])
+            l.post_attention_layernorm.weight.copy_(w[p + ".post_norm.weight"])
+            for n in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                getattr(l.self_attn, n).weight.copy_(w[f"{p}.{n}.weight"])
+            for n in ("gate_proj", "up_proj", "down_proj"):
+                getattr(l.mlp, n).weight.copy_(w[f"{p}.{n}.weight"])
+            l.self_attn_layer_scale.scale.copy_(w[p + ".attn_scale"])
+            l.mlp_layer_scale.scale.copy_(w[p + ".mlp_scale"])
+        m.norm.weight.copy_(w["codec.tf.norm.weight"])
+    x = torch.randn(2, 100, k.tf_hidden, generator=torch.Generator().manual_seed(3))   # 100 > window 72
+    with torch.no_grad():
+        ref = m(inputs_embeds=x).last_hidden_state
+    assert torch.allclose(O.codec_transformer(w, cfg, x), ref, rtol=1e-4, atol=1e-5)
+
+
+def test_convnext_and_decoder_blocks_match_cousin(tiny):
+    cfg, ws = tiny
+    w, k = ws.fp, cfg.codec
+    from transformers.models.qwen3_omni_moe import modeling_qwen3_omni_moe as MM
+    g = torch.Generator().manual_seed(4)
+    # ConvNeXt block
+    blk = MM.Qwen3OmniMoeConvNeXtBlock(k.latent_dim).eval()
+    p = "codec.up.0.cnx"
+    with torch.no_grad():
+        blk.dwconv.conv.weight.copy_(w[p + ".dw.weight"]); blk.dwconv.conv.bias.copy_(w[p + ".dw.bias"])
+        blk.norm.weight.copy_(w[p + ".ln.weight"]); blk.norm.bias.copy_(w[p + ".ln.bias"])
+        blk.pwconv1.weight.copy_(w[p + ".pw1.weight"]); blk.pwconv1.bias.copy_(w[p + ".pw1.bias"])
+        blk.pwconv2.weight.copy_(w[p + ".pw2.weight"]); blk.pwconv2.bias.copy_(w[p + ".pw2.bias"])
+        blk.gamma.copy_(w[p + ".gamma"])
+    x = torch.randn(2, k.latent_dim, 19, generator=g)
+    with torch.no_grad():
+        assert torch.allclose(O.convnext_block(w, p, x), blk(x), rtol=1e-4, atol=1e-5)
+    # transposed conv of the x2 upsampler (k == stride: no trim)
+    tc = MM.Qwen3OmniMoeCausalTransConvNet(k.latent_dim, k.latent_dim, 2, 2).eval()
+    with torch.no_grad():
+        tc.conv.weight.copy_(w["codec.up.0.tconv.weight"]); tc.conv.bias.copy_(w["codec.up.0.tconv.bias"])
+        assert torch.allclose(O.causal_tconv1d(x, w["codec.up.0.tconv.weight"], w["codec.up.0.tconv.bias"], 2), tc(x),
+                              rtol=1e-4, atol=1e-5)
+    # decoder blocks (SnakeBeta + transposed conv with the cousin's both-sides trim + dilated residual units)
+    hc = _c2w_cfg(cfg)
+    ch = k.decoder_dim
+    for i, r in enumerate(k.upsample_rates):
+        db = MM.Qwen3OmniMoeCode2WavDecoderBlock(hc, i).eval()
+        p = f"codec.dec.blocks.{i}"
+        with torch.no_grad():
+            db.block[0].alpha.copy_(w[p + ".snake.alpha"]); db.block[0].beta.copy_(w[p + ".snake.beta"])
+            db.block[1].conv.weight.copy_(w[p + ".tconv.weight"]); db.block[1].conv.bias.copy_(w[p + ".tconv.bias"])
+            for j in range(3):
+                u, ru = f"{p}.units.{j}", db.block[2 + j]
+                ru.act1.alpha.copy_(w[u + ".snake1.alpha"]); ru.act1.beta.copy_(w[u + ".snake1.beta"])
+                ru.conv1.conv.weight.copy_(w[u + ".conv1.weight"]); ru.conv1.conv.bias.copy_(w[u + ".conv1.bias"])
+                ru.act2.alpha.copy_(w[u + ".snake2.alpha"]); ru.act2.beta.copy_(w[u + ".snake2.beta"])
+                ru.conv2.conv.weight.copy_(w[u + ".conv2.weight"]); ru.conv2.conv.bias.copy_(w[u + ".conv2.bias"])
+        x = torch.randn(2, ch, 23, generator=g)
+        with torch.no_grad():
+            ref = db(x)
+        got = O.decoder_block(w, cfg, p, x, r)
+        assert got.shape == ref.shape == (2, ch // 2, (23 - 1) * r)
+        assert torch.allclose(got, ref, rtol=1e-4, atol=1e-5)
+        ch //= 2
+
+
+def test_out_len_matches_cousin_sample_count():
+    # the cousin turns 375 frames (chunks of 300 + 75 with 25 frames of context) into 718 890 samples
+    k = Cfg.full().codec
+    assert k.hop == 1920
+    first, second = k.out_len(300), k.out_len(25 + 75) - 25 * k.hop
+    assert first + second == 718890
+
+
+def test_rvq_matches_mimi_split_quantizer(tiny):
+    cfg, ws = tiny
+    k, w = cfg.codec, ws.fp
+    from transformers.models.mimi import configuration_mimi as MC, modeling_mimi as MMi
+    mc = MC.MimiConfig(hidden_size=k.rvq_out_dim, codebook_size=k.codebook_size, codebook_dim=k.codebook_dim,
+                       vector_quantization_hidden_dimension=k.codebook_dim, num_quantizers=k.num_quantizers,
+                       num_semantic_quantizers=k.num_semantic)
+    q = MMi.MimiSplitResidualVectorQuantizer(mc).eval()
+    with torch.no_grad():
+        for grp, rvq in (("semantic", q.semantic_residual_vector_quantizer), ("acoustic", q.acoustic_residual_vector_quantizer)):
+            for i, layer in enumerate(rvq.layers):
+                layer.codebook.embed_sum.copy_(w[f"codec.rvq.{grp}.codebooks.{i}.embed_sum"])
+                usage = torch.rand(k.codebook_size, generator=torch.Generator().manual_seed(i)) * 2
+                usage[:3] = 0.0                                   # exercises the clamp(min=1e-5)
+                layer.codebook.cluster_usage.copy_(usage)
+                w[f"codec.rvq.{grp}.codebooks.{i}.cluster_usage"] = usage.clone()
+            rvq.output_proj.weight.copy_(w[f"codec.rvq.{grp}.out_proj.weight"][:, :, None])
+    codes = torch.randint(0, k.codebook_size, (2, k.num_quantizers, 11), generator=torch.Generator().manual_seed(5))
+    codes[0, :, 0] = 1
+    with torch.no_grad():
+        ref = q.decode(codes)
+    got = O.rvq_decode(w, cfg, codes)
+    for grp in ("semantic", "acoustic"):                          # restore
+        for i in range(k.num_semantic if grp == "semantic" else k.num_quantizers - k.num_semantic):
+            w[f"codec.rvq.{grp}.codebooks.{i}.cluster_usage"] = torch.ones(k.codebook_size)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+
+
+def test_sampler_matches_hf_processors():
+    from transformers.generation import logits_process as LP
+    V = 3072
+    g = torch.Generator().manual_seed(6)
+    for trial in range(20):
+        logits = torch.randn(V, generator=g) * 2
+        hist = torch.randint(0, V, (30,), generator=g).tolist()
+        sp = O.SamplingParams(do_sample=True, temperature=0.9, top_k=50, top_p=0.8 if trial % 2 else 1.0,
+                              repetition_penalty=1.05, min_new_tokens=2, suppress_lo=V - 1024, suppress_hi=V, eos_id=2150)
+        n_gen = trial % 4
+        got = O.process_logits(logits, sp, hist, n_gen)
+        ids = torch.tensor([hist])
+        s = logits[None].clone()
+        s = LP.RepetitionPenaltyLogitsProcessor(1.05)(ids, s)
+        if n_gen < 2:
+            s[0, 2150] = float("-inf")       # MinNewTokensLengthLogitsProcessor, logits_process.py:164
+        sup = [i for i in range(V - 1024, V) if i != 2150]
+        s = LP.SuppressTokensLogitsProcessor(sup)(ids, s)
+        s = LP.TemperatureLogitsWarper(0.9)(ids, s)
+        s = LP.TopKLogitsWarper(50)(ids, s)
+        if sp.top_p < 1.0:
+            s = LP.TopPLogitsWarper(0.8)(ids, s)
+        assert torch.equal(torch.isfinite(got), torch.isfinite(s[0]))
+        m = torch.isfinite(got)
+        assert torch.allclose(got[m], s[0][m], rtol=1e-6, atol=1e-6)
+    # draw: inverse CDF in index order
+    sc = torch.full((8,), float("-inf")); sc[2], sc[5] = 0.0, 0.0
+    sp = O.SamplingParams(do_sample=True)
+    assert O.draw(sc, sp, 0.25) == 2 and O.draw(sc, sp, 0.75) == 5 and O.draw(sc, sp, 0.0) == 2
+    assert O.draw(sc, O.SamplingParams(), None) == 2          # greedy tie -> lowest index
+
+
+def test_next_input_sum_matches_cousin_driver(tiny):
+    """Frame-loop glue (cousin :3262-3277): next input = sum of the 16 code embeddings + trailing text / tts_pad."""
+    cfg, ws = tiny
+    m = O.OracleModel(cfg, ws.fp)
+    h = torch.randn(cfg.talker.hidden_size, generator=torch.Generator().manual_seed(7))
+    codes, acc = m.cp_frame(h, 5)
+    embs = [ws.fp["talker.codec_embedding"][5]] + [ws.fp[f"cp.embeddings.{g}"][c] for g, c in enumerate(codes)]
+    assert len(codes) == cfg.cp.num_code_groups - 1
+    assert torch.allclose(acc, torch.stack(embs).sum(0), rtol=1e-6, atol=1e-7)
