@@ -111,14 +111,15 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
 #pragma unroll
         for (int e = 0; e < EPL; ++e) { acc[r][e] = 0.f; qr[r][e] = (s0 < s1) ? q_s[r][sl * EPL + e] : 0.f; }
     }
-    for (int tok = s0 + hwid; tok < s1; tok += 16) {
-        const int tok2 = tok + 8;
-        const bool has2 = tok2 < s1;
-        const __nv_bfloat16* kp = p.kv_pool + (size_t)btbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
-                                  (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
-        const __nv_bfloat16* kp2 = has2 ? p.kv_pool + (size_t)btbl[tok2 / Q3T_KV_PAGE] * page_elems + head_off +
-                                              (size_t)(tok2 % Q3T_KV_PAGE) * D + sl * EPL
-                                        : kp;
+    // trip count is warp-uniform (both half-warps shuffle together); out-of-range tokens are masked
+    for (int base = s0; base < s1; base += 16) {
+        const int tok = base + hwid, tok2 = tok + 8;
+        const bool has1 = tok < s1, has2 = tok2 < s1;
+        const int t1 = has1 ? tok : s0, t2 = has2 ? tok2 : s0;
+        const __nv_bfloat16* kp = p.kv_pool + (size_t)btbl[t1 / Q3T_KV_PAGE] * page_elems + head_off +
+                                  (size_t)(t1 % Q3T_KV_PAGE) * D + sl * EPL;
+        const __nv_bfloat16* kp2 = p.kv_pool + (size_t)btbl[t2 / Q3T_KV_PAGE] * page_elems + head_off +
+                                   (size_t)(t2 % Q3T_KV_PAGE) * D + sl * EPL;
         float k0[EPL], v0[EPL], k1[EPL], v1[EPL];
         load_bf16_row<EPL>(kp, k0);
         load_bf16_row<EPL>(kp + v_off, v0);
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
                 sa += __shfl_xor_sync(0xffffffffu, sa, o);
                 sb += __shfl_xor_sync(0xffffffffu, sb, o);
             }
+            if (!has1) sa = -INFINITY;
             if (!has2) sb = -INFINITY;
             const float mn = fmaxf(m_run[r], fmaxf(sa, sb));
+            if (mn == -INFINITY) continue;             // nothing seen yet by this half-warp
             const float corr = __expf(m_run[r] - mn);   // exp(-inf) = 0 on the first token
             const float pa = __expf(sa - mn), pb = __expf(sb - mn);
             l_run[r] = l_run[r] * corr + pa + pb;

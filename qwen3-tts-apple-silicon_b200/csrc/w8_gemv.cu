@@ -63,10 +63,16 @@ __device__ __forceinline__ void load_unit(UnitRegs& r, const uint8_t* tile, int 
 struct GemvSmem {
     uint4* xfrag;   // [K/64][32] B-fragment-ordered digits
     float* xsum;    // [2][K/64] per-group sum of x (real units)
-    float* xf;      // [M][K] staged activations
+    float* xscl;    // [2][K/64] per-group fixed-point scale (block floating point, one exponent per 64 inputs)
     float* red;     // [16 warps][16 rows][2]
-    float* scratch; // [32] reductions, [32..33] xscale
+    float* scratch; // [32] reductions
 };
+
+constexpr int GEMV_MAXV = 4;   // float4 per thread per row: K <= 4*4*512 = 8192
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 template <int M>
 __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvParams p) {
@@ -75,12 +81,35 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
     GemvSmem s;
     s.xfrag = reinterpret_cast<uint4*>(smem_raw);
     s.xsum = reinterpret_cast<float*>(smem_raw + (size_t)ngroups * 512);
-    s.xf = s.xsum + 2 * ngroups;
-    s.red = s.xf + (size_t)M * K;
+    s.xscl = s.xsum + 2 * ngroups;
+    s.red = s.xscl + 2 * ngroups;
     s.scratch = s.red + GEMV_WARPS * 16 * 2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K4 = K >> 2;
+    const int ks = p.ks, nteams = GEMV_WARPS / ks, team = warp / ks, jw = warp % ks;
+    const int rt_begin = (int)(((long long)p.nrt * blockIdx.x) / gridDim.x);
+    const int rt_end = (int)(((long long)p.nrt * (blockIdx.x + 1)) / gridDim.x);
+    const int U = 2 * p.nkc;
+
+    // ---- start the HBM stream before anything else: this CTA's row tiles are one contiguous slab; ask the
+    // L2 for all of it now so the weight traffic overlaps the activation prologue and the compute below
+    if (tid < 32) {
+        const uint8_t* slab = p.w + (size_t)rt_begin * p.nkc * Q3T_TILE_BYTES;
+        const size_t slab_bytes = (size_t)(rt_end - rt_begin) * p.nkc * Q3T_TILE_BYTES;   // multiple of 16
+        constexpr uint32_t PIECE = 16384;
+        for (size_t off = (size_t)tid * PIECE; off < slab_bytes; off += 32 * (size_t)PIECE) {
+            const size_t n = slab_bytes - off < PIECE ? slab_bytes - off : PIECE;
+            l2_prefetch_bulk(slab + off, (uint32_t)n);
+        }
+    }
+    // first unit of this warp's first row tile: loads are independent of x, issue them before the prologue
+    UnitRegs cur;
+    {
+        const int rt = rt_begin + team;
+        if (rt < rt_end && jw < U)
+            load_unit(cur, p.w + ((size_t)rt * p.nkc + (jw >> 1)) * Q3T_TILE_BYTES, jw & 1, lane);
+    }
 
     // ------------------------------------------------------------------ prologue: x -> digits
     if (M == 1) {  // columns 4..7 (second batch row) must read as zero
@@ -91,74 +120,81 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
     for (int m = 0; m < M; ++m) {
         const float* xr = p.x + m * p.x_stride;
         if (p.gather_idx) xr += (long long)p.gather_idx[m * p.gather_idx_stride] * p.gather_row_stride;
-        float* xf = s.xf + (size_t)m * K;
+        float4 xv[GEMV_MAXV];
         float ss = 0.f;
-        for (int k4 = tid; k4 < K4; k4 += GEMV_THREADS) {
-            float4 v = reinterpret_cast<const float4*>(xr)[k4];
-            if (p.prologue == Q3T_PRO_SWIGLU) {
-                const float4 u = reinterpret_cast<const float4*>(xr + K)[k4];
-                v.x = silu_f(v.x) * u.x; v.y = silu_f(v.y) * u.y; v.z = silu_f(v.z) * u.z; v.w = silu_f(v.w) * u.w;
+#pragma unroll
+        for (int i = 0; i < GEMV_MAXV; ++i) {
+            const int k4 = tid + i * GEMV_THREADS;
+            if (k4 < K4) {
+                float4 v = reinterpret_cast<const float4*>(xr)[k4];
+                if (p.prologue == Q3T_PRO_SWIGLU) {
+                    const float4 u = reinterpret_cast<const float4*>(xr + K)[k4];
+                    v.x = silu_f(v.x) * u.x; v.y = silu_f(v.y) * u.y; v.z = silu_f(v.z) * u.z; v.w = silu_f(v.w) * u.w;
+                }
+                xv[i] = v;
+                ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
             }
-            reinterpret_cast<float4*>(xf)[k4] = v;
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
-        float rstd = 1.f;
         if (p.prologue == Q3T_PRO_RMSNORM) {
             const float tot = block_sum(ss, s.scratch);
-            rstd = rsqrtf(tot / (float)K + p.eps);
-        }
-        float amax = 0.f;
-        for (int k4 = tid; k4 < K4; k4 += GEMV_THREADS) {
-            float4 v = reinterpret_cast<float4*>(xf)[k4];
-            if (p.prologue == Q3T_PRO_RMSNORM) {
-                const float4 nw = reinterpret_cast<const float4*>(p.norm_w)[k4];
-                v.x = nw.x * (v.x * rstd); v.y = nw.y * (v.y * rstd); v.z = nw.z * (v.z * rstd); v.w = nw.w * (v.w * rstd);
-                reinterpret_cast<float4*>(xf)[k4] = v;
-            }
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-        }
-        amax = block_max(amax, s.scratch);
-        const float inv = amax > 0.f ? 1073741824.f / amax : 0.f;
-        const float xscale = amax * (1.f / 1073741824.f);
-        if (tid == 0) s.scratch[32 + m] = xscale;
-        for (int k4 = tid; k4 < K4; k4 += GEMV_THREADS) {   // K % 256 == 0 -> whole warps stay converged
-            const float4 v = reinterpret_cast<float4*>(xf)[k4];
-            int e[4] = {__float2int_rn(v.x * inv), __float2int_rn(v.y * inv), __float2int_rn(v.z * inv),
-                        __float2int_rn(v.w * inv)};
-            long long gs = (long long)e[0] + e[1] + e[2] + e[3];
-            uint32_t wd[4] = {0, 0, 0, 0};
+            const float rstd = rsqrtf(tot / (float)K + p.eps);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                int v0 = e[i];
-#pragma unroll
-                for (int d = 0; d < 3; ++d) {
-                    const int dg = (int)(signed char)(v0 & 0xff);
-                    wd[d] |= (uint32_t)(dg & 0xff) << (8 * i);
-                    v0 = (v0 - dg) >> 8;
+            for (int i = 0; i < GEMV_MAXV; ++i) {
+                const int k4 = tid + i * GEMV_THREADS;
+                if (k4 < K4) {
+                    const float4 nw = reinterpret_cast<const float4*>(p.norm_w)[k4];
+                    float4& v = xv[i];
+                    v.x = nw.x * (v.x * rstd); v.y = nw.y * (v.y * rstd); v.z = nw.z * (v.z * rstd); v.w = nw.w * (v.w * rstd);
                 }
-                wd[3] |= (uint32_t)(v0 & 0xff) << (8 * i);
             }
-            const int k = k4 << 2, G = k >> 6, kk = k & 63;
-            const int r = ((kk >> 5) << 1) | ((kk >> 4) & 1), t = (kk >> 2) & 3;
-            uint32_t* base = reinterpret_cast<uint32_t*>(s.xfrag + G * 32);
+        }
 #pragma unroll
-            for (int d = 0; d < 4; ++d) base[((4 * m + d) * 4 + t) * 4 + r] = wd[d];
-            // 16 consecutive lanes cover one 64-wide group
+        for (int i = 0; i < GEMV_MAXV; ++i) {
+            const int k4 = tid + i * GEMV_THREADS;   // K % 256 == 0 -> whole warps stay converged
+            if (k4 < K4) {
+                const float4 v = xv[i];
+                // block floating point: one scale per 64-wide quantisation group (16 consecutive lanes)
+                float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
-            if ((lane & 15) == 0) s.xsum[m * ngroups + G] = (float)gs * xscale;
+                for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+                const float inv = amax > 0.f ? 1073741824.f / amax : 0.f;
+                const float xscale = amax * (1.f / 1073741824.f);
+                int e[4] = {__float2int_rn(v.x * inv), __float2int_rn(v.y * inv), __float2int_rn(v.z * inv),
+                            __float2int_rn(v.w * inv)};
+                long long gs = (long long)e[0] + e[1] + e[2] + e[3];
+                uint32_t wd[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    int v0 = e[q];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int dg = (int)(signed char)(v0 & 0xff);
+                        wd[d] |= (uint32_t)(dg & 0xff) << (8 * q);
+                        v0 = (v0 - dg) >> 8;
+                    }
+                    wd[3] |= (uint32_t)(v0 & 0xff) << (8 * q);
+                }
+                const int k = k4 << 2, G = k >> 6, kk = k & 63;
+                const int r = ((kk >> 5) << 1) | ((kk >> 4) & 1), t = (kk >> 2) & 3;
+                uint32_t* base = reinterpret_cast<uint32_t*>(s.xfrag + G * 32);
+#pragma unroll
+                for (int d = 0; d < 4; ++d) base[((4 * m + d) * 4 + t) * 4 + r] = wd[d];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+                if ((lane & 15) == 0) {
+                    s.xsum[m * ngroups + G] = (float)gs * xscale;
+                    s.xscl[m * ngroups + G] = xscale;
+                }
+            }
         }
     }
     __syncthreads();
 
     // ------------------------------------------------------------------ main loop
-    const int ks = p.ks, nteams = GEMV_WARPS / ks, team = warp / ks, jw = warp % ks;
-    const int rt_begin = (int)(((long long)p.nrt * blockIdx.x) / gridDim.x);
-    const int rt_end = (int)(((long long)p.nrt * (blockIdx.x + 1)) / gridDim.x);
-    const int U = 2 * p.nkc;
-    const int g = lane >> 2, t = lane & 3, mt = t >> 1;
-    const float xscale_t = s.scratch[32 + (M == 2 ? mt : 0)];
+    const int g = lane >> 2, t = lane & 3, mt = (M == 2) ? (t >> 1) : 0;
     const float pw_lo = (t & 1) ? 65536.f : 1.f, pw_hi = pw_lo * 256.f;
+    const float* xscl = s.xscl + mt * ngroups;
+    const float* xsum = s.xsum + mt * ngroups;
 
     for (int rt0 = rt_begin; rt0 < rt_end; rt0 += nteams) {
         const int rt = rt0 + team;
@@ -167,9 +203,9 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
             const uint8_t* row_base = p.w + (size_t)rt * p.nkc * Q3T_TILE_BYTES;
             float f[4] = {0.f, 0.f, 0.f, 0.f};
             float bacc_lo = 0.f, bacc_hi = 0.f;
-            UnitRegs cur, nxt;
+            UnitRegs nxt;
             int u = jw;
-            if (u < U) load_unit(cur, row_base + (size_t)(u >> 1) * Q3T_TILE_BYTES, u & 1, lane);
+            if (rt0 != rt_begin && u < U) load_unit(cur, row_base + (size_t)(u >> 1) * Q3T_TILE_BYTES, u & 1, lane);
             for (; u < U; u += ks) {
                 const int un = u + ks;
                 if (un < U) load_unit(nxt, row_base + (size_t)(un >> 1) * Q3T_TILE_BYTES, un & 1, lane);
@@ -184,16 +220,16 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
                     imma_16832(acc, cur.q[2 * jj].x, cur.q[2 * jj].y, cur.q[2 * jj].z, cur.q[2 * jj].w, b.x, b.y);
                     imma_16832(acc, cur.q[2 * jj + 1].x, cur.q[2 * jj + 1].y, cur.q[2 * jj + 1].z,
                                cur.q[2 * jj + 1].w, b.z, b.w);
-                    const float slo = jj ? bf16hi(sw_lo) : bf16lo(sw_lo), shi = jj ? bf16hi(sw_hi) : bf16lo(sw_hi);
+                    const float xg = xscl[G];
+                    const float slo = (jj ? bf16hi(sw_lo) : bf16lo(sw_lo)) * xg;
+                    const float shi = (jj ? bf16hi(sw_hi) : bf16lo(sw_hi)) * xg;
                     f[0] = fmaf(slo, (float)acc[0], f[0]);
                     f[1] = fmaf(slo, (float)acc[1], f[1]);
                     f[2] = fmaf(shi, (float)acc[2], f[2]);
                     f[3] = fmaf(shi, (float)acc[3], f[3]);
-                    if (M == 2 || mt == 0) {
-                        const float xs = s.xsum[mt * ngroups + G];
-                        bacc_lo = fmaf(jj ? bf16hi(bw_lo) : bf16lo(bw_lo), xs, bacc_lo);
-                        bacc_hi = fmaf(jj ? bf16hi(bw_hi) : bf16lo(bw_hi), xs, bacc_hi);
-                    }
+                    const float xs = xsum[G];
+                    bacc_lo = fmaf(jj ? bf16hi(bw_lo) : bf16lo(bw_lo), xs, bacc_lo);
+                    bacc_hi = fmaf(jj ? bf16hi(bw_hi) : bf16lo(bw_hi), xs, bacc_hi);
                 }
                 if (un < U) cur = nxt;
             }
@@ -201,12 +237,13 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
             float v_hi = f[2] * pw_lo + f[3] * pw_hi;
             v_lo += __shfl_xor_sync(0xffffffffu, v_lo, 1);
             v_hi += __shfl_xor_sync(0xffffffffu, v_hi, 1);
-            res_lo = fmaf(v_lo, xscale_t, bacc_lo);
-            res_hi = fmaf(v_hi, xscale_t, bacc_hi);
+            res_lo = v_lo + bacc_lo;
+            res_hi = v_hi + bacc_hi;
         }
-        if ((t & 1) == 0 && (M == 2 || mt == 0)) {
-            s.red[(warp * 16 + g) * 2 + mt] = res_lo;
-            s.red[(warp * 16 + g + 8) * 2 + mt] = res_hi;
+        if ((t & 1) == 0 && (M == 2 || t == 0)) {
+            const int mo = t >> 1;
+            s.red[(warp * 16 + g) * 2 + mo] = res_lo;
+            s.red[(warp * 16 + g + 8) * 2 + mo] = res_hi;
         }
         __syncthreads();
         if (jw == 0 && rt < rt_end) {
@@ -227,7 +264,8 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
 
 static size_t gemv_smem_bytes(int M, int K) {
     const int ng = K / 64;
-    return (size_t)ng * 512 + sizeof(float) * (2 * ng + (size_t)M * K + GEMV_WARPS * 16 * 2 + 40);
+    (void)M;
+    return (size_t)ng * 512 + sizeof(float) * (4 * ng + GEMV_WARPS * 16 * 2 + 40);
 }
 
 static int g_num_sms = 0;

@@ -40,13 +40,16 @@ for n, k in [(4096, 2048), (2048, 2048), (12288, 2048), (2048, 6144), (3072, 204
         a.w.w, a.w.N, a.w.K, a.M, a.prologue = b.data_ptr(), n, k, 1, L.PRO_RAW
         a.x, a.x_stride, a.y, a.y_stride = x.data_ptr(), k, y.data_ptr(), n
         args.append(a)
-    st = L.stream_ptr()
-
-    def run():
+    def run_all():
+        st = L.stream_ptr()
         for a in args:
             lib.q3t_w8_gemv(C.byref(a), st)
-    ms = ev_time(run, 20) / copies
-    print(f"gemv N={n:6d} K={k:5d}  {ms*1e3:8.2f} us  {nbytes/ms/1e6:8.1f} GB/s  ({nbytes/1e6:.1f} MB)")
+    run_all(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run_all()
+    ms = ev_time(g.replay, 20) / copies
+    print(f"gemv N={n:6d} K={k:5d}  {ms*1e3:8.2f} us/launch (graph of {copies})  {nbytes/ms/1e6:8.1f} GB/s  ({nbytes/1e6:.1f} MB)")
     del blobs
 
 # ---- full-size talker step / frame
