@@ -48,15 +48,32 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
 
     const int kvh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int pos = p.pos[b], ctx = pos + 1;
-    int chunk = (ctx + p.nsplit - 1) / p.nsplit;
-    chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
-    const int s0 = split * chunk, s1 = min(ctx, s0 + chunk);
-    const bool owner = (pos >= s0 && pos < s1);
     const int* btbl = p.block_tbl + (size_t)b * p.max_pages;
     const size_t page_elems = (size_t)2 * p.Hkv * Q3T_KV_PAGE * D;
     const size_t head_off = (size_t)kvh * Q3T_KV_PAGE * D;
     const size_t v_off = (size_t)p.Hkv * Q3T_KV_PAGE * D;
+    pdl_launch_dependents();
+    {   // before waiting for the QKV GEMV: pull this CTA's K/V pages towards L2.  `pos` may still be one step
+        // stale here (it only steers a prefetch); the authoritative read happens after pdl_wait().
+        const int ctx_h = __ldcg(p.pos + b) + 1;
+        int ch = (ctx_h + p.nsplit - 1) / p.nsplit;
+        ch = (ch + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
+        const int h0 = split * ch, h1 = min(ctx_h, h0 + ch);
+        const int npg = h1 > h0 ? (h1 - 1) / Q3T_KV_PAGE - h0 / Q3T_KV_PAGE + 1 : 0;
+        for (int i = tid; i < 2 * npg; i += 128) {
+            const int pg = h0 / Q3T_KV_PAGE + (i >> 1);
+            if (pg < p.max_pages) {
+                const __nv_bfloat16* src = p.kv_pool + (size_t)btbl[pg] * page_elems + head_off + ((i & 1) ? v_off : 0);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(Q3T_KV_PAGE * D * 2) : "memory");
+            }
+        }
+    }
+    pdl_wait();
+    const int pos = __ldcg(p.pos + b), ctx = pos + 1;
+    int chunk = (ctx + p.nsplit - 1) / p.nsplit;
+    chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
+    const int s0 = split * chunk, s1 = min(ctx, s0 + chunk);
+    const bool owner = (pos >= s0 && pos < s1);
     const int qkv_dim = (p.H + 2 * p.Hkv) * D;
     const float* row = p.qkv + (size_t)b * qkv_dim;
 
@@ -203,7 +220,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
 template <int D, int REP>
 static int launch_attn_t(const AttnParams& p, cudaStream_t stream) {
     dim3 grid(p.Hkv, p.nsplit, p.B);
-    attn_decode_kernel<D, REP><<<grid, 128, 0, stream>>>(p);
+    launch_pdl(attn_decode_kernel<D, REP>, grid, dim3(128), 0, stream, p);
     Q3T_CHECK_LAUNCH("attn_decode");
     return 0;
 }

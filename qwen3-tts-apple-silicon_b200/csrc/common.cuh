@@ -11,6 +11,7 @@ namespace q3t {
 // ---- error plumbing (no exception crosses the C ABI) -----------------------------------------
 extern thread_local char g_err[512];
 extern unsigned long long g_launches;
+extern int g_use_pdl;   // programmatic dependent launch between consecutive kernels (env Q3T_PDL=0 disables)
 
 #define Q3T_CHECK_LAUNCH(name)                                                        \
     do {                                                                              \
@@ -26,6 +27,25 @@ extern unsigned long long g_launches;
     do {                                                                              \
         if (!(cond)) { snprintf(q3t::g_err, sizeof(q3t::g_err), "%s:%d: %s", __FILE__, __LINE__, msg); return 2; } \
     } while (0)
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Every kernel of the decode chain (a) lets its successor start early and (b) waits for its predecessor only
+// right before it touches activations, so the successor's weight prefetch overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_use_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // ---- warp / block reductions --------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

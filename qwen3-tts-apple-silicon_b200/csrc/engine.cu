@@ -15,6 +15,8 @@ int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       float* __restrict__ y, int H, float eps) {
     __shared__ float red[32];
+    pdl_wait();
+    pdl_launch_dependents();
     const float* xr = x + (size_t)blockIdx.x * H;
     float* yr = y + (size_t)blockIdx.x * H;
     float ss = 0.f;
@@ -25,6 +27,8 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
 }
 
 __global__ void advance_kernel(int* pos, int B, int* step) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int i = threadIdx.x;
     if (i < B) pos[i] += 1;
     if (step && i == 0) *step += 1;
@@ -37,6 +41,8 @@ __global__ void __launch_bounds__(256) next_input_kernel(const float* __restrict
                                                          int G, int H, const float* __restrict__ trailing,
                                                          int n_trailing, const int* step_p, float* x, int* codes,
                                                          int max_frames) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x, step = *step_p;
     const int* cc = cur_codes + b * G;
     const int trow = step < n_trailing - 1 ? step : n_trailing - 1;
@@ -50,7 +56,7 @@ __global__ void __launch_bounds__(256) next_input_kernel(const float* __restrict
 }
 
 int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, cudaStream_t s) {
-    rmsnorm_kernel<<<M, 256, 0, s>>>(x, w, y, H, eps);
+    launch_pdl(rmsnorm_kernel, dim3(M), dim3(256), 0, s, x, w, y, H, eps);
     Q3T_CHECK_LAUNCH("rmsnorm");
     return 0;
 }
@@ -108,7 +114,7 @@ static int talker_step(const q3t_frame_args* f, int want_logits, int bump_step, 
     if (want_logits)
         Q3T_TRY(gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr,
                           0, f->logits, f->talker_vocab, s));
-    advance_kernel<<<1, 1024, 0, s>>>(f->pos, f->B, bump_step ? f->step : nullptr);
+    launch_pdl(advance_kernel, dim3(1), dim3(1024), 0, s, f->pos, f->B, bump_step ? f->step : (int*)nullptr);
     Q3T_CHECK_LAUNCH("advance");
     return 0;
 }
@@ -145,8 +151,9 @@ static int frame(const q3t_frame_args* f, cudaStream_t s) {
                           nullptr, 0, lg, f->cp_vocab, s));
         Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));
     }
-    next_input_kernel<<<B, 256, 0, s>>>(f->codec_embedding, f->cp_embeddings_dev, f->cur_codes, G, H, f->trailing,
-                                        f->n_trailing, f->step, f->x, f->codes, f->max_frames);
+    launch_pdl(next_input_kernel, dim3(B), dim3(256), 0, s, f->codec_embedding, f->cp_embeddings_dev,
+               (const int*)f->cur_codes, G, H, f->trailing, f->n_trailing, (const int*)f->step, f->x, f->codes,
+               f->max_frames);
     Q3T_CHECK_LAUNCH("next_input");
     return talker_step(f, 1, 1, s);
 }

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
     __shared__ int sh_i[4];
     __shared__ float sh_f[2];
 
+    pdl_wait();
+    pdl_launch_dependents();
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int V = p.V;
     const int step = p.step ? *p.step : 0;
@@ -223,7 +225,7 @@ int launch_sample(const q3t_sample_args* a, cudaStream_t stream) {
     p.out_stride = a->out_stride; p.fo_stride = a->fo_stride; p.fo_step_stride = a->fo_step_stride;
     p.forced = a->forced; p.own = a->own;
     p.done = a->done;
-    sample_kernel<<<a->B, SAMPLE_THREADS, 0, stream>>>(p);
+    launch_pdl(sample_kernel, dim3(a->B), dim3(SAMPLE_THREADS), 0, stream, p);
     Q3T_CHECK_LAUNCH("sample");
     return 0;
 }

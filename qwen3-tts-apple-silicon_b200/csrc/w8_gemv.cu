@@ -20,7 +20,7 @@
 
 namespace q3t {
 
-constexpr int GEMV_THREADS = 512;
+constexpr int GEMV_THREADS = 256;   // half an SM: the PDL successor's CTA co-resides and prefetches
 constexpr int GEMV_WARPS = GEMV_THREADS / 32;
 
 struct GemvParams {
@@ -68,7 +68,7 @@ struct GemvSmem {
     float* scratch; // [32] reductions
 };
 
-constexpr int GEMV_MAXV = 4;   // float4 per thread per row: K <= 4*4*512 = 8192
+constexpr int GEMV_MAXV = 8;   // float4 per thread per row: K <= 8*4*256 = 8192
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
     const int rt_end = (int)(((long long)p.nrt * (blockIdx.x + 1)) / gridDim.x);
     const int U = 2 * p.nkc;
 
+    pdl_launch_dependents();   // the next kernel may start its own weight prefetch now
     // ---- start the HBM stream before anything else: this CTA's row tiles are one contiguous slab; ask the
     // L2 for all of it now so the weight traffic overlaps the activation prologue and the compute below
     if (tid < 32) {
@@ -116,6 +117,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
         for (int i = tid; i < ngroups * 32; i += GEMV_THREADS)
             if (((i & 31) >> 2) >= 4) s.xfrag[i] = make_uint4(0, 0, 0, 0);
     }
+    pdl_wait();   // activations written by the predecessor are visible from here on
 #pragma unroll
     for (int m = 0; m < M; ++m) {
         const float* xr = p.x + m * p.x_stride;
@@ -291,7 +293,7 @@ int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream) {
     p.y = a->y; p.y_stride = a->y_stride;
     const int grid = p.nrt < num_sms() ? p.nrt : num_sms();
     const int per_cta = (p.nrt + grid - 1) / grid;
-    int ks = 16;
+    int ks = GEMV_WARPS;
     while (ks > 1 && (GEMV_WARPS / ks) < per_cta) ks >>= 1;
     while (ks > 2 * p.nkc) ks >>= 1;
     p.ks = ks;
@@ -302,8 +304,8 @@ int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream) {
         cudaFuncSetAttribute(w8_gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
-    if (a->M == 1) w8_gemv_kernel<1><<<grid, GEMV_THREADS, smem, stream>>>(p);
-    else w8_gemv_kernel<2><<<grid, GEMV_THREADS, smem, stream>>>(p);
+    if (a->M == 1) launch_pdl(w8_gemv_kernel<1>, dim3(grid), dim3(GEMV_THREADS), smem, stream, p);
+    else launch_pdl(w8_gemv_kernel<2>, dim3(grid), dim3(GEMV_THREADS), smem, stream, p);
     Q3T_CHECK_LAUNCH("w8_gemv");
     return 0;
 }
