@@ -141,12 +141,33 @@ typedef struct {
     int hidden, n_layers, n_heads, n_kv_heads, head_dim, inter;
     float eps;
     const q3t_layer* layers_host;   /* HOST array [n_layers] */
+    const q3t_layer* layers_dev;    /* the same array in DEVICE memory (persistent stack-pass kernel) */
     const float* final_norm;
     const float* inv_freq;          /* [head_dim/2] */
     void* kv_pool; long long kv_layer_stride_bytes;   /* bf16 pages, per-layer stride */
     const int* block_tbl; int max_pages;
     int attn_nsplit;
 } q3t_stack;
+
+/* ---------------------------------------------------------------------------------------------
+ * Persistent stack pass (batch 1): ONE cooperative launch = every layer of a dense Qwen3 stack for one token
+ * + final RMSNorm + optional head GEMV.  Weights stream through a TMA/mbarrier shared-memory ring; phases are
+ * separated by grid-wide barriers (csrc/mega.cu).  Replaces 5*n_layers+2 launches of the kernels above.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    q3t_stack stack;
+    q3t_w8 head;            /* head.w == NULL: no head GEMV */
+    const int* pos;         /* [1] position of the token being fed */
+    const float* x_in;      /* [hidden] */
+    float* hidden_out;      /* [hidden] post-final-norm, or NULL */
+    float* logits_out;      /* [head.N] */
+    float* work;            /* q3t_stack_pass_work_floats() floats */
+    int* counters;          /* [n_kv_heads] zero-initialised once */
+    unsigned int* barrier;  /* [1] */
+} q3t_stack_pass_args;
+
+int q3t_stack_pass(const q3t_stack_pass_args* a, void* stream);
+long long q3t_stack_pass_work_floats(const q3t_stack* st, int head_n);
 
 typedef struct {
     int B;
@@ -187,6 +208,9 @@ typedef struct {
     const float* trailing; /* [B, n_trailing, H]; row min(step, n_trailing-1) is added (last row = tts_pad) */
     int n_trailing;
     const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
+    /* persistent-kernel path (used when use_mega != 0 and B == 1) */
+    int use_mega;
+    float* mega_work; unsigned int* mega_barrier;
 } q3t_frame_args;
 
 /* one talker forward for the token currently in `x` (prefill token or decode step), logits optional */

@@ -10,6 +10,7 @@ namespace q3t {
 int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream);
 int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream);
 int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
+int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream);
 
 // ---- small kernels --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -106,14 +107,32 @@ static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x,
     return 0;
 }
 
+// batch-1 persistent path: one cooperative launch for the whole stack (+ final norm + head)
+static int mega_pass(const q3t_frame_args* f, const q3t_stack& st, const q3t_w8* head, const int* pos, const float* x_in,
+                     float* hidden_out, float* logits_out, cudaStream_t s) {
+    q3t_stack_pass_args a;
+    memset(&a, 0, sizeof(a));
+    a.stack = st;
+    if (head) a.head = *head;
+    a.pos = pos; a.x_in = x_in; a.hidden_out = hidden_out; a.logits_out = logits_out;
+    a.work = f->mega_work; a.counters = f->attn_counters; a.barrier = f->mega_barrier;
+    return launch_stack_pass(&a, s);
+}
+
+static inline bool mega_on(const q3t_frame_args* f) { return f->use_mega && f->B == 1 && f->mega_work && f->mega_barrier; }
+
 static int talker_step(const q3t_frame_args* f, int want_logits, int bump_step, cudaStream_t s) {
     const q3t_stack& t = f->talker;
     Q3T_REQUIRE(f->B >= 1 && f->B <= 1024, "talker_step: batch out of range");
-    Q3T_TRY(stack_forward(f, t, f->x, f->pos, s));
-    Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
-    if (want_logits)
-        Q3T_TRY(gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr,
-                          0, f->logits, f->talker_vocab, s));
+    if (mega_on(f)) {
+        Q3T_TRY(mega_pass(f, t, want_logits ? &f->codec_head : nullptr, f->pos, f->x, f->hidden, f->logits, s));
+    } else {
+        Q3T_TRY(stack_forward(f, t, f->x, f->pos, s));
+        Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
+        if (want_logits)
+            Q3T_TRY(gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0,
+                              nullptr, 0, f->logits, f->talker_vocab, s));
+    }
     launch_pdl(advance_kernel, dim3(1), dim3(1024), 0, s, f->pos, f->B, bump_step ? f->step : (int*)nullptr);
     Q3T_CHECK_LAUNCH("advance");
     return 0;
@@ -139,16 +158,22 @@ static int frame(const q3t_frame_args* f, cudaStream_t s) {
     // code 0 from the talker logits
     Q3T_TRY(sample_into(f, f->logits, f->talker_vocab, f->talker_sp, f->seen, 0, f->done, s));
     // code predictor: position 0 = projected talker hidden, position 1 = projected embedding of code 0
+    const bool mega = mega_on(f);
     Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, f->hidden, H, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->xc, Hc, s));
-    Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
+    if (mega) Q3T_TRY(mega_pass(f, c, nullptr, f->cp_pos, f->xc, nullptr, nullptr, s));
+    else Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
     for (int g = 0; g < G - 1; ++g) {
         const float* table = g == 0 ? f->codec_embedding : f->cp_embeddings_host[g - 1];
         Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, table, 0, nullptr, 0.f, f->cur_codes + g, G, H, 0, nullptr, 0, f->xc,
                           Hc, s));
-        Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
         float* lg = f->keep_cp_logits ? f->cp_logits + (size_t)g * B * f->cp_vocab : f->cp_logits;
-        Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
-                          nullptr, 0, lg, f->cp_vocab, s));
+        if (mega) {
+            Q3T_TRY(mega_pass(f, c, &f->cp_heads_host[g], f->cp_pos + (size_t)(g + 1) * B, f->xc, nullptr, lg, s));
+        } else {
+            Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
+            Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
+                              nullptr, 0, lg, f->cp_vocab, s));
+        }
         Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));
     }
     launch_pdl(next_input_kernel, dim3(B), dim3(256), 0, s, f->codec_embedding, f->cp_embeddings_dev,

@@ -41,7 +41,8 @@ class TalkerEngine:
     """Talker + code predictor on one GPU for a fixed batch of `B` lock-step sequences."""
 
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", batch: int = 1, max_frames: int = 512,
-                 max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1):
+                 max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1,
+                 use_mega: bool = True):
         self.lib = L.load()
         self.cfg, self.dev, self.B = cfg, torch.device(device), batch
         self.max_frames, self.max_ctx, self.max_trailing = max_frames, max_ctx, max_trailing
@@ -87,6 +88,9 @@ class TalkerEngine:
             st.hidden, st.n_layers, st.n_heads, st.n_kv_heads = sc.hidden_size, sc.num_layers, sc.num_heads, sc.num_kv_heads
             st.head_dim, st.inter, st.eps = sc.head_dim, sc.intermediate_size, sc.rms_norm_eps
             st.layers_host = C.cast(layers, C.POINTER(L.Layer))
+            raw = bytes(memoryview(layers).cast("B"))
+            ldev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+            st.layers_dev = self.keep(ldev)
             st.final_norm = self.keep(fp(prefix + ".norm.weight"))
             st.inv_freq = self.keep(_rope_inv_freq(sc.head_dim, sc.rope_theta, dev))
             layer_elems = n_pages * 2 * sc.num_kv_heads * L.KV_PAGE * sc.head_dim
@@ -159,6 +163,13 @@ class TalkerEngine:
         fa.seen, fa.done = self.keep(self.seen), self.keep(self.done)
         fa.trailing, fa.n_trailing = self.keep(self.trailing), max_trailing
         fa.forced_codes = 0
+        # persistent stack-pass kernel (batch 1): workspace + grid barrier word
+        nwork = max(self.lib.q3t_stack_pass_work_floats(C.byref(self.talker_stack), t.vocab_size),
+                    self.lib.q3t_stack_pass_work_floats(C.byref(self.cp_stack), c.vocab_size))
+        self.mega_work = torch.zeros(int(nwork), **f32)
+        self.mega_barrier = torch.zeros(4, **i32)
+        fa.mega_work, fa.mega_barrier = self.keep(self.mega_work), self.keep(self.mega_barrier)
+        fa.use_mega = int(use_mega and self.B == 1)
         self.set_sampling()
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.use_graphs = True
@@ -183,6 +194,11 @@ class TalkerEngine:
         cs.do_sample = int(do_sample if cp_do_sample is None else cp_do_sample)
         cs.temperature, cs.top_k, cs.top_p, cs.repetition_penalty = cp_temperature, cp_top_k, cp_top_p, 1.0
         cs.min_new_tokens, cs.suppress_lo, cs.suppress_hi, cs.eos_id, cs.seed = 0, -1, -1, -1, seed + 1
+        self._graphs = {}
+
+    def set_mega(self, on: bool):
+        """Switch between the persistent stack-pass kernel (batch 1) and the one-kernel-per-contraction path."""
+        self.fa.use_mega = int(on and self.B == 1)
         self._graphs = {}
 
     def set_forced(self, forced: Optional[torch.Tensor]):

@@ -89,6 +89,25 @@ def test_free_running_greedy_codes_bit_exact(small_setup):
     assert torch.equal(codes_d[:safe], codes_o[:safe]), f"greedy codes differ before frame {safe}"
 
 
+def test_persistent_kernel_and_multikernel_paths_agree(small_setup):
+    """The batch-1 persistent stack-pass kernel and the one-kernel-per-contraction path implement the same arithmetic
+    (different but fixed summation orders): same greedy codes, logits within fp32 noise."""
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 11, 21)
+    pre, tr = oracle.build_prefill(ids, speaker="aiden", language="english")
+    e = model.engine
+    e.set_sampling(do_sample=False)
+    out = {}
+    for mega in (True, False):
+        e.set_mega(mega)
+        codes = model.generate_codes(pre.cuda(), tr.cuda(), 10).cpu().long()
+        out[mega] = (codes, e.logits[0].clone().cpu())
+    e.set_mega(True)
+    assert torch.equal(out[True][0], out[False][0])
+    assert _rel(out[True][1], out[False][1]) < 1e-4
+    assert torch.equal(out[True][0][:6], oracle.generate(pre, tr, 6))
+
+
 def test_streaming_trailing_text_and_graph_replay_equals_eager(small_setup):
     cfg, ws, model, oracle = small_setup
     ids = _text_ids(cfg, 9, 4)
