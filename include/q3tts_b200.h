@@ -164,6 +164,7 @@ typedef struct {
     float* work;            /* q3t_stack_pass_work_floats() floats */
     int* counters;          /* [n_kv_heads] zero-initialised once */
     unsigned int* barrier;  /* [1] */
+    unsigned long long* timing;  /* optional [grid][1024] globaltimer stamps (profiling aid), or NULL */
 } q3t_stack_pass_args;
 
 int q3t_stack_pass(const q3t_stack_pass_args* a, void* stream);

@@ -42,7 +42,16 @@ struct MegaParams {
     float* part_qkv; float* part_o; float* part_gu; float* part_down; float* part_head;   // [MG_MAXSLOT][N]
     float* attn_out; float* attn_work; int* attn_counters; int attn_nsplit;
     unsigned int* bar;
+    unsigned long long* timing;                  // optional: [gridDim][MG_NSTAMP] globaltimer stamps of thread 0
 };
+constexpr int MG_NSTAMP = 1024;
+
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define MG_STAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < MG_NSTAMP) p.timing[(size_t)blockIdx.x * MG_NSTAMP + st.nstamp++] = gtimer(); } while (0)
 
 // ---- tile geometry ------------------------------------------------------------------------------------------------
 struct Geo {
@@ -195,7 +204,7 @@ __device__ __forceinline__ void tile_dot(const MegaSmem& s, const uint8_t* tile,
     out_hi = v_hi + bacc_hi;
 }
 
-struct ConsumerState { uint32_t tile_i; unsigned int bar_target; };
+struct ConsumerState { uint32_t tile_i; unsigned int bar_target; int nstamp; };
 
 // GEMV phase (consumers): tiles of this CTA out of the ring -> per-CTA partial rows in global `part`.
 __device__ __forceinline__ void gemv_phase(const MegaSmem& s, const Geo& geo, float* part, ConsumerState& st, int cta) {
@@ -453,7 +462,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) stack_pass_kernel(const MegaPar
 
     // =============================== consumers ================================================================
     ConsumerState st;
-    st.tile_i = 0; st.bar_target = 0;
+    st.tile_i = 0; st.bar_target = 0; st.nstamp = 0;
+    MG_STAMP();
     const int H = p.hidden, H4 = H >> 2;
     // residual stream: private copy per CTA
     for (int k4 = tid; k4 < H4; k4 += MG_CTHREADS)
@@ -497,11 +507,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) stack_pass_kernel(const MegaPar
         const q3t_layer& L = p.layers[l];
         // ---- QKV
         norm_prologue(l > 0 ? p.part_down : nullptr, &g_down, L.input_norm, nullptr);
+        MG_STAMP();
         gemv_phase(s, g_qkv, p.part_qkv, st, cta);
+        MG_STAMP();
         grid_sync(p, st);
+        MG_STAMP();
         // ---- attention
         attn_phase<D, REP>(p, s, g_qkv, l, cta);
+        MG_STAMP();
         grid_sync(p, st);
+        MG_STAMP();
         // ---- O projection: x = attention output
         {
             const int K4 = q_dim >> 2;
@@ -509,12 +524,18 @@ __global__ void __launch_bounds__(MG_THREADS, 1) stack_pass_kernel(const MegaPar
                 if (k4 < K4) emit_digits(s, __ldcg(reinterpret_cast<const float4*>(p.attn_out) + k4), k4, lane);
             cbar();
         }
+        MG_STAMP();
         gemv_phase(s, g_o, p.part_o, st, cta);
+        MG_STAMP();
         grid_sync(p, st);
+        MG_STAMP();
         // ---- gate/up: resid += O ; x = rmsnorm(resid)
         norm_prologue(p.part_o, &g_o, L.post_norm, nullptr);
+        MG_STAMP();
         gemv_phase(s, g_gu, p.part_gu, st, cta);
+        MG_STAMP();
         grid_sync(p, st);
+        MG_STAMP();
         // ---- down: x = silu(gate) * up
         {
             const int I = p.inter, K4 = I >> 2;
@@ -530,8 +551,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) stack_pass_kernel(const MegaPar
             }
             cbar();
         }
+        MG_STAMP();
         gemv_phase(s, g_down, p.part_down, st, cta);
+        MG_STAMP();
         grid_sync(p, st);
+        MG_STAMP();
     }
     // ---- final norm (+ head)
     norm_prologue(p.part_down, &g_down, p.final_norm, p.hidden_out);
@@ -588,7 +612,7 @@ int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream) {
     {   // a row tile may straddle at most MG_MAXSLOT CTAs
         const int geo[5][2] = {{qkv_n, st.hidden}, {st.hidden, st.n_heads * st.head_dim}, {2 * st.inter, st.hidden},
                                {st.hidden, st.inter}, {a->head.w ? a->head.N : 16, st.hidden}};
-        for (int i = 0; i < 5; ++i) {
+        for (int i = 0; i < (a->head.w ? 5 : 4); ++i) {
             const int nkc = geo[i][1] / 256, T = (geo[i][0] / 16) * nkc, G = T < grid ? T : grid;
             const int per = T / G;
             Q3T_REQUIRE((nkc - 1 + per - 1) / per + 1 <= MG_MAXSLOT, "stack_pass: row tile straddles too many CTAs");
@@ -611,7 +635,7 @@ int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream) {
     p.part_head = ws; ws += (size_t)MG_MAXSLOT * (p.has_head ? a->head.N : 0);
     p.attn_out = ws; ws += (size_t)st.n_heads * st.head_dim;
     p.attn_work = ws;
-    p.attn_counters = a->counters; p.attn_nsplit = st.attn_nsplit; p.bar = a->barrier;
+    p.attn_counters = a->counters; p.attn_nsplit = st.attn_nsplit; p.bar = a->barrier; p.timing = a->timing;
     const int rep = st.n_heads / st.n_kv_heads;
     if (rep == 2) return launch_mega_t<128, 2>(p, grid, stream);
     if (rep == 1) return launch_mega_t<128, 1>(p, grid, stream);

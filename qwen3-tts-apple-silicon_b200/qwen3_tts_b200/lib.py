@@ -71,7 +71,7 @@ class FrameArgs(C.Structure):
 
 class StackPassArgs(C.Structure):
     _fields_ = [("stack", Stack), ("head", W8), ("pos", vp), ("x_in", vp), ("hidden_out", vp), ("logits_out", vp),
-                ("work", vp), ("counters", vp), ("barrier", vp)]
+                ("work", vp), ("counters", vp), ("barrier", vp), ("timing", vp)]
 
 
 class TapGemmArgs(C.Structure):
