@@ -10,7 +10,7 @@ objs=(); pids=()
 mkdir -p "$here/build"
 for f in glue w8_gemv attn_decode sampler engine codec mega; do
   src="$here/$f.cu"; obj="$here/build/$f.o"
-  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$here/common.cuh" -nt "$obj" ] || [ "$here/../../include/q3tts_b200.h" -nt "$obj" ]; then
+  if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$here/common.cuh" -nt "$obj" ] || [ "$here/sampler.cuh" -nt "$obj" ] || [ "$here/../../include/q3tts_b200.h" -nt "$obj" ]; then
     "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" &
     pids+=($!)
   fi
