@@ -45,7 +45,8 @@ unsigned long long q3t_launch_count(void);
  *   y[m, :] = epilogue( W8 . prologue(x[m, :]) )
  * prologue: RAW            x is [M, K]
  *           RMSNORM        x is [M, K]; x * rsqrt(mean(x^2)+eps) * norm_w      (mx.fast.rms_norm)
- *           SWIGLU         x is [M, 2K]; silu(x[:, :K]) * x[:, K:]
+ *           SWIGLU         x is [M, 2K] with gate/up interleaved in blocks of 8 (x[16j+r] = gate[8j+r],
+ *                          x[16j+8+r] = up[8j+r], r < 8: the row order of the fused gate_up matrix); silu(gate) * up
  * gather  : if `gather_idx` != NULL, row m of x is x + gather_idx[m*gather_idx_stride] * gather_row_stride
  * epilogue: (+ lin_bias[N]) -> act (0 none, 1 SiLU) -> (+ resid[m, :])   ; y may alias resid
  * ------------------------------------------------------------------------------------------- */
@@ -151,8 +152,10 @@ typedef struct {
 
 /* ---------------------------------------------------------------------------------------------
  * Persistent stack pass (batch 1): ONE cooperative launch = every layer of a dense Qwen3 stack for one token
- * + final RMSNorm + optional head GEMV.  Weights stream through a TMA/mbarrier shared-memory ring; phases are
- * separated by grid-wide barriers (csrc/mega.cu).  Replaces 5*n_layers+2 launches of the kernels above.
+ * + final RMSNorm + optional head GEMV (csrc/frame_ll.cu).  Weights stream through a TMA/mbarrier shared-memory
+ * ring; activations cross CTAs as 64-bit {value, phase tag} words (no grid barrier).  Replaces 5*n_layers+2
+ * launches of the kernels above.  In matrices handed to this kernel the fused gate/up rows are interleaved in
+ * blocks of 8 (rows 16j..16j+7 = gate rows 8j.., rows 16j+8..16j+15 = the matching up rows).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     q3t_stack stack;
@@ -161,14 +164,15 @@ typedef struct {
     const float* x_in;      /* [hidden] */
     float* hidden_out;      /* [hidden] post-final-norm, or NULL */
     float* logits_out;      /* [head.N] */
-    float* work;            /* q3t_stack_pass_work_floats() floats */
-    int* counters;          /* [n_kv_heads] zero-initialised once */
-    unsigned int* barrier;  /* [1] */
-    unsigned long long* timing;  /* optional [grid][1024] globaltimer stamps (profiling aid), or NULL */
+    void* ll_work;          /* exchange buffers, q3t_ll_work_bytes() bytes, zero-initialised once */
+    long long ll_work_bytes;
+    unsigned int* ll_state; /* [2] zero-initialised once: phase-tag counter (persists across launches), error code */
+    unsigned long long* timing;  /* optional [grid][2048] globaltimer stamps (profiling aid), or NULL */
 } q3t_stack_pass_args;
 
 int q3t_stack_pass(const q3t_stack_pass_args* a, void* stream);
-long long q3t_stack_pass_work_floats(const q3t_stack* st, int head_n);
+/* workspace size for the persistent kernels; `cp` may be NULL (stack pass only) */
+long long q3t_ll_work_bytes(const q3t_stack* talker, const q3t_stack* cp, int head_max);
 
 typedef struct {
     int B;
@@ -209,9 +213,11 @@ typedef struct {
     const float* trailing; /* [B, n_trailing, H]; row min(step, n_trailing-1) is added (last row = tts_pad) */
     int n_trailing;
     const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
-    /* persistent-kernel path (used when use_mega != 0 and B == 1) */
+    /* persistent-kernel path (used when use_mega != 0 and B == 1): the whole frame is ONE launch (csrc/frame_ll.cu) */
     int use_mega;
-    float* mega_work; unsigned int* mega_barrier;
+    const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */
+    void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
+    unsigned long long* ll_timing;  /* optional profiling stamps, or NULL */
 } q3t_frame_args;
 
 /* one talker forward for the token currently in `x` (prefill token or decode step), logits optional */

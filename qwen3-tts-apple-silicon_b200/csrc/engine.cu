@@ -11,6 +11,7 @@ int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream);
 int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream);
 int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
 int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream);
+int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream);
 
 // ---- small kernels --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -107,7 +108,7 @@ static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x,
     return 0;
 }
 
-// batch-1 persistent path: one cooperative launch for the whole stack (+ final norm + head)
+// batch-1 persistent path: one cooperative launch for the whole talker stack (+ final norm + head)
 static int mega_pass(const q3t_frame_args* f, const q3t_stack& st, const q3t_w8* head, const int* pos, const float* x_in,
                      float* hidden_out, float* logits_out, cudaStream_t s) {
     q3t_stack_pass_args a;
@@ -115,11 +116,11 @@ static int mega_pass(const q3t_frame_args* f, const q3t_stack& st, const q3t_w8*
     a.stack = st;
     if (head) a.head = *head;
     a.pos = pos; a.x_in = x_in; a.hidden_out = hidden_out; a.logits_out = logits_out;
-    a.work = f->mega_work; a.counters = f->attn_counters; a.barrier = f->mega_barrier;
+    a.ll_work = f->ll_work; a.ll_work_bytes = f->ll_work_bytes; a.ll_state = f->ll_state; a.timing = f->ll_timing;
     return launch_stack_pass(&a, s);
 }
 
-static inline bool mega_on(const q3t_frame_args* f) { return f->use_mega && f->B == 1 && f->mega_work && f->mega_barrier; }
+static inline bool mega_on(const q3t_frame_args* f) { return f->use_mega && f->B == 1 && f->ll_work && f->ll_state; }
 
 static int talker_step(const q3t_frame_args* f, int want_logits, int bump_step, cudaStream_t s) {
     const q3t_stack& t = f->talker;
@@ -155,25 +156,21 @@ static int sample_into(const q3t_frame_args* f, const float* logits, int V, cons
 static int frame(const q3t_frame_args* f, cudaStream_t s) {
     const q3t_stack& c = f->cp;
     const int B = f->B, G = f->n_groups, H = f->talker.hidden, Hc = c.hidden;
+    // batch 1: the whole frame (sampler, 16 code-predictor passes, next input, talker step) is ONE persistent launch
+    if (mega_on(f)) return launch_frame_ll(f, s);
     // code 0 from the talker logits
     Q3T_TRY(sample_into(f, f->logits, f->talker_vocab, f->talker_sp, f->seen, 0, f->done, s));
     // code predictor: position 0 = projected talker hidden, position 1 = projected embedding of code 0
-    const bool mega = mega_on(f);
     Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, f->hidden, H, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->xc, Hc, s));
-    if (mega) Q3T_TRY(mega_pass(f, c, nullptr, f->cp_pos, f->xc, nullptr, nullptr, s));
-    else Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
+    Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
     for (int g = 0; g < G - 1; ++g) {
         const float* table = g == 0 ? f->codec_embedding : f->cp_embeddings_host[g - 1];
         Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, table, 0, nullptr, 0.f, f->cur_codes + g, G, H, 0, nullptr, 0, f->xc,
                           Hc, s));
         float* lg = f->keep_cp_logits ? f->cp_logits + (size_t)g * B * f->cp_vocab : f->cp_logits;
-        if (mega) {
-            Q3T_TRY(mega_pass(f, c, &f->cp_heads_host[g], f->cp_pos + (size_t)(g + 1) * B, f->xc, nullptr, lg, s));
-        } else {
-            Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
-            Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
-                              nullptr, 0, lg, f->cp_vocab, s));
-        }
+        Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
+        Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
+                          nullptr, 0, lg, f->cp_vocab, s));
         Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));
     }
     launch_pdl(next_input_kernel, dim3(B), dim3(256), 0, s, f->codec_embedding, f->cp_embeddings_dev,

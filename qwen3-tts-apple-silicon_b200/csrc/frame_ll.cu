@@ -1,0 +1,1002 @@
+// Persistent data-flow kernel for batch-1 decode: ONE cooperative launch runs either
+//   * a token through a whole dense Qwen3 stack (talker prefill token / talker decode step), or
+//   * a whole 80 ms FRAME of the generation hot loop: sample code 0 -> 16 code-predictor passes (15 sampled codes) ->
+//     next-input embedding sum -> talker decode step -> logits of the next frame                         (K7)
+// Replaces the per-frame body of mlx_audio's Model.generate loop (reference call site sessions/custom.py:163-170;
+// structural cousin transformers qwen3_omni_moe/modeling_qwen3_omni_moe.py:3243-3279).
+//
+// Why it looks like this (measurements: tools/ubench.cu -> profiles/r01_ubench.txt):
+//   * a grid-wide barrier on 148 CTAs costs 1.8 us (atomic + fence + poll, cooperative-groups grid.sync() included) and
+//     the data still has to be read afterwards; a layer has five dependent contractions, so barriers alone would cost
+//     more than the 8.2 us a layer's 53.7 MB of W8 weights need at the HBM roofline.  Here there are NO barriers and NO
+//     fences between phases: every activation crosses CTAs as a 64-bit {fp32 value, 32-bit phase tag} word written with
+//     one st.relaxed.gpu and polled with ld.relaxed.gpu until the tag matches (the "LL" protocol of collective
+//     libraries, applied inside one GPU).  One store->poll hop is ~0.3 us, a full all-to-all exchange ~1.0 us.
+//   * weights never wait for activations: a producer warp per CTA streams this CTA's tiles of EVERY matrix of the
+//     launch, in program order, through a 32-slot shared-memory ring with cp.async.bulk (TMA, `UBLKCP`) + mbarrier
+//     full/empty pairs (four issuing lanes: one lane tops out at ~186 cycles per 4352-byte tile);
+//   * 16 consumer warps run the IMMA dequant-dot (uint8 codes x signed base-256 digits of the block-fixed-point
+//     activation, exact int32 sums per quantisation group - see w8_gemv.cu) out of the ring;
+//   * row tiles (16 output rows x all of K) are dealt to CTAs whole, so every output element has exactly one producer and
+//     epilogues (bias, SwiGLU) run before the value is published; the residual stream is replicated per CTA in shared
+//     memory, so residual adds never touch global memory;
+//   * attention: (kv head, 128-token split) units on the first n_kv*nsplit CTAs; old K/V rows are in registers before
+//     the q/k/v words arrive; partial (m, l, acc) records are LL words merged by every consumer of the O projection.
+// Re-use of an exchange buffer is safe without extra synchronisation because every phase is an all-to-all dependency:
+// a CTA can only be one phase ahead of the slowest CTA, and each buffer is rewritten five or more phases later.
+#include "sampler.cuh"
+
+namespace q3t {
+
+typedef unsigned long long u64;
+
+constexpr int LL_CWARPS = 16;
+constexpr int LL_CTHREADS = LL_CWARPS * 32;      // 512 consumers
+constexpr int LL_THREADS = LL_CTHREADS + 32;     // + producer warp
+constexpr int LL_NSLOT = 32;                     // ring slots of one 4352-byte tile
+constexpr int LL_PLANES = 4;                     // producer lanes issuing TMA copies
+constexpr int LL_MAXK = 6144;                    // largest contraction length (talker intermediate size)
+constexpr int LL_MAXH = 2048;                    // largest hidden size (one float4 per consumer thread)
+constexpr int LL_MAXT = 64;                      // max tiles of one matrix per CTA
+constexpr int LL_MAXSPLIT = 16;                  // attention splits per kv head
+constexpr int LL_REC = 130;                      // attention record: 128 acc + m + l
+constexpr int LL_SPIN_LIMIT = 1 << 22;           // watchdog: a poll that spins this long (~1 s) aborts the launch
+constexpr int LL_NSTAMP = 2048;
+
+enum { LL_MODE_STACK = 0, LL_MODE_FRAME = 1 };
+enum { EPI_RAW = 0, EPI_SWIGLU = 1 };
+
+struct LLStack {
+    const q3t_layer* layers;                     // DEVICE array
+    int n_layers, hidden, n_heads, n_kv, head_dim, inter;
+    float eps;
+    const float* final_norm; const float* inv_freq;
+    __nv_bfloat16* kv_pool; long long kv_layer_stride;   // elements
+    const int* block_tbl;
+};
+
+struct LLParams {
+    int mode;
+    LLStack talker, cp;
+    // exchange buffers (64-bit {value, tag} words)
+    u64 *x_qkv, *x_attn, *x_o, *x_act, *x_down, *x_head, *x_proj;
+    unsigned int* state;                         // [0] tag base (persists across launches), [1] error code
+    unsigned long long* timing;                  // optional [grid][LL_NSTAMP]
+    // ---- stack mode
+    int which;                                   // 0 = talker stack, 1 = code-predictor stack
+    const int* pos; const float* x_in; float* hidden_out; float* logits_out; q3t_w8 head;
+    // ---- frame mode
+    q3t_w8 codec_head, cp_proj; const q3t_w8* cp_heads;          // DEVICE array [G-1]
+    const float* codec_embedding; const float* const* cp_embeddings;   // DEVICE array [G-1]
+    int emb_dim, talker_vocab, cp_vocab, n_groups;
+    q3t_sampling talker_sp, cp_sp;
+    float* x; float* hidden; float* logits; float* cp_logits; int keep_cp_logits;
+    int* pos_talker; int* step; int* cur_codes; int* codes; int* own_codes; int max_frames;
+    unsigned int* seen; int* done;
+    const float* trailing; int n_trailing; const int* forced;
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(LL_CTHREADS) : "memory"); }
+
+__device__ __forceinline__ void ll_fail(unsigned int* state, unsigned int code) {
+    atomicExch(state + 1, code);
+    __threadfence_system();
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* state, unsigned int code) {
+    int spins = 0;
+    while (!mbar_try(bar, parity))
+        if (++spins > LL_SPIN_LIMIT) ll_fail(state, code);
+}
+
+// ---- LL words -----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ll_st(u64* p, float v, uint32_t tag) {
+    const u64 w = ((u64)tag << 32) | (u64)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ void ll_ld2(const u64* p, u64& a, u64& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ float ll_val(u64 w) { return __uint_as_float((uint32_t)w); }
+__device__ __forceinline__ bool ll_ok(u64 w, uint32_t tag) { return (uint32_t)(w >> 32) == tag; }
+
+// NV float4s (4 consecutive words each) at p[i]; all loads are issued before the first tag is looked at
+template <int NV>
+__device__ __forceinline__ void ll_ld4n(const u64* const (&p)[NV], const bool (&on)[NV], uint32_t tag, float4 (&out)[NV],
+                                        unsigned int* state) {
+    u64 w[NV][4];
+    bool ok[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        ok[i] = !on[i];
+        if (on[i]) { ll_ld2(p[i], w[i][0], w[i][1]); ll_ld2(p[i] + 2, w[i][2], w[i][3]); }
+    }
+    int spins = 0;
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (!ok[i]) ok[i] = ll_ok(w[i][0], tag) && ll_ok(w[i][1], tag) && ll_ok(w[i][2], tag) && ll_ok(w[i][3], tag);
+            all = all && ok[i];
+        }
+        if (all) break;
+        if (++spins > LL_SPIN_LIMIT) ll_fail(state, 0x100u | (tag & 0xffu));
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            if (!ok[i]) { ll_ld2(p[i], w[i][0], w[i][1]); ll_ld2(p[i] + 2, w[i][2], w[i][3]); }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        out[i] = on[i] ? make_float4(ll_val(w[i][0]), ll_val(w[i][1]), ll_val(w[i][2]), ll_val(w[i][3])) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float4 ll_ld4(const u64* p, uint32_t tag, unsigned int* state) {
+    const u64* const pp[1] = {p};
+    const bool on[1] = {true};
+    float4 o[1];
+    ll_ld4n<1>(pp, on, tag, o, state);
+    return o[0];
+}
+
+__device__ __forceinline__ void imma_16832_ll(int (&c)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+        : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+// ---- shared memory --------------------------------------------------------------------------------------------------------
+struct LLSmem {
+    uint8_t* ring;          // [LL_NSLOT][4352]
+    uint4* xfrag;           // [LL_MAXK/64][32] digit planes in mma B-fragment order (lanes 16..31 stay zero); sampler scratch
+    float* xsum;            // [LL_MAXK/64]
+    float* xscl;            // [LL_MAXK/64]
+    float* resid;           // [LL_MAXH]
+    float* xnext;           // [LL_MAXH] next talker input, accumulated while the code predictor runs
+    float* tile_out;        // [LL_MAXT][16]
+    float* att;             // attention scratch: q [2][128], new k/v [2][128], partials [16][2][130]
+    float* red;             // [64]
+    float* cs;              // [64] cos(pos * inv_freq)
+    float* sn;              // [64]
+    int* ibuf;              // [64] sampler scratch ints
+    uint64_t* full;         // [LL_NSLOT]
+    uint64_t* empty;        // [LL_NSLOT]
+};
+constexpr size_t LL_ATT_FLOATS = 4 * 128 + 16 * 2 * LL_REC;
+constexpr size_t LL_SMEM_BYTES = (size_t)LL_NSLOT * Q3T_TILE_BYTES + (size_t)(LL_MAXK / 64) * 512 + 2 * (LL_MAXK / 64) * 4 +
+                                 2 * LL_MAXH * 4 + LL_MAXT * 16 * 4 + LL_ATT_FLOATS * 4 + 64 * 4 + 128 * 4 + 64 * 4 +
+                                 2 * LL_NSLOT * 8 + 128;
+
+struct CState {
+    uint32_t seq;           // tiles consumed so far (ring sequence number)
+    uint32_t gen;           // phase tag counter
+    int nstamp;
+};
+
+#define LL_STAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP) p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = gtimer(); } while (0)
+
+__device__ __forceinline__ float cblock_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    cbar();
+    if (lane == 0) red[wid] = v;
+    cbar();
+    float r = (lane < LL_CWARPS) ? red[lane] : 0.f;
+    return warp_sum(r);
+}
+
+// v = 4 consecutive inputs starting at k = 4*k4 -> signed base-256 digit planes + per-group sum/scale.
+// Whole warps call this together (16 lanes share a 64-wide quantisation group).
+__device__ __forceinline__ void emit_digits(const LLSmem& s, float4 v, int k4, int lane) {
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float inv = amax > 0.f ? 1073741824.f / amax : 0.f;
+    const float xscale = amax * (1.f / 1073741824.f);
+    const int e0 = __float2int_rn(v.x * inv), e1 = __float2int_rn(v.y * inv), e2 = __float2int_rn(v.z * inv), e3 = __float2int_rn(v.w * inv);
+    // e = sum_i d_i 256^i with d_i in [-128,127]:  bytes of (e + 0x80808080) are d_i + 128; xor 0x80 gives the s8 encoding
+    const uint32_t u0 = ((uint32_t)e0 + 0x80808080u) ^ 0x80808080u, u1 = ((uint32_t)e1 + 0x80808080u) ^ 0x80808080u;
+    const uint32_t u2 = ((uint32_t)e2 + 0x80808080u) ^ 0x80808080u, u3 = ((uint32_t)e3 + 0x80808080u) ^ 0x80808080u;
+    const uint32_t t0 = __byte_perm(u0, u1, 0x5140), t1 = __byte_perm(u2, u3, 0x5140);
+    const uint32_t t2 = __byte_perm(u0, u1, 0x7362), t3 = __byte_perm(u2, u3, 0x7362);
+    uint32_t wd[4];
+    wd[0] = __byte_perm(t0, t1, 0x5410); wd[1] = __byte_perm(t0, t1, 0x7632);
+    wd[2] = __byte_perm(t2, t3, 0x5410); wd[3] = __byte_perm(t2, t3, 0x7632);
+    const int k = k4 << 2, G = k >> 6, kk = k & 63;
+    const int r = ((kk >> 5) << 1) | ((kk >> 4) & 1), t = (kk >> 2) & 3;
+    uint32_t* base = reinterpret_cast<uint32_t*>(s.xfrag + G * 32);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) base[(d * 4 + t) * 4 + r] = wd[d];
+    float gs = ((float)e0 + (float)e1) + ((float)e2 + (float)e3);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
+    if ((lane & 15) == 0) { s.xsum[G] = gs * xscale; s.xscl[G] = xscale; }
+}
+
+// One 4352-byte tile out of the ring against the digit planes: 16 output rows (partial over this tile's 256 inputs).
+__device__ __forceinline__ void tile_dot(const LLSmem& s, const uint8_t* tile, int kc, int lane, float& out_lo, float& out_hi) {
+    const int g = lane >> 2, t = lane & 3;
+    const uint4 mlo = *reinterpret_cast<const uint4*>(tile + 4096 + g * 16);
+    const uint4 mhi = *reinterpret_cast<const uint4*>(tile + 4096 + (g + 8) * 16);
+    const uint32_t slo_w[2] = {mlo.x, mlo.y}, shi_w[2] = {mhi.x, mhi.y}, blo_w[2] = {mlo.z, mlo.w}, bhi_w[2] = {mhi.z, mhi.w};
+    float f[4] = {0.f, 0.f, 0.f, 0.f}, bacc_lo = 0.f, bacc_hi = 0.f;
+#pragma unroll
+    for (int j4 = 0; j4 < 4; ++j4) {
+        const int G = kc * 4 + j4;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + 0) * 512 + lane * 16);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + 1) * 512 + lane * 16);
+        const uint4 b = s.xfrag[G * 32 + lane];
+        int acc[4] = {0, 0, 0, 0};
+        imma_16832_ll(acc, a0, b.x, b.y);
+        imma_16832_ll(acc, a1, b.z, b.w);
+        const float xg = s.xscl[G], xs = s.xsum[G];
+        const uint32_t sw_lo = slo_w[j4 >> 1], sw_hi = shi_w[j4 >> 1], bw_lo = blo_w[j4 >> 1], bw_hi = bhi_w[j4 >> 1];
+        const float slo = ((j4 & 1) ? bf16hi(sw_lo) : bf16lo(sw_lo)) * xg;
+        const float shi = ((j4 & 1) ? bf16hi(sw_hi) : bf16lo(sw_hi)) * xg;
+        f[0] = fmaf(slo, (float)acc[0], f[0]);
+        f[1] = fmaf(slo, (float)acc[1], f[1]);
+        f[2] = fmaf(shi, (float)acc[2], f[2]);
+        f[3] = fmaf(shi, (float)acc[3], f[3]);
+        bacc_lo = fmaf((j4 & 1) ? bf16hi(bw_lo) : bf16lo(bw_lo), xs, bacc_lo);
+        bacc_hi = fmaf((j4 & 1) ? bf16hi(bw_hi) : bf16lo(bw_hi), xs, bacc_hi);
+    }
+    const float pw_lo = (t & 1) ? 65536.f : 1.f, pw_hi = pw_lo * 256.f;
+    float v_lo = f[0] * pw_lo + f[1] * pw_hi, v_hi = f[2] * pw_lo + f[3] * pw_hi;
+    v_lo += __shfl_xor_sync(0xffffffffu, v_lo, 1);
+    v_hi += __shfl_xor_sync(0xffffffffu, v_hi, 1);
+    out_lo = v_lo + bacc_lo;   // valid in lanes with t == 0 (columns 0..3 = the four digits of the one batch row)
+    out_hi = v_hi + bacc_hi;
+}
+
+__device__ __forceinline__ void row_range(int nrt, int cta, int grid, int& rb, int& re) {
+    rb = (int)(((long long)nrt * cta) / grid);
+    re = (int)(((long long)nrt * (cta + 1)) / grid);
+}
+
+// ---- GEMV phase (consumers): this CTA's row tiles out of the ring -> epilogue -> LL words (+ optional plain copy) --------
+__device__ __forceinline__ void gemv_phase(const LLParams& p, const LLSmem& s, CState& st, const q3t_w8& W, int epi,
+                                           u64* ll_out, float* plain_out, uint32_t tag) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nkc = W.K >> 8;
+    int rb, re;
+    row_range(W.N >> 4, blockIdx.x, gridDim.x, rb, re);
+    const int nt = (re - rb) * nkc;
+    for (int j = warp; j < nt; j += LL_CWARPS) {
+        const uint32_t i = st.seq + j, slot = i % LL_NSLOT, par = (i / LL_NSLOT) & 1;
+        mbar_wait(smem_u32(&s.full[slot]), par, p.state, 0x200u);
+        float lo, hi;
+        tile_dot(s, s.ring + (size_t)slot * Q3T_TILE_BYTES, j % nkc, lane, lo, hi);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.empty[slot]));
+        if ((lane & 3) == 0) { s.tile_out[j * 16 + (lane >> 2)] = lo; s.tile_out[j * 16 + (lane >> 2) + 8] = hi; }
+    }
+    st.seq += nt;
+    cbar();
+    const int nloc = re - rb;
+    if (epi == EPI_SWIGLU) {
+        // rows 0..7 of a tile are gate rows, rows 8..15 the matching up rows (weights interleaved at load)
+        for (int i = tid; i < nloc * 8; i += LL_CTHREADS) {
+            const int rtl = i >> 3, r = i & 7;
+            float g = 0.f, u = 0.f;
+            for (int kc = 0; kc < nkc; ++kc) { g += s.tile_out[(rtl * nkc + kc) * 16 + r]; u += s.tile_out[(rtl * nkc + kc) * 16 + r + 8]; }
+            ll_st(ll_out + (size_t)(rb + rtl) * 8 + r, silu_f(g) * u, tag);
+        }
+    } else {
+        for (int i = tid; i < nloc * 16; i += LL_CTHREADS) {
+            const int rtl = i >> 4, r = i & 15, n = (rb + rtl) * 16 + r;
+            float v = 0.f;
+            for (int kc = 0; kc < nkc; ++kc) v += s.tile_out[(rtl * nkc + kc) * 16 + r];
+            if (W.lin_bias) v += W.lin_bias[n];
+            ll_st(ll_out + n, v, tag);
+            if (plain_out) plain_out[n] = v;
+        }
+    }
+}
+
+// ---- prologues: phase input -> digit planes in shared memory ---------------------------------------------------------------
+// resid (+= LL words of the previous projection) -> RMSNorm -> digits
+__device__ __forceinline__ void pro_norm(const LLParams& p, const LLSmem& s, const u64* ll_add, uint32_t tag_add,
+                                         const float* norm_w, float* hidden_out, int H, float eps) {
+    const int tid = threadIdx.x, lane = tid & 31, H4 = H >> 2;
+    const bool on = tid < H4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+        v = reinterpret_cast<float4*>(s.resid)[tid];
+        if (ll_add) {
+            const float4 a = ll_ld4(ll_add + 4 * tid, tag_add, p.state);
+            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            reinterpret_cast<float4*>(s.resid)[tid] = v;
+        }
+    }
+    const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    const float rstd = rsqrtf(cblock_sum(ss, s.red) / (float)H + eps);
+    if (on) {
+        const float4 nw = reinterpret_cast<const float4*>(norm_w)[tid];
+        v.x = nw.x * (v.x * rstd); v.y = nw.y * (v.y * rstd); v.z = nw.z * (v.z * rstd); v.w = nw.w * (v.w * rstd);
+        if (hidden_out && blockIdx.x == 0) reinterpret_cast<float4*>(hidden_out)[tid] = v;
+        emit_digits(s, v, tid, lane);
+    }
+    cbar();
+}
+
+// LL words (already activated values) -> digits; K <= LL_MAXK
+__device__ __forceinline__ void pro_ll(const LLParams& p, const LLSmem& s, const u64* ll, uint32_t tag, int K) {
+    const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
+    constexpr int NV = LL_MAXK / 4 / LL_CTHREADS;   // 3
+    const u64* pp[NV]; bool on[NV]; float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { const int k4 = tid + i * LL_CTHREADS; on[i] = k4 < K4; pp[i] = ll + 4 * (size_t)k4; }
+    ll_ld4n<NV>(pp, on, tag, v, p.state);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        if (on[i]) emit_digits(s, v[i], tid + i * LL_CTHREADS, lane);
+    cbar();
+}
+
+// plain fp32 vector in global memory (constant table row or a vector written by an earlier launch) -> digits;
+// optionally accumulated into xnext (the next talker input)
+__device__ __forceinline__ void pro_plain(const LLSmem& s, const float* x, int K, int accumulate) {
+    const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
+    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(x) + k4);
+        if (accumulate == 1) reinterpret_cast<float4*>(s.xnext)[k4] = v;
+        else if (accumulate == 2) {
+            float4 a = reinterpret_cast<float4*>(s.xnext)[k4];
+            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+            reinterpret_cast<float4*>(s.xnext)[k4] = a;
+        }
+        emit_digits(s, v, k4, lane);
+    }
+    cbar();
+}
+
+// attention partial records of every split -> merged head outputs -> digits  (input of the O projection)
+__device__ __forceinline__ void pro_attn(const LLParams& p, const LLSmem& s, const u64* ll_attn, uint32_t tag, int q_dim,
+                                         int nsplit) {
+    const int tid = threadIdx.x, lane = tid & 31, K4 = q_dim >> 2;
+    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) {
+        const int head = (k4 << 2) >> 7, d = (k4 << 2) & 127;
+        const u64* rec0 = ll_attn + (size_t)head * LL_MAXSPLIT * LL_REC;
+        float M = -INFINITY, L = 0.f;
+        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int sp0 = 0; sp0 < nsplit; sp0 += 2) {
+            const bool two = sp0 + 1 < nsplit;
+            const u64* r0 = rec0 + (size_t)sp0 * LL_REC;
+            const u64* r1 = r0 + LL_REC;
+            u64 a0[4], a1[4], m0, l0, m1 = 0, l1 = 0;
+            int spins = 0;
+            for (;;) {
+                ll_ld2(r0 + d, a0[0], a0[1]); ll_ld2(r0 + d + 2, a0[2], a0[3]); ll_ld2(r0 + 128, m0, l0);
+                if (two) { ll_ld2(r1 + d, a1[0], a1[1]); ll_ld2(r1 + d + 2, a1[2], a1[3]); ll_ld2(r1 + 128, m1, l1); }
+                bool ok = ll_ok(a0[0], tag) && ll_ok(a0[1], tag) && ll_ok(a0[2], tag) && ll_ok(a0[3], tag) && ll_ok(m0, tag) && ll_ok(l0, tag);
+                if (two) ok = ok && ll_ok(a1[0], tag) && ll_ok(a1[1], tag) && ll_ok(a1[2], tag) && ll_ok(a1[3], tag) && ll_ok(m1, tag) && ll_ok(l1, tag);
+                if (ok) break;
+                if (++spins > LL_SPIN_LIMIT) ll_fail(p.state, 0x300u);
+            }
+            {
+                const float ms = ll_val(m0), Mn = fmaxf(M, ms);
+                const float c = __expf(M - Mn), w = __expf(ms - Mn);
+                L = L * c + ll_val(l0) * w;
+                A.x = A.x * c + ll_val(a0[0]) * w; A.y = A.y * c + ll_val(a0[1]) * w;
+                A.z = A.z * c + ll_val(a0[2]) * w; A.w = A.w * c + ll_val(a0[3]) * w;
+                M = Mn;
+            }
+            if (two) {
+                const float ms = ll_val(m1), Mn = fmaxf(M, ms);
+                const float c = __expf(M - Mn), w = __expf(ms - Mn);
+                L = L * c + ll_val(l1) * w;
+                A.x = A.x * c + ll_val(a1[0]) * w; A.y = A.y * c + ll_val(a1[1]) * w;
+                A.z = A.z * c + ll_val(a1[2]) * w; A.w = A.w * c + ll_val(a1[3]) * w;
+                M = Mn;
+            }
+        }
+        const float il = 1.f / L;
+        emit_digits(s, make_float4(A.x * il, A.y * il, A.z * il, A.w * il), k4, lane);
+    }
+    cbar();
+}
+
+// ---- attention geometry (uniform over the grid) -----------------------------------------------------------------------------
+__device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int& chunk, int& nsplit) {
+    int maxsplit = grid / n_kv;
+    if (maxsplit > LL_MAXSPLIT) maxsplit = LL_MAXSPLIT;
+    if (maxsplit < 1) maxsplit = 1;
+    chunk = 128;
+    if (ctx > chunk * maxsplit) {
+        chunk = (ctx + maxsplit - 1) / maxsplit;
+        chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
+    }
+    nsplit = (ctx + chunk - 1) / chunk;
+}
+
+// ---- attention phase: q/k RMSNorm + RoPE + KV-page write + split-KV GQA decode attention -> LL records ----------------------
+template <int REP>
+__device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, const LLStack& S, int layer, int pos,
+                                           const u64* ll_qkv, uint32_t tag_qkv, u64* ll_attn, uint32_t tag_out) {
+    constexpr int D = 128, EPL = 8, PRE = 4;
+    int chunk, nsplit;
+    attn_geometry(pos + 1, S.n_kv, gridDim.x, chunk, nsplit);
+    const int cta = blockIdx.x;
+    if (cta >= S.n_kv * nsplit) return;
+    const int kvh = cta % S.n_kv, split = cta / S.n_kv;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hw = lane >> 4, sl = lane & 15, hwid = warp * 2 + hw;
+    const int ctx = pos + 1, s0 = split * chunk, s1 = min(ctx, s0 + chunk);
+    const bool owner = (pos >= s0 && pos < s1);
+    float* q_s = s.att;                           // [REP][D], pre-scaled by 1/sqrt(D)
+    float* new_s = s.att + 2 * D;                 // [2][D]: k, v of the new token as stored (bf16-rounded)
+    float* part_s = s.att + 4 * D;                // [16 warps][REP][LL_REC]
+    __nv_bfloat16* pool = S.kv_pool + (size_t)layer * S.kv_layer_stride;
+    const size_t page_elems = (size_t)2 * S.n_kv * Q3T_KV_PAGE * D;
+    const size_t head_off = (size_t)kvh * Q3T_KV_PAGE * D;
+    const size_t v_off = (size_t)S.n_kv * Q3T_KV_PAGE * D;
+    const int n_iter = (s1 - s0 + 31) >> 5;
+
+    // 1. rows already in the cache: into registers before anything that depends on this step's QKV output
+    uint4 kreg[PRE], vreg[PRE];
+#pragma unroll
+    for (int i = 0; i < PRE; ++i) {
+        const int tok = s0 + hwid + 32 * i;
+        kreg[i] = make_uint4(0, 0, 0, 0); vreg[i] = make_uint4(0, 0, 0, 0);
+        if (tok < s1 && tok < pos) {
+            const __nv_bfloat16* kp = pool + (size_t)S.block_tbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
+                                      (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
+            kreg[i] = __ldcg(reinterpret_cast<const uint4*>(kp));
+            vreg[i] = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
+        }
+    }
+    // 2. q heads of this kv head (+ k, v of the new token on the split that owns it)
+    if (warp < REP + 2) {
+        const bool is_q = warp < REP, is_k = warp == REP;
+        if (is_q || owner) {
+            const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
+            const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
+            float x[4] = {xv.x, xv.y, xv.z, xv.w};
+            if (is_q || is_k) {
+                float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
+                ss = warp_sum(ss);
+                const float rstd = rsqrtf(ss / (float)D + S.eps);
+                const float* nw = is_q ? S.layers[layer].q_norm : S.layers[layer].k_norm;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) x[e] = nw[lane * 4 + e] * (x[e] * rstd);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float other = __shfl_xor_sync(0xffffffffu, x[e], 16);
+                    const float cs = s.cs[(lane & 15) * 4 + e], sn = s.sn[(lane & 15) * 4 + e];
+                    x[e] = (lane < 16) ? (x[e] * cs - other * sn) : (x[e] * cs + other * sn);
+                }
+            }
+            if (is_q) {
+                const float sc = rsqrtf((float)D);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) q_s[warp * D + lane * 4 + e] = x[e] * sc;
+            } else {
+                __nv_bfloat16 hb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { hb[e] = __float2bfloat16_rn(x[e]); new_s[(is_k ? 0 : D) + lane * 4 + e] = __bfloat162float(hb[e]); }
+                __nv_bfloat16* dst = pool + (size_t)S.block_tbl[pos / Q3T_KV_PAGE] * page_elems + head_off + (is_k ? 0 : v_off) +
+                                     (size_t)(pos % Q3T_KV_PAGE) * D + lane * 4;
+                *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hb);
+            }
+        }
+    }
+    cbar();
+    // 3. online softmax per half-warp (one token per half-warp per iteration)
+    float m_run[REP], l_run[REP], acc[REP][EPL], qr[REP][EPL];
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+        m_run[r] = -INFINITY; l_run[r] = 0.f;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) { acc[r][e] = 0.f; qr[r][e] = q_s[r * D + sl * EPL + e]; }
+    }
+    auto step = [&](int tok, uint4 kr, uint4 vr) {
+        const bool has = tok < s1;
+        float k0[EPL], v0[EPL];
+        if (has && tok == pos) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) { k0[e] = new_s[sl * EPL + e]; v0[e] = new_s[D + sl * EPL + e]; }
+        } else {
+            const uint32_t* ku = reinterpret_cast<const uint32_t*>(&kr);
+            const uint32_t* vu = reinterpret_cast<const uint32_t*>(&vr);
+#pragma unroll
+            for (int i = 0; i < EPL / 2; ++i) {
+                k0[2 * i] = bf16lo(ku[i]); k0[2 * i + 1] = bf16hi(ku[i]);
+                v0[2 * i] = bf16lo(vu[i]); v0[2 * i + 1] = bf16hi(vu[i]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < REP; ++r) {
+            float sa = 0.f;
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) sa = fmaf(qr[r][e], k0[e], sa);
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
+            if (has) {
+                const float mn = fmaxf(m_run[r], sa);
+                const float corr = __expf(m_run[r] - mn), pa = __expf(sa - mn);
+                l_run[r] = l_run[r] * corr + pa;
+#pragma unroll
+                for (int e = 0; e < EPL; ++e) acc[r][e] = fmaf(pa, v0[e], acc[r][e] * corr);
+                m_run[r] = mn;
+            }
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < PRE; ++i)
+        if (i < n_iter) step(s0 + hwid + 32 * i, kreg[i], vreg[i]);
+    for (int i = PRE; i < n_iter; ++i) {
+        const int tok = s0 + hwid + 32 * i;
+        uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
+        if (tok < s1 && tok < pos) {
+            const __nv_bfloat16* kp = pool + (size_t)S.block_tbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
+                                      (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
+            kr = __ldcg(reinterpret_cast<const uint4*>(kp));
+            vr = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
+        }
+        step(tok, kr, vr);
+    }
+    // 4. merge the two half-warps of a warp, then the 16 warps through shared memory
+#pragma unroll
+    for (int r = 0; r < REP; ++r) {
+        const float mo = __shfl_xor_sync(0xffffffffu, m_run[r], 16), lo = __shfl_xor_sync(0xffffffffu, l_run[r], 16);
+        const float mn = fmaxf(m_run[r], mo);
+        const float wa = (m_run[r] == -INFINITY) ? 0.f : __expf(m_run[r] - mn), wb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            const float ao = __shfl_xor_sync(0xffffffffu, acc[r][e], 16);
+            acc[r][e] = acc[r][e] * wa + ao * wb;
+        }
+        l_run[r] = l_run[r] * wa + lo * wb;
+        m_run[r] = mn;
+        if (hw == 0) {
+#pragma unroll
+            for (int e = 0; e < EPL; ++e) part_s[(warp * REP + r) * LL_REC + sl * EPL + e] = acc[r][e];
+            if (sl == 0) { part_s[(warp * REP + r) * LL_REC + D] = m_run[r]; part_s[(warp * REP + r) * LL_REC + D + 1] = l_run[r]; }
+        }
+    }
+    cbar();
+    for (int i = tid; i < REP * D; i += LL_CTHREADS) {
+        const int r = i / D, d = i % D;
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < LL_CWARPS; ++w) M = fmaxf(M, part_s[(w * REP + r) * LL_REC + D]);
+        float L = 0.f, A = 0.f;
+#pragma unroll
+        for (int w = 0; w < LL_CWARPS; ++w) {
+            const float mh = part_s[(w * REP + r) * LL_REC + D];
+            const float wt = (mh == -INFINITY) ? 0.f : __expf(mh - M);
+            L = fmaf(part_s[(w * REP + r) * LL_REC + D + 1], wt, L);
+            A = fmaf(part_s[(w * REP + r) * LL_REC + d], wt, A);
+        }
+        u64* rec = ll_attn + ((size_t)(kvh * REP + r) * LL_MAXSPLIT + split) * LL_REC;
+        ll_st(rec + d, A, tag_out);
+        if (d == 0) { ll_st(rec + D, M, tag_out); ll_st(rec + D + 1, L, tag_out); }
+    }
+}
+
+// ---- one token through a dense stack (consumers) ------------------------------------------------------------------------------
+// resid must hold the stack input (or zeros when first_add carries it as LL words).  On return: if want_final, the digit
+// planes hold the final-norm output (and hidden_out is written by CTA 0); tag_last = tag of the last down projection.
+struct StackIO {
+    const u64* first_add; uint32_t first_tag;
+    bool want_final; float* hidden_out;
+};
+
+__device__ __forceinline__ void stack_consume(const LLParams& p, const LLSmem& s, CState& st, const LLStack& S, int pos,
+                                              const StackIO& io) {
+    const int tid = threadIdx.x;
+    const int q_dim = S.n_heads * S.head_dim, rep = S.n_heads / S.n_kv;
+    // RoPE table of this position (rotate_half convention, fp32 cos/sin as the oracle)
+    if (tid < S.head_dim / 2) {
+        float sn, cs;
+        sincosf((float)pos * S.inv_freq[tid], &sn, &cs);
+        s.cs[tid] = cs; s.sn[tid] = sn;
+    }
+    int chunk, nsplit;
+    attn_geometry(pos + 1, S.n_kv, gridDim.x, chunk, nsplit);
+    const u64* add = io.first_add;
+    uint32_t add_tag = io.first_tag;
+    for (int l = 0; l < S.n_layers; ++l) {
+        const q3t_layer& L = S.layers[l];
+        // ---- QKV
+        pro_norm(p, s, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
+        LL_STAMP();
+        const uint32_t t_qkv = ++st.gen;
+        gemv_phase(p, s, st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
+        LL_STAMP();
+        // ---- attention (first n_kv*nsplit CTAs)
+        const uint32_t t_att = ++st.gen;
+        if (rep == 2) attn_phase<2>(p, s, S, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
+        else attn_phase<1>(p, s, S, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
+        LL_STAMP();
+        // ---- O projection
+        pro_attn(p, s, p.x_attn, t_att, q_dim, nsplit);
+        LL_STAMP();
+        const uint32_t t_o = ++st.gen;
+        gemv_phase(p, s, st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
+        LL_STAMP();
+        // ---- gate/up (+ SwiGLU in the epilogue)
+        pro_norm(p, s, p.x_o, t_o, L.post_norm, nullptr, S.hidden, S.eps);
+        LL_STAMP();
+        const uint32_t t_act = ++st.gen;
+        gemv_phase(p, s, st, L.gate_up, EPI_SWIGLU, p.x_act, nullptr, t_act);
+        LL_STAMP();
+        // ---- down
+        pro_ll(p, s, p.x_act, t_act, S.inter);
+        LL_STAMP();
+        const uint32_t t_down = ++st.gen;
+        gemv_phase(p, s, st, L.down, EPI_RAW, p.x_down, nullptr, t_down);
+        LL_STAMP();
+        add = p.x_down; add_tag = t_down;
+    }
+    if (io.want_final) pro_norm(p, s, add, add_tag, S.final_norm, io.hidden_out, S.hidden, S.eps);
+}
+
+// ---- producer side: the same program, streaming instead of computing ---------------------------------------------------------
+struct Producer {
+    const LLSmem& s; unsigned int* state; int lane; uint32_t seq;
+    __device__ __forceinline__ void stream(const q3t_w8& W) {
+        const int nkc = W.K >> 8;
+        int rb, re;
+        row_range(W.N >> 4, blockIdx.x, gridDim.x, rb, re);
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(W.w) + (size_t)rb * nkc * Q3T_TILE_BYTES;
+        const int nt = (re - rb) * nkc;
+        for (int t = 0; t < nt; ++t, ++seq, src += Q3T_TILE_BYTES) {
+            if ((int)(seq % LL_PLANES) != lane) continue;
+            const uint32_t slot = seq % LL_NSLOT, par = (seq / LL_NSLOT) & 1;
+            mbar_wait(smem_u32(&s.empty[slot]), par ^ 1, state, 0x400u);
+            const uint32_t fb = smem_u32(&s.full[slot]);
+            mbar_expect_tx(fb, Q3T_TILE_BYTES);
+            tma_load_1d(smem_u32(s.ring + (size_t)slot * Q3T_TILE_BYTES), src, Q3T_TILE_BYTES, fb);
+        }
+    }
+    __device__ __forceinline__ void stack(const LLStack& S) {
+        for (int l = 0; l < S.n_layers; ++l) {
+            const q3t_layer& L = S.layers[l];
+            stream(L.qkv); stream(L.o); stream(L.gate_up); stream(L.down);
+        }
+    }
+};
+
+// ---- in-kernel sampler (every CTA computes the same choice; CTA 0 records it) ------------------------------------------------
+// scores come from plain logits (previous launch) or from LL words of the head GEMV of this launch
+__device__ __forceinline__ int sample_here(const LLParams& p, const LLSmem& s, const float* plain, const u64* ll, uint32_t tag,
+                                           int V, const q3t_sampling& sp, const unsigned int* seen, int step, int g) {
+    const int tid = threadIdx.x;
+    float* sc = reinterpret_cast<float*>(s.xfrag);            // [V]  (aliases the digit planes: re-zeroed below)
+    float* pe = sc + SAMPLE_MAXV;                              // [V]
+    unsigned short* cand = reinterpret_cast<unsigned short*>(pe + SAMPLE_MAXV);   // [V]
+    SampleScratch scr;
+    scr.sc = sc; scr.pe = pe; scr.cand = cand;
+    scr.hist = reinterpret_cast<unsigned int*>(cand + SAMPLE_MAXV);                  // [256]
+    scr.redf = s.red; scr.redi = s.ibuf; scr.sh_i = s.ibuf + 32;
+    const int V4 = V >> 2;
+    for (int k4 = tid; k4 < V4; k4 += LL_CTHREADS) {
+        float4 v;
+        if (plain) v = __ldcg(reinterpret_cast<const float4*>(plain) + k4);
+        else v = ll_ld4(ll + 4 * (size_t)k4, tag, p.state);
+        const int i = k4 << 2;
+        sc[i] = sample_score(v.x, i, sp, seen, step);
+        sc[i + 1] = sample_score(v.y, i + 1, sp, seen, step);
+        sc[i + 2] = sample_score(v.z, i + 2, sp, seen, step);
+        sc[i + 3] = sample_score(v.w, i + 3, sp, seen, step);
+    }
+    cbar();
+    const float u = sp.do_sample ? hash_uniform(sp.seed, step, g, 0) : 0.f;
+    const int choice = sample_core<LL_CTHREADS>(scr, V, sp, u, tid, [] { cbar(); });
+    // the scratch lived in the digit planes: lanes 16..31 of every group must read as zero again
+    for (int i = tid; i < (LL_MAXK / 64) * 16; i += LL_CTHREADS) s.xfrag[(i >> 4) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
+    cbar();
+    return choice;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LLSmem s;
+    {
+        unsigned char* q = smem_raw;
+        s.ring = q; q += (size_t)LL_NSLOT * Q3T_TILE_BYTES;
+        s.xfrag = reinterpret_cast<uint4*>(q); q += (size_t)(LL_MAXK / 64) * 512;
+        s.xsum = reinterpret_cast<float*>(q); q += (LL_MAXK / 64) * 4;
+        s.xscl = reinterpret_cast<float*>(q); q += (LL_MAXK / 64) * 4;
+        s.resid = reinterpret_cast<float*>(q); q += LL_MAXH * 4;
+        s.xnext = reinterpret_cast<float*>(q); q += LL_MAXH * 4;
+        s.tile_out = reinterpret_cast<float*>(q); q += LL_MAXT * 16 * 4;
+        s.att = reinterpret_cast<float*>(q); q += LL_ATT_FLOATS * 4;
+        s.red = reinterpret_cast<float*>(q); q += 64 * 4;
+        s.cs = reinterpret_cast<float*>(q); q += 64 * 4;
+        s.sn = reinterpret_cast<float*>(q); q += 64 * 4;
+        s.ibuf = reinterpret_cast<int*>(q); q += 64 * 4;
+        s.full = reinterpret_cast<uint64_t*>(q); q += LL_NSLOT * 8;
+        s.empty = reinterpret_cast<uint64_t*>(q);
+    }
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < LL_NSLOT; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < (LL_MAXK / 64) * 32; i += LL_THREADS) s.xfrag[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const int G = p.n_groups;
+
+    if (warp == LL_CWARPS) {
+        // =========================== producer ================================================================
+        if (lane < LL_PLANES) {
+            Producer pr{s, p.state, lane, 0u};
+            if (p.mode == LL_MODE_STACK) {
+                pr.stack(p.which ? p.cp : p.talker);
+                if (p.head.w) pr.stream(p.head);
+            } else {
+                pr.stream(p.cp_proj); pr.stack(p.cp);
+                for (int g = 0; g < G - 1; ++g) { pr.stream(p.cp_proj); pr.stack(p.cp); pr.stream(p.cp_heads[g]); }
+                pr.stack(p.talker); pr.stream(p.codec_head);
+            }
+        }
+        return;
+    }
+
+    // =============================== consumers ================================================================
+    CState st;
+    st.seq = 0; st.nstamp = 0;
+    st.gen = *reinterpret_cast<volatile unsigned int*>(p.state);
+    LL_STAMP();
+    if (p.mode == LL_MODE_STACK) {
+        const LLStack& S = p.which ? p.cp : p.talker;
+        const int pos = __ldcg(p.pos);
+        for (int k4 = tid; k4 < (S.hidden >> 2); k4 += LL_CTHREADS)
+            reinterpret_cast<float4*>(s.resid)[k4] = __ldcg(reinterpret_cast<const float4*>(p.x_in) + k4);
+        cbar();
+        StackIO io{nullptr, 0u, p.hidden_out != nullptr || p.head.w != nullptr, p.hidden_out};
+        stack_consume(p, s, st, S, pos, io);
+        if (p.head.w) {
+            const uint32_t t_head = ++st.gen;
+            gemv_phase(p, s, st, p.head, EPI_RAW, p.x_head, p.logits_out, t_head);
+        }
+        LL_STAMP();
+    } else {
+        const int step = __ldcg(p.step), pos_t = __ldcg(p.pos_talker);
+        const int H = p.talker.hidden, Hc = p.cp.hidden, E = p.emb_dim;
+        const long long fo = (long long)step * G;             // offset of this frame in forced / own / codes
+        const bool rec = (cta == 0 && tid == 0);
+        // ---- code 0 from the talker logits of the previous launch
+        int code = sample_here(p, s, p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, 0);
+        if (rec) {
+            if (p.own_codes && step < p.max_frames) p.own_codes[fo] = code;
+        }
+        if (p.forced) code = p.forced[fo];
+        if (rec) {
+            p.cur_codes[0] = code;
+            if (step < p.max_frames) p.codes[fo] = code;
+            if (p.done && code == p.talker_sp.eos_id) p.done[0] = 1;
+        }
+        const int code0 = code;
+        LL_STAMP();
+        // ---- code predictor: position 0 = projected talker hidden
+        auto cp_pass = [&](const float* src, int src_dim, int accumulate, int pos, const q3t_w8* head, int g) -> int {
+            pro_plain(s, src, src_dim, accumulate);
+            const uint32_t t_proj = ++st.gen;
+            gemv_phase(p, s, st, p.cp_proj, EPI_RAW, p.x_proj, nullptr, t_proj);
+            for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS) reinterpret_cast<float4*>(s.resid)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+            cbar();
+            StackIO io{p.x_proj, t_proj, head != nullptr, nullptr};
+            stack_consume(p, s, st, p.cp, pos, io);
+            if (!head) return 0;
+            const uint32_t t_head = ++st.gen;
+            float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g * p.cp_vocab : p.cp_logits) : nullptr;
+            gemv_phase(p, s, st, *head, EPI_RAW, p.x_head, lg, t_head);
+            int c = sample_here(p, s, nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g + 1);
+            if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo + g + 1] = c;
+            if (p.forced) c = p.forced[fo + g + 1];
+            if (rec) {
+                p.cur_codes[g + 1] = c;
+                if (step < p.max_frames) p.codes[fo + g + 1] = c;
+            }
+            return c;
+        };
+        cp_pass(p.hidden, H, 0, 0, nullptr, 0);
+        LL_STAMP();
+        for (int g = 0; g < G - 1; ++g) {
+            const float* row = (g == 0 ? p.codec_embedding : p.cp_embeddings[g - 1]) + (size_t)code * E;
+            code = cp_pass(row, E, g == 0 ? 1 : 2, g + 1, &p.cp_heads[g], g);
+            LL_STAMP();
+        }
+        // ---- next talker input: running sum (+ last code's row) + trailing text row   (order g = 0..15, then text)
+        {
+            const float* last = p.cp_embeddings[G - 2] + (size_t)code * E;
+            const int trow = step < p.n_trailing - 1 ? step : p.n_trailing - 1;
+            const float* tr = p.trailing + (size_t)trow * H;
+            for (int k4 = tid; k4 < (H >> 2); k4 += LL_CTHREADS) {
+                float4 a = reinterpret_cast<float4*>(s.xnext)[k4];
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(last) + k4);
+                const float4 c = __ldcg(reinterpret_cast<const float4*>(tr) + k4);
+                a.x = (a.x + b.x) + c.x; a.y = (a.y + b.y) + c.y; a.z = (a.z + b.z) + c.z; a.w = (a.w + b.w) + c.w;
+                reinterpret_cast<float4*>(s.resid)[k4] = a;
+                if (cta == 0) reinterpret_cast<float4*>(p.x)[k4] = a;
+            }
+            cbar();
+        }
+        // ---- talker decode step
+        StackIO io{nullptr, 0u, true, p.hidden};
+        stack_consume(p, s, st, p.talker, pos_t, io);
+        const uint32_t t_head = ++st.gen;
+        gemv_phase(p, s, st, p.codec_head, EPI_RAW, p.x_head, p.logits, t_head);
+        LL_STAMP();
+        // state other CTAs read at the start of the launch is only updated here, after the last all-to-all exchange
+        if (rec) {
+            *p.pos_talker = pos_t + 1; *p.step = step + 1;
+            if (p.seen) atomicOr(p.seen + (code0 >> 5), 1u << (code0 & 31));
+        }
+    }
+    if (cta == 0 && tid == 0) *reinterpret_cast<volatile unsigned int*>(p.state) = st.gen;
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------------------
+int num_sms();
+
+static void fill_stack(LLStack& d, const q3t_stack& st) {
+    d.layers = st.layers_dev; d.n_layers = st.n_layers; d.hidden = st.hidden; d.n_heads = st.n_heads; d.n_kv = st.n_kv_heads;
+    d.head_dim = st.head_dim; d.inter = st.inter; d.eps = st.eps; d.final_norm = st.final_norm; d.inv_freq = st.inv_freq;
+    d.kv_pool = (__nv_bfloat16*)st.kv_pool; d.kv_layer_stride = st.kv_layer_stride_bytes / 2; d.block_tbl = st.block_tbl;
+}
+
+static int check_stack(const q3t_stack& st, int grid) {
+    Q3T_REQUIRE(st.layers_dev != nullptr, "frame_ll: layers_dev missing");
+    Q3T_REQUIRE(st.head_dim == 128, "frame_ll: head_dim must be 128");
+    Q3T_REQUIRE(st.n_heads == st.n_kv_heads || st.n_heads == 2 * st.n_kv_heads, "frame_ll: H/Hkv must be 1 or 2");
+    Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
+    Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
+    Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
+    const int qkv_n = (st.n_heads + 2 * st.n_kv_heads) * st.head_dim;
+    const int n_max = 2 * st.inter > qkv_n ? 2 * st.inter : qkv_n;
+    const long long t1 = ((long long)(n_max / 16) + grid - 1) / grid * (st.hidden / 256);
+    const long long t2 = ((long long)(st.hidden / 16) + grid - 1) / grid * (st.inter / 256);
+    Q3T_REQUIRE(t1 <= LL_MAXT && t2 <= LL_MAXT, "frame_ll: too many tiles per CTA");
+    return 0;
+}
+
+// exchange-buffer layout inside the caller's workspace (64-bit words)
+static long long ll_words(const q3t_stack* t, const q3t_stack* c, int head_max) {
+    long long w = 0;
+    const q3t_stack* ss[2] = {t, c};
+    long long qkv = 0, attn = 0, hid = 0, act = 0;
+    for (int i = 0; i < 2; ++i) {
+        if (!ss[i]) continue;
+        const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
+        qkv = q > qkv ? q : qkv;
+        const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
+        attn = a > attn ? a : attn;
+        hid = ss[i]->hidden > hid ? ss[i]->hidden : hid;
+        act = ss[i]->inter > act ? ss[i]->inter : act;
+    }
+    w = qkv + attn + 3 * hid + act + head_max + 64;
+    return (w + 15) / 16 * 16;
+}
+
+static void carve(LLParams& p, void* work, const q3t_stack* t, const q3t_stack* c, int head_max) {
+    long long qkv = 0, attn = 0, hid = 0, act = 0;
+    const q3t_stack* ss[2] = {t, c};
+    for (int i = 0; i < 2; ++i) {
+        if (!ss[i]) continue;
+        const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
+        qkv = q > qkv ? q : qkv;
+        const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
+        attn = a > attn ? a : attn;
+        hid = ss[i]->hidden > hid ? ss[i]->hidden : hid;
+        act = ss[i]->inter > act ? ss[i]->inter : act;
+    }
+    auto up = [](long long v) { return (v + 15) / 16 * 16; };
+    u64* w = (u64*)work;
+    p.x_qkv = w; w += up(qkv);
+    p.x_attn = w; w += up(attn);
+    p.x_o = w; w += up(hid);
+    p.x_down = w; w += up(hid);
+    p.x_proj = w; w += up(hid);
+    p.x_act = w; w += up(act);
+    p.x_head = w;
+    (void)head_max;
+}
+
+static int launch_ll(const LLParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(frame_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM_BYTES);
+        attr_set = true;
+    }
+    static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(num_sms()); cfg.blockDim = dim3(LL_THREADS); cfg.dynamicSmemBytes = LL_SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, frame_ll_kernel, p);
+    Q3T_CHECK_LAUNCH("frame_ll");
+    return 0;
+}
+
+int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream) {
+    const int grid = num_sms();
+    if (int rc = check_stack(a->stack, grid)) return rc;
+    Q3T_REQUIRE(a->ll_work && a->ll_state, "stack_pass: workspace missing");
+    if (a->head.w) Q3T_REQUIRE(a->head.N % 16 == 0 && a->head.K == a->stack.hidden, "stack_pass: head shape");
+    LLParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = LL_MODE_STACK; p.which = 0;
+    fill_stack(p.talker, a->stack);
+    carve(p, a->ll_work, &a->stack, nullptr, a->head.w ? a->head.N : 0);
+    Q3T_REQUIRE(ll_words(&a->stack, nullptr, a->head.w ? a->head.N : 0) * 8 <= a->ll_work_bytes, "stack_pass: workspace too small");
+    p.state = a->ll_state; p.timing = a->timing;
+    p.pos = a->pos; p.x_in = a->x_in; p.hidden_out = a->hidden_out; p.logits_out = a->logits_out; p.head = a->head;
+    p.n_groups = 1;
+    return launch_ll(p, stream);
+}
+
+int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream) {
+    const int grid = num_sms();
+    if (int rc = check_stack(f->talker, grid)) return rc;
+    if (int rc = check_stack(f->cp, grid)) return rc;
+    Q3T_REQUIRE(f->B == 1, "frame_ll: batch 1 only");
+    Q3T_REQUIRE(f->ll_work && f->ll_state && f->cp_heads_dev && f->cp_embeddings_dev, "frame_ll: workspace / device tables missing");
+    Q3T_REQUIRE(f->talker_vocab <= SAMPLE_MAXV && f->cp_vocab <= SAMPLE_MAXV && f->talker_vocab % 16 == 0 && f->cp_vocab % 16 == 0,
+                "frame_ll: vocabulary size");
+    Q3T_REQUIRE(f->cp_proj.K == f->talker.hidden && f->cp_proj.N == f->cp.hidden, "frame_ll: cp_proj shape (embedding width must equal the talker hidden size)");
+    const int head_max = f->talker_vocab > f->cp_vocab ? f->talker_vocab : f->cp_vocab;
+    Q3T_REQUIRE(ll_words(&f->talker, &f->cp, head_max) * 8 <= f->ll_work_bytes, "frame_ll: workspace too small");
+    LLParams p;
+    memset(&p, 0, sizeof(p));
+    p.mode = LL_MODE_FRAME;
+    fill_stack(p.talker, f->talker); fill_stack(p.cp, f->cp);
+    carve(p, f->ll_work, &f->talker, &f->cp, head_max);
+    p.state = f->ll_state; p.timing = f->ll_timing;
+    p.codec_head = f->codec_head; p.cp_proj = f->cp_proj; p.cp_heads = f->cp_heads_dev;
+    p.codec_embedding = f->codec_embedding; p.cp_embeddings = f->cp_embeddings_dev;
+    p.emb_dim = f->talker.hidden; p.talker_vocab = f->talker_vocab; p.cp_vocab = f->cp_vocab; p.n_groups = f->n_groups;
+    p.talker_sp = f->talker_sp; p.cp_sp = f->cp_sp;
+    p.x = f->x; p.hidden = f->hidden; p.logits = f->logits; p.cp_logits = f->cp_logits; p.keep_cp_logits = f->keep_cp_logits;
+    p.pos_talker = f->pos; p.step = f->step; p.cur_codes = f->cur_codes; p.codes = f->codes; p.own_codes = f->own_codes;
+    p.max_frames = f->max_frames; p.seen = f->seen; p.done = f->done; p.trailing = f->trailing; p.n_trailing = f->n_trailing;
+    p.forced = f->forced_codes;
+    return launch_ll(p, stream);
+}
+
+}  // namespace q3t
+
+extern "C" int q3t_stack_pass(const q3t_stack_pass_args* a, void* stream) {
+    return q3t::launch_stack_pass(a, (cudaStream_t)stream);
+}
+
+extern "C" long long q3t_ll_work_bytes(const q3t_stack* talker, const q3t_stack* cp, int head_max) {
+    return q3t::ll_words(talker, cp, head_max) * 8;
+}

@@ -128,10 +128,15 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) w8_gemv_kernel(const GemvPara
         for (int i = 0; i < GEMV_MAXV; ++i) {
             const int k4 = tid + i * GEMV_THREADS;
             if (k4 < K4) {
-                float4 v = reinterpret_cast<const float4*>(xr)[k4];
+                float4 v;
                 if (p.prologue == Q3T_PRO_SWIGLU) {
-                    const float4 u = reinterpret_cast<const float4*>(xr + K)[k4];
+                    // gate/up interleaved in blocks of 8: act[8j + r] = silu(x[16j + r]) * x[16j + 8 + r]
+                    const int gi = ((k4 >> 1) << 4) + ((k4 & 1) << 2);
+                    v = *reinterpret_cast<const float4*>(xr + gi);
+                    const float4 u = *reinterpret_cast<const float4*>(xr + gi + 8);
                     v.x = silu_f(v.x) * u.x; v.y = silu_f(v.y) * u.y; v.z = silu_f(v.z) * u.z; v.w = silu_f(v.w) * u.w;
+                } else {
+                    v = reinterpret_cast<const float4*>(xr)[k4];
                 }
                 xv[i] = v;
                 ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;

@@ -59,11 +59,18 @@ class TalkerEngine:
         def fp(name):
             return ws.fp[name].to(dev, torch.float32).contiguous()
 
-        def w8(names: Sequence[str], bias_name: Optional[str] = None) -> L.W8:
+        def w8(names: Sequence[str], bias_name: Optional[str] = None, interleave8: bool = False) -> L.W8:
             trips = [ws.q[n] for n in names]
             q = torch.cat([x[0] for x in trips], 0).to(dev)
             s = torch.cat([x[1] for x in trips], 0).to(dev)
             b = torch.cat([x[2] for x in trips], 0).to(dev)
+            if interleave8:
+                # fused gate/up: rows 16j..16j+7 = gate rows 8j.., rows 16j+8..16j+15 = the matching up rows, so one
+                # 16-row weight tile holds both operands of silu(gate) * up (SwiGLU runs in the GEMV epilogue)
+                half = q.shape[0] // 2
+                idx = torch.arange(half, device=dev).view(-1, 8)
+                perm = torch.cat([idx, idx + half], 1).reshape(-1)
+                q, s, b = q[perm].contiguous(), s[perm].contiguous(), b[perm].contiguous()
             blob = pack_w8(q, s, b)
             self.w_bytes += blob.numel()
             o = L.W8()
@@ -82,7 +89,7 @@ class TalkerEngine:
                 ly.k_norm = self.keep(fp(p + ".k_norm.weight"))
                 ly.o = w8([p + ".o_proj"])
                 ly.post_norm = self.keep(fp(p + ".post_norm.weight"))
-                ly.gate_up = w8([p + ".gate_proj", p + ".up_proj"])
+                ly.gate_up = w8([p + ".gate_proj", p + ".up_proj"], interleave8=True)
                 ly.down = w8([p + ".down_proj"])
             st = L.Stack()
             st.hidden, st.n_layers, st.n_heads, st.n_kv_heads = sc.hidden_size, sc.num_layers, sc.num_heads, sc.num_kv_heads
@@ -122,6 +129,8 @@ class TalkerEngine:
         fa.cp_embeddings_dev = self.keep(self._cp_emb_dev)
         self._cp_heads = (L.W8 * (self.G - 1))(*[w8([f"cp.heads.{g}"]) for g in range(self.G - 1)])
         fa.cp_heads_host = C.cast(self._cp_heads, C.POINTER(L.W8))
+        self._cp_heads_dev = torch.frombuffer(bytearray(bytes(memoryview(self._cp_heads).cast("B"))), dtype=torch.uint8).to(dev)
+        fa.cp_heads_dev = self.keep(self._cp_heads_dev)
         fa.cp_vocab, fa.n_groups = c.vocab_size, self.G
         # text side (prefill only)
         self.text_embedding = fp("talker.text_embedding")
@@ -163,12 +172,11 @@ class TalkerEngine:
         fa.seen, fa.done = self.keep(self.seen), self.keep(self.done)
         fa.trailing, fa.n_trailing = self.keep(self.trailing), max_trailing
         fa.forced_codes = 0
-        # persistent stack-pass kernel (batch 1): workspace + grid barrier word
-        nwork = max(self.lib.q3t_stack_pass_work_floats(C.byref(self.talker_stack), t.vocab_size),
-                    self.lib.q3t_stack_pass_work_floats(C.byref(self.cp_stack), c.vocab_size))
-        self.mega_work = torch.zeros(int(nwork), **f32)
-        self.mega_barrier = torch.zeros(4, **i32)
-        fa.mega_work, fa.mega_barrier = self.keep(self.mega_work), self.keep(self.mega_barrier)
+        # persistent kernels (batch 1): exchange buffers of 64-bit {value, tag} words + [tag counter, error code]
+        nbytes = int(self.lib.q3t_ll_work_bytes(C.byref(self.talker_stack), C.byref(self.cp_stack), max(V, Vc)))
+        self.ll_work = torch.zeros(nbytes // 8, device=dev, dtype=torch.int64)
+        self.ll_state = torch.zeros(4, **i32)
+        fa.ll_work, fa.ll_work_bytes, fa.ll_state, fa.ll_timing = self.keep(self.ll_work), nbytes, self.keep(self.ll_state), 0
         fa.use_mega = int(use_mega and self.B == 1)
         self.set_sampling()
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}

@@ -66,12 +66,13 @@ class FrameArgs(C.Structure):
                 ("keep_cp_logits", i32), ("xc", vp), ("qkv", vp), ("attn", vp), ("gu", vp), ("attn_work", vp),
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
-                ("n_trailing", i32), ("forced_codes", vp), ("use_mega", i32), ("mega_work", vp), ("mega_barrier", vp)]
+                ("n_trailing", i32), ("forced_codes", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
+                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp)]
 
 
 class StackPassArgs(C.Structure):
     _fields_ = [("stack", Stack), ("head", W8), ("pos", vp), ("x_in", vp), ("hidden_out", vp), ("logits_out", vp),
-                ("work", vp), ("counters", vp), ("barrier", vp), ("timing", vp)]
+                ("ll_work", vp), ("ll_work_bytes", i64), ("ll_state", vp), ("timing", vp)]
 
 
 class TapGemmArgs(C.Structure):
@@ -82,7 +83,7 @@ class TapGemmArgs(C.Structure):
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_rmsnorm", "q3t_attn_decode",
-           "q3t_sample", "q3t_stack_pass", "q3t_stack_pass_work_floats", "q3t_talker_step", "q3t_frame", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
+           "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
            "q3t_window_attn", "q3t_snake", "q3t_clamp_pcm16"]
 
 _lib = None
@@ -108,8 +109,8 @@ def load() -> C.CDLL:
     lib.q3t_attn_decode.argtypes = [C.POINTER(AttnArgs), vp]
     lib.q3t_sample.argtypes = [C.POINTER(SampleArgs), vp]
     lib.q3t_stack_pass.argtypes = [C.POINTER(StackPassArgs), vp]
-    lib.q3t_stack_pass_work_floats.argtypes = [C.POINTER(Stack), i32]
-    lib.q3t_stack_pass_work_floats.restype = i64
+    lib.q3t_ll_work_bytes.argtypes = [C.POINTER(Stack), C.POINTER(Stack), i32]
+    lib.q3t_ll_work_bytes.restype = i64
     lib.q3t_talker_step.argtypes = [C.POINTER(FrameArgs), i32, vp]
     lib.q3t_frame.argtypes = [C.POINTER(FrameArgs), vp]
     lib.q3t_rvq_gather_sum.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, vp, vp]
