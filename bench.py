@@ -11,8 +11,8 @@ passes, next-input sum] -> codec decode of the 240 frames to a 24 kHz waveform (
 
 `value`  : device-resident inputs (prefill embeddings already in HBM), CUDA-event time, max over ranks.
 `e2e`    : same metric through the public API with HOST inputs (pinned token ids -> H2D -> ... -> waveform D2H).
-`roofline`: talker decode step (141 W8-GEMV launches + 28 attention launches per token): algorithmic bytes per
-            step / CUDA-event step time, against MEASURED_PEAKS.json hbm_gbs.
+`roofline`: talker decode step (one persistent data-flow launch, csrc/frame_ll.cu): algorithmic bytes per step
+             / CUDA-event step time, against MEASURED_PEAKS.json hbm_gbs.
 """
 import argparse
 import json
@@ -265,9 +265,8 @@ def main():
     peak, peak_src = peaks()
     achieved = step_b / (ms_tok / 1e3) / 1e9
     launches_step = e.launches_per_frame
-    # launches inside one timed step: L0 prefill token steps + FRAMES frames + the codec
-    t = cfg.talker
-    per_tok = t.num_layers * 5 + 3
+    # launches inside one timed step: L0 prefill token steps + FRAMES frames + the codec (counted at graph capture)
+    per_tok = e.launches.get("step", 0)
     gpu_launches = args.steps * (L0 * per_tok + FRAMES * (launches_step or 0) + codec_launches)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "w8a32(f32 accumulate)",
@@ -275,7 +274,7 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(ids_host.numel() * 8 + ins_host.numel() * 8),
                     "d2h_bytes_per_step": int(wav_host.numel() * 4), "ms_per_step": ms_e2e},
             "gpu_launches": int(gpu_launches), "launches_per_frame": launches_step,
-            "roofline": {"bound": "hbm", "kernel": "w8_gemv_kernel (talker decode step: 141 GEMV + 28 attention launches, CUDA graph)",
+            "roofline": {"bound": "hbm", "kernel": "frame_ll_kernel, stack mode (talker decode step = ONE persistent launch: 28 layers + final norm + codec head)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                          "frac_of_8TBps": achieved / 8000.0, "traffic": None, "bytes_per_step": step_b, "weight_bytes": w_b,
                          "kv_bytes": kv_b, "us_per_talker_step": ms_tok * 1e3, "ctx": L0 + FRAMES // 2},

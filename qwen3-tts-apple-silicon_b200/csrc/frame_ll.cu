@@ -24,6 +24,7 @@
 //     the q/k/v words arrive; partial (m, l, acc) records are LL words merged by every consumer of the O projection.
 // Re-use of an exchange buffer is safe without extra synchronisation because every phase is an all-to-all dependency:
 // a CTA can only be one phase ahead of the slowest CTA, and each buffer is rewritten five or more phases later.
+#include <stdlib.h>
 #include "sampler.cuh"
 
 namespace q3t {
@@ -62,6 +63,7 @@ struct LLParams {
     u64 *x_qkv, *x_attn, *x_o, *x_act, *x_down, *x_head, *x_proj;
     unsigned int* state;                         // [0] tag base (persists across launches), [1] error code
     unsigned long long* timing;                  // optional [grid][LL_NSTAMP]
+    int pf_dist;                                 // L2 prefetch distance in tiles ahead of the TMA cursor (0 = off)
     // ---- stack mode
     int which;                                   // 0 = talker stack, 1 = code-predictor stack
     const int* pos; const float* x_in; float* hidden_out; float* logits_out; q3t_w8 head;
@@ -176,43 +178,112 @@ __device__ __forceinline__ void imma_16832_ll(int (&c)[4], const uint4 a, const 
 }
 
 // ---- shared memory --------------------------------------------------------------------------------------------------------
+// Phases are device functions that reach the launch parameters and the carve-up through the dynamic shared-memory base.
+// LL_FN selects inlining: fully inlined is ~0.35 us per phase faster than calls (measured), at 600 KB of SASS.
+extern __shared__ __align__(128) unsigned char ll_smem_raw[];
+
+#ifndef LL_FN
+#define LL_FN __forceinline__
+#endif
+
+// per-CTA view of one W8 matrix / one layer, built once per launch in shared memory: no phase starts with a dependent
+// global-memory load of a descriptor, a norm-weight pointer or an integer division for its row-tile range
+struct MatD {
+    const uint8_t* w; const float* bias;
+    int nkc, rb, re, N;
+};
+struct LayerD {
+    MatD qkv, o, gu, down;
+    const float *input_norm, *post_norm, *q_norm, *k_norm;
+};
+constexpr int LL_MAXLAYERS = 40;                 // talker + code-predictor layers
+constexpr int LL_MAXHEADS = 24;                  // cp_proj, codec head / stack head, code-predictor heads
+
 struct LLSmem {
+    LayerD* lay;            // [LL_MAXLAYERS]  talker layers first, then code-predictor layers
+    MatD* hd;               // [LL_MAXHEADS]   0 = cp_proj, 1 = codec head (or the stack-mode head), 2.. = cp heads
     uint8_t* ring;          // [LL_NSLOT][4352]
     uint4* xfrag;           // [LL_MAXK/64][32] digit planes in mma B-fragment order (lanes 16..31 stay zero); sampler scratch
     float* xsum;            // [LL_MAXK/64]
     float* xscl;            // [LL_MAXK/64]
     float* resid;           // [LL_MAXH]
-    float* xnext;           // [LL_MAXH] next talker input, accumulated while the code predictor runs
     float* tile_out;        // [LL_MAXT][16]
     float* att;             // attention scratch: q [2][128], new k/v [2][128], partials [16][2][130]
-    float* red;             // [64]
+    float* red;             // [2][32] block reductions, double buffered
     float* cs;              // [64] cos(pos * inv_freq)
     float* sn;              // [64]
     int* ibuf;              // [64] sampler scratch ints
+    int* pages;             // [64] KV page ids of this CTA's attention chunk (constant during a pass)
     uint64_t* full;         // [LL_NSLOT]
     uint64_t* empty;        // [LL_NSLOT]
 };
 constexpr size_t LL_ATT_FLOATS = 4 * 128 + 16 * 2 * LL_REC;
-constexpr size_t LL_SMEM_BYTES = (size_t)LL_NSLOT * Q3T_TILE_BYTES + (size_t)(LL_MAXK / 64) * 512 + 2 * (LL_MAXK / 64) * 4 +
-                                 2 * LL_MAXH * 4 + LL_MAXT * 16 * 4 + LL_ATT_FLOATS * 4 + 64 * 4 + 128 * 4 + 64 * 4 +
-                                 2 * LL_NSLOT * 8 + 128;
+constexpr size_t LL_OFF_LAY = 1024;                                      // the first KB holds a copy of LLParams
+constexpr size_t LL_OFF_HD = LL_OFF_LAY + LL_MAXLAYERS * sizeof(LayerD);
+constexpr size_t LL_OFF_RING = (LL_OFF_HD + LL_MAXHEADS * sizeof(MatD) + 127) / 128 * 128;
+constexpr size_t LL_OFF_XFRAG = LL_OFF_RING + (size_t)LL_NSLOT * Q3T_TILE_BYTES;
+constexpr size_t LL_OFF_XSUM = LL_OFF_XFRAG + (size_t)(LL_MAXK / 64) * 512;
+constexpr size_t LL_OFF_XSCL = LL_OFF_XSUM + (LL_MAXK / 64) * 4;
+constexpr size_t LL_OFF_RESID = LL_OFF_XSCL + (LL_MAXK / 64) * 4;
+constexpr size_t LL_OFF_TILE = LL_OFF_RESID + LL_MAXH * 4;
+constexpr size_t LL_OFF_ATT = LL_OFF_TILE + LL_MAXT * 16 * 4;
+constexpr size_t LL_OFF_RED = LL_OFF_ATT + LL_ATT_FLOATS * 4;
+constexpr size_t LL_OFF_CS = LL_OFF_RED + 64 * 4;
+constexpr size_t LL_OFF_SN = LL_OFF_CS + 64 * 4;
+constexpr size_t LL_OFF_IBUF = LL_OFF_SN + 64 * 4;
+constexpr size_t LL_OFF_PAGES = LL_OFF_IBUF + 64 * 4;
+constexpr size_t LL_OFF_FULL = LL_OFF_PAGES + 64 * 4;
+constexpr size_t LL_OFF_EMPTY = LL_OFF_FULL + LL_NSLOT * 8;
+constexpr size_t LL_SMEM_BYTES = LL_OFF_EMPTY + LL_NSLOT * 8;
+static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
+
+__device__ __forceinline__ const LLParams& ll_params() { return *reinterpret_cast<const LLParams*>(ll_smem_raw); }
+__device__ __forceinline__ LLSmem ll_smem() {
+    LLSmem s;
+    unsigned char* b = ll_smem_raw;
+    s.lay = reinterpret_cast<LayerD*>(b + LL_OFF_LAY);
+    s.hd = reinterpret_cast<MatD*>(b + LL_OFF_HD);
+    s.ring = b + LL_OFF_RING;
+    s.xfrag = reinterpret_cast<uint4*>(b + LL_OFF_XFRAG);
+    s.xsum = reinterpret_cast<float*>(b + LL_OFF_XSUM);
+    s.xscl = reinterpret_cast<float*>(b + LL_OFF_XSCL);
+    s.resid = reinterpret_cast<float*>(b + LL_OFF_RESID);
+    s.tile_out = reinterpret_cast<float*>(b + LL_OFF_TILE);
+    s.att = reinterpret_cast<float*>(b + LL_OFF_ATT);
+    s.red = reinterpret_cast<float*>(b + LL_OFF_RED);
+    s.cs = reinterpret_cast<float*>(b + LL_OFF_CS);
+    s.sn = reinterpret_cast<float*>(b + LL_OFF_SN);
+    s.ibuf = reinterpret_cast<int*>(b + LL_OFF_IBUF);
+    s.pages = reinterpret_cast<int*>(b + LL_OFF_PAGES);
+    s.full = reinterpret_cast<uint64_t*>(b + LL_OFF_FULL);
+    s.empty = reinterpret_cast<uint64_t*>(b + LL_OFF_EMPTY);
+    return s;
+}
 
 struct CState {
     uint32_t seq;           // tiles consumed so far (ring sequence number)
     uint32_t gen;           // phase tag counter
     int nstamp;
+    int nsplit;             // attention geometry of the current pass
+    int chunk;
+    int red_par;            // parity of the double-buffered block-reduction scratch
 };
 
+#ifdef LL_FINE
+#define LL_FSTAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP) p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = gtimer(); } while (0)
+#else
+#define LL_FSTAMP() do { } while (0)
+#endif
 #define LL_STAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP) p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = gtimer(); } while (0)
 
-__device__ __forceinline__ float cblock_sum(float v, float* red) {
+// block sum over the 512 consumer threads; `red` is double buffered by `parity`, so one barrier per call is enough
+__device__ __forceinline__ float cblock_sum(float v, float* red, int parity) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     v = warp_sum(v);
+    float* r = red + parity * 32;
+    if (lane == 0) r[wid] = v;
     cbar();
-    if (lane == 0) red[wid] = v;
-    cbar();
-    float r = (lane < LL_CWARPS) ? red[lane] : 0.f;
-    return warp_sum(r);
+    return warp_sum((lane < LL_CWARPS) ? r[lane] : 0.f);
 }
 
 // v = 4 consecutive inputs starting at k = 4*k4 -> signed base-256 digit planes + per-group sum/scale.
@@ -278,45 +349,46 @@ __device__ __forceinline__ void tile_dot(const LLSmem& s, const uint8_t* tile, i
     out_hi = v_hi + bacc_hi;
 }
 
-__device__ __forceinline__ void row_range(int nrt, int cta, int grid, int& rb, int& re) {
-    rb = (int)(((long long)nrt * cta) / grid);
-    re = (int)(((long long)nrt * (cta + 1)) / grid);
-}
-
 // ---- GEMV phase (consumers): this CTA's row tiles out of the ring -> epilogue -> LL words (+ optional plain copy) --------
-__device__ __forceinline__ void gemv_phase(const LLParams& p, const LLSmem& s, CState& st, const q3t_w8& W, int epi,
-                                           u64* ll_out, float* plain_out, uint32_t tag) {
+__device__ LL_FN void gemv_phase(CState& st, const MatD& W, int epi, u64* ll_out, float* plain_out, uint32_t tag) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nkc = W.K >> 8;
-    int rb, re;
-    row_range(W.N >> 4, blockIdx.x, gridDim.x, rb, re);
-    const int nt = (re - rb) * nkc;
+    const int nkc = W.nkc, rb = W.rb, nloc = W.re - W.rb;
+    const int nt = nloc * nkc;
+    int kc = warp % nkc;                     // tile j covers k-chunk j % nkc (j = warp, warp + 16, ...)
+    const int kstep = LL_CWARPS % nkc;
     for (int j = warp; j < nt; j += LL_CWARPS) {
         const uint32_t i = st.seq + j, slot = i % LL_NSLOT, par = (i / LL_NSLOT) & 1;
         mbar_wait(smem_u32(&s.full[slot]), par, p.state, 0x200u);
         float lo, hi;
-        tile_dot(s, s.ring + (size_t)slot * Q3T_TILE_BYTES, j % nkc, lane, lo, hi);
+        tile_dot(s, s.ring + (size_t)slot * Q3T_TILE_BYTES, kc, lane, lo, hi);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.empty[slot]));
         if ((lane & 3) == 0) { s.tile_out[j * 16 + (lane >> 2)] = lo; s.tile_out[j * 16 + (lane >> 2) + 8] = hi; }
+        kc += kstep; if (kc >= nkc) kc -= nkc;
     }
     st.seq += nt;
     cbar();
-    const int nloc = re - rb;
-    if (epi == EPI_SWIGLU) {
-        // rows 0..7 of a tile are gate rows, rows 8..15 the matching up rows (weights interleaved at load)
-        for (int i = tid; i < nloc * 8; i += LL_CTHREADS) {
-            const int rtl = i >> 3, r = i & 7;
-            float g = 0.f, u = 0.f;
-            for (int kc = 0; kc < nkc; ++kc) { g += s.tile_out[(rtl * nkc + kc) * 16 + r]; u += s.tile_out[(rtl * nkc + kc) * 16 + r + 8]; }
-            ll_st(ll_out + (size_t)(rb + rtl) * 8 + r, silu_f(g) * u, tag);
-        }
-    } else {
-        for (int i = tid; i < nloc * 16; i += LL_CTHREADS) {
-            const int rtl = i >> 4, r = i & 15, n = (rb + rtl) * 16 + r;
-            float v = 0.f;
-            for (int kc = 0; kc < nkc; ++kc) v += s.tile_out[(rtl * nkc + kc) * 16 + r];
-            if (W.lin_bias) v += W.lin_bias[n];
+    // rows: four lanes per output row add every fourth k-chunk, two shuffles finish the sum (fixed order); a warp
+    // covers 8 rows per iteration.  SwiGLU tiles hold gate rows 0..7 and the matching up rows 8..15 (weights interleaved
+    // at load): slots 0..3 of a warp take gate rows, slots 4..7 the matching up rows, paired with one more shuffle.
+    const int q = lane & 3, sl = lane >> 2;
+    const float* bias = W.bias;
+    for (int i0 = warp << 3; i0 < nloc * 16; i0 += LL_CTHREADS / 4) {
+        int rtl, r;
+        if (epi == EPI_SWIGLU) { const int blk = i0 >> 3; rtl = blk >> 1; r = ((blk & 1) << 2) + (sl & 3) + ((sl >> 2) << 3); }
+        else { const int i = i0 + sl; rtl = i >> 4; r = i & 15; }
+        float v = 0.f;
+        for (int k = q; k < nkc; k += 4) v += s.tile_out[(rtl * nkc + k) * 16 + r];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (epi == EPI_SWIGLU) {
+            const float u = __shfl_xor_sync(0xffffffffu, v, 16);
+            if (sl < 4 && q == 0) ll_st(ll_out + (size_t)(rb + rtl) * 8 + (r & 7), silu_f(v) * u, tag);
+        } else if (q == 0) {
+            const int n = (rb + rtl) * 16 + r;
+            if (bias) v += bias[n];
             ll_st(ll_out + n, v, tag);
             if (plain_out) plain_out[n] = v;
         }
@@ -325,12 +397,15 @@ __device__ __forceinline__ void gemv_phase(const LLParams& p, const LLSmem& s, C
 
 // ---- prologues: phase input -> digit planes in shared memory ---------------------------------------------------------------
 // resid (+= LL words of the previous projection) -> RMSNorm -> digits
-__device__ __forceinline__ void pro_norm(const LLParams& p, const LLSmem& s, const u64* ll_add, uint32_t tag_add,
-                                         const float* norm_w, float* hidden_out, int H, float eps) {
+__device__ LL_FN void pro_norm(CState& st, const u64* ll_add, uint32_t tag_add, const float* norm_w, float* hidden_out, int H,
+                               float eps) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, H4 = H >> 2;
     const bool on = tid < H4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f), nw = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on) {
+        nw = __ldg(reinterpret_cast<const float4*>(norm_w) + tid);      // in flight while the words are polled
         v = reinterpret_cast<float4*>(s.resid)[tid];
         if (ll_add) {
             const float4 a = ll_ld4(ll_add + 4 * tid, tag_add, p.state);
@@ -339,9 +414,9 @@ __device__ __forceinline__ void pro_norm(const LLParams& p, const LLSmem& s, con
         }
     }
     const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    const float rstd = rsqrtf(cblock_sum(ss, s.red) / (float)H + eps);
+    st.red_par ^= 1;
+    const float rstd = rsqrtf(cblock_sum(ss, s.red, st.red_par) / (float)H + eps);
     if (on) {
-        const float4 nw = reinterpret_cast<const float4*>(norm_w)[tid];
         v.x = nw.x * (v.x * rstd); v.y = nw.y * (v.y * rstd); v.z = nw.z * (v.z * rstd); v.w = nw.w * (v.w * rstd);
         if (hidden_out && blockIdx.x == 0) reinterpret_cast<float4*>(hidden_out)[tid] = v;
         emit_digits(s, v, tid, lane);
@@ -350,7 +425,9 @@ __device__ __forceinline__ void pro_norm(const LLParams& p, const LLSmem& s, con
 }
 
 // LL words (already activated values) -> digits; K <= LL_MAXK
-__device__ __forceinline__ void pro_ll(const LLParams& p, const LLSmem& s, const u64* ll, uint32_t tag, int K) {
+__device__ LL_FN void pro_ll(const u64* ll, uint32_t tag, int K) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
     constexpr int NV = LL_MAXK / 4 / LL_CTHREADS;   // 3
     const u64* pp[NV]; bool on[NV]; float4 v[NV];
@@ -363,26 +440,18 @@ __device__ __forceinline__ void pro_ll(const LLParams& p, const LLSmem& s, const
     cbar();
 }
 
-// plain fp32 vector in global memory (constant table row or a vector written by an earlier launch) -> digits;
-// optionally accumulated into xnext (the next talker input)
-__device__ __forceinline__ void pro_plain(const LLSmem& s, const float* x, int K, int accumulate) {
+// plain fp32 vector in global memory (constant table row or a vector written by an earlier launch) -> digits
+__device__ LL_FN void pro_plain(const float* x, int K) {
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
-    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(x) + k4);
-        if (accumulate == 1) reinterpret_cast<float4*>(s.xnext)[k4] = v;
-        else if (accumulate == 2) {
-            float4 a = reinterpret_cast<float4*>(s.xnext)[k4];
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-            reinterpret_cast<float4*>(s.xnext)[k4] = a;
-        }
-        emit_digits(s, v, k4, lane);
-    }
+    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) emit_digits(s, __ldcg(reinterpret_cast<const float4*>(x) + k4), k4, lane);
     cbar();
 }
 
 // attention partial records of every split -> merged head outputs -> digits  (input of the O projection)
-__device__ __forceinline__ void pro_attn(const LLParams& p, const LLSmem& s, const u64* ll_attn, uint32_t tag, int q_dim,
-                                         int nsplit) {
+__device__ LL_FN void pro_attn(const u64* ll_attn, uint32_t tag, int q_dim, int nsplit) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, K4 = q_dim >> 2;
     for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) {
         const int head = (k4 << 2) >> 7, d = (k4 << 2) & 127;
@@ -431,7 +500,7 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int& 
     int maxsplit = grid / n_kv;
     if (maxsplit > LL_MAXSPLIT) maxsplit = LL_MAXSPLIT;
     if (maxsplit < 1) maxsplit = 1;
-    chunk = 128;
+    chunk = 64;
     if (ctx > chunk * maxsplit) {
         chunk = (ctx + maxsplit - 1) / maxsplit;
         chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
@@ -441,14 +510,15 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int& 
 
 // ---- attention phase: q/k RMSNorm + RoPE + KV-page write + split-KV GQA decode attention -> LL records ----------------------
 template <int REP>
-__device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, const LLStack& S, int layer, int pos,
-                                           const u64* ll_qkv, uint32_t tag_qkv, u64* ll_attn, uint32_t tag_out) {
-    constexpr int D = 128, EPL = 8, PRE = 4;
-    int chunk, nsplit;
-    attn_geometry(pos + 1, S.n_kv, gridDim.x, chunk, nsplit);
+__device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
+                                 uint32_t tag_qkv, u64* ll_attn, uint32_t tag_out) {
+    constexpr int D = 128, EPL = 8, PRE = 2;
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
+    const int chunk = st.chunk, nsplit = st.nsplit;
     const int cta = blockIdx.x;
     if (cta >= S.n_kv * nsplit) return;
-    const int kvh = cta % S.n_kv, split = cta / S.n_kv;
+    const int split = cta / S.n_kv, kvh = cta - split * S.n_kv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hw = lane >> 4, sl = lane & 15, hwid = warp * 2 + hw;
     const int ctx = pos + 1, s0 = split * chunk, s1 = min(ctx, s0 + chunk);
@@ -462,33 +532,39 @@ __device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, c
     const size_t v_off = (size_t)S.n_kv * Q3T_KV_PAGE * D;
     const int n_iter = (s1 - s0 + 31) >> 5;
 
-    // 1. rows already in the cache: into registers before anything that depends on this step's QKV output
+    // 1. everything that does not depend on this step's QKV output is in flight before the words are polled:
+    //    rows already in the cache (registers), the q/k norm weights
     uint4 kreg[PRE], vreg[PRE];
 #pragma unroll
     for (int i = 0; i < PRE; ++i) {
         const int tok = s0 + hwid + 32 * i;
         kreg[i] = make_uint4(0, 0, 0, 0); vreg[i] = make_uint4(0, 0, 0, 0);
         if (tok < s1 && tok < pos) {
-            const __nv_bfloat16* kp = pool + (size_t)S.block_tbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
+            const __nv_bfloat16* kp = pool + (size_t)s.pages[(tok - s0) / Q3T_KV_PAGE] * page_elems + head_off +
                                       (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
             kreg[i] = __ldcg(reinterpret_cast<const uint4*>(kp));
             vreg[i] = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
         }
     }
+    LL_FSTAMP();   // A: preload issued
     // 2. q heads of this kv head (+ k, v of the new token on the split that owns it)
     if (warp < REP + 2) {
         const bool is_q = warp < REP, is_k = warp == REP;
         if (is_q || owner) {
+            float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (is_q || is_k) nw4 = __ldg(reinterpret_cast<const float4*>(is_q ? LD.q_norm : LD.k_norm) + lane);
+            const int page_new = owner ? s.pages[(pos - s0) / Q3T_KV_PAGE] : 0;
             const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
             const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
+            LL_FSTAMP();   // B: q words arrived
             float x[4] = {xv.x, xv.y, xv.z, xv.w};
             if (is_q || is_k) {
+                const float nw[4] = {nw4.x, nw4.y, nw4.z, nw4.w};
                 float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
                 ss = warp_sum(ss);
                 const float rstd = rsqrtf(ss / (float)D + S.eps);
-                const float* nw = is_q ? S.layers[layer].q_norm : S.layers[layer].k_norm;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) x[e] = nw[lane * 4 + e] * (x[e] * rstd);
+                for (int e = 0; e < 4; ++e) x[e] = nw[e] * (x[e] * rstd);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const float other = __shfl_xor_sync(0xffffffffu, x[e], 16);
@@ -504,13 +580,15 @@ __device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, c
                 __nv_bfloat16 hb[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) { hb[e] = __float2bfloat16_rn(x[e]); new_s[(is_k ? 0 : D) + lane * 4 + e] = __bfloat162float(hb[e]); }
-                __nv_bfloat16* dst = pool + (size_t)S.block_tbl[pos / Q3T_KV_PAGE] * page_elems + head_off + (is_k ? 0 : v_off) +
+                __nv_bfloat16* dst = pool + (size_t)page_new * page_elems + head_off + (is_k ? 0 : v_off) +
                                      (size_t)(pos % Q3T_KV_PAGE) * D + lane * 4;
                 *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hb);
             }
         }
     }
+    LL_FSTAMP();   // C: q normalised, rotated, stored
     cbar();
+    LL_FSTAMP();   // D: barrier
     // 3. online softmax per half-warp (one token per half-warp per iteration)
     float m_run[REP], l_run[REP], acc[REP][EPL], qr[REP][EPL];
 #pragma unroll
@@ -558,13 +636,14 @@ __device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, c
         const int tok = s0 + hwid + 32 * i;
         uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
         if (tok < s1 && tok < pos) {
-            const __nv_bfloat16* kp = pool + (size_t)S.block_tbl[tok / Q3T_KV_PAGE] * page_elems + head_off +
+            const __nv_bfloat16* kp = pool + (size_t)s.pages[(tok - s0) / Q3T_KV_PAGE] * page_elems + head_off +
                                       (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
             kr = __ldcg(reinterpret_cast<const uint4*>(kp));
             vr = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
         }
         step(tok, kr, vr);
     }
+    LL_FSTAMP();   // E: scores + online softmax done
     // 4. merge the two half-warps of a warp, then the 16 warps through shared memory
 #pragma unroll
     for (int r = 0; r < REP; ++r) {
@@ -584,19 +663,27 @@ __device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, c
             if (sl == 0) { part_s[(warp * REP + r) * LL_REC + D] = m_run[r]; part_s[(warp * REP + r) * LL_REC + D + 1] = l_run[r]; }
         }
     }
+    LL_FSTAMP();   // F: half-warp merge stored
     cbar();
+    LL_FSTAMP();   // G: barrier
     for (int i = tid; i < REP * D; i += LL_CTHREADS) {
         const int r = i / D, d = i % D;
-        float M = -INFINITY;
+        // 48 independent shared-memory loads, then a max tree and 16 independent exponentials
+        float mh[LL_CWARPS], lh[LL_CWARPS], ah[LL_CWARPS];
 #pragma unroll
-        for (int w = 0; w < LL_CWARPS; ++w) M = fmaxf(M, part_s[(w * REP + r) * LL_REC + D]);
+        for (int w = 0; w < LL_CWARPS; ++w) {
+            mh[w] = part_s[(w * REP + r) * LL_REC + D]; lh[w] = part_s[(w * REP + r) * LL_REC + D + 1];
+            ah[w] = part_s[(w * REP + r) * LL_REC + d];
+        }
+        float M = mh[0];
+#pragma unroll
+        for (int w = 1; w < LL_CWARPS; ++w) M = fmaxf(M, mh[w]);
         float L = 0.f, A = 0.f;
 #pragma unroll
         for (int w = 0; w < LL_CWARPS; ++w) {
-            const float mh = part_s[(w * REP + r) * LL_REC + D];
-            const float wt = (mh == -INFINITY) ? 0.f : __expf(mh - M);
-            L = fmaf(part_s[(w * REP + r) * LL_REC + D + 1], wt, L);
-            A = fmaf(part_s[(w * REP + r) * LL_REC + d], wt, A);
+            const float wt = (mh[w] == -INFINITY) ? 0.f : __expf(mh[w] - M);
+            L = fmaf(lh[w], wt, L);
+            A = fmaf(ah[w], wt, A);
         }
         u64* rec = ll_attn + ((size_t)(kvh * REP + r) * LL_MAXSPLIT + split) * LL_REC;
         ll_st(rec + d, A, tag_out);
@@ -605,15 +692,16 @@ __device__ __forceinline__ void attn_phase(const LLParams& p, const LLSmem& s, c
 }
 
 // ---- one token through a dense stack (consumers) ------------------------------------------------------------------------------
-// resid must hold the stack input (or zeros when first_add carries it as LL words).  On return: if want_final, the digit
-// planes hold the final-norm output (and hidden_out is written by CTA 0); tag_last = tag of the last down projection.
+// resid must hold the stack input (or zeros when first_add carries it as LL words).  On return, if want_final, the digit
+// planes hold the final-norm output (and hidden_out is written by CTA 0).
 struct StackIO {
     const u64* first_add; uint32_t first_tag;
     bool want_final; float* hidden_out;
 };
 
-__device__ __forceinline__ void stack_consume(const LLParams& p, const LLSmem& s, CState& st, const LLStack& S, int pos,
-                                              const StackIO& io) {
+__device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const StackIO& io) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
     const int q_dim = S.n_heads * S.head_dim, rep = S.n_heads / S.n_kv;
     // RoPE table of this position (rotate_half convention, fp32 cos/sin as the oracle)
@@ -622,55 +710,74 @@ __device__ __forceinline__ void stack_consume(const LLParams& p, const LLSmem& s
         sincosf((float)pos * S.inv_freq[tid], &sn, &cs);
         s.cs[tid] = cs; s.sn[tid] = sn;
     }
-    int chunk, nsplit;
-    attn_geometry(pos + 1, S.n_kv, gridDim.x, chunk, nsplit);
+    attn_geometry(pos + 1, S.n_kv, gridDim.x, st.chunk, st.nsplit);
+    if ((int)blockIdx.x < S.n_kv * st.nsplit) {
+        // page ids of this CTA's attention chunk: constant during the pass, so no attention phase starts with a
+        // dependent block-table load in front of its K/V loads
+        const int split = blockIdx.x / S.n_kv, p0 = (split * st.chunk) / Q3T_KV_PAGE;
+        const int np = min(st.chunk / Q3T_KV_PAGE, (pos / Q3T_KV_PAGE) - p0 + 1);
+        if (tid < np && tid < 64) s.pages[tid] = S.block_tbl[p0 + tid];
+    }
     const u64* add = io.first_add;
     uint32_t add_tag = io.first_tag;
     for (int l = 0; l < S.n_layers; ++l) {
-        const q3t_layer& L = S.layers[l];
+        const LayerD& L = lay[l];
         // ---- QKV
-        pro_norm(p, s, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
+        pro_norm(st, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
         LL_STAMP();
         const uint32_t t_qkv = ++st.gen;
-        gemv_phase(p, s, st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
+        gemv_phase(st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
         LL_STAMP();
         // ---- attention (first n_kv*nsplit CTAs)
         const uint32_t t_att = ++st.gen;
-        if (rep == 2) attn_phase<2>(p, s, S, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
-        else attn_phase<1>(p, s, S, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
+        if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
+        else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
         LL_STAMP();
         // ---- O projection
-        pro_attn(p, s, p.x_attn, t_att, q_dim, nsplit);
+        pro_attn(p.x_attn, t_att, q_dim, st.nsplit);
         LL_STAMP();
         const uint32_t t_o = ++st.gen;
-        gemv_phase(p, s, st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
+        gemv_phase(st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
         LL_STAMP();
         // ---- gate/up (+ SwiGLU in the epilogue)
-        pro_norm(p, s, p.x_o, t_o, L.post_norm, nullptr, S.hidden, S.eps);
+        pro_norm(st, p.x_o, t_o, L.post_norm, nullptr, S.hidden, S.eps);
         LL_STAMP();
         const uint32_t t_act = ++st.gen;
-        gemv_phase(p, s, st, L.gate_up, EPI_SWIGLU, p.x_act, nullptr, t_act);
+        gemv_phase(st, L.gu, EPI_SWIGLU, p.x_act, nullptr, t_act);
         LL_STAMP();
         // ---- down
-        pro_ll(p, s, p.x_act, t_act, S.inter);
+        pro_ll(p.x_act, t_act, S.inter);
         LL_STAMP();
         const uint32_t t_down = ++st.gen;
-        gemv_phase(p, s, st, L.down, EPI_RAW, p.x_down, nullptr, t_down);
+        gemv_phase(st, L.down, EPI_RAW, p.x_down, nullptr, t_down);
         LL_STAMP();
         add = p.x_down; add_tag = t_down;
     }
-    if (io.want_final) pro_norm(p, s, add, add_tag, S.final_norm, io.hidden_out, S.hidden, S.eps);
+    if (io.want_final) pro_norm(st, add, add_tag, S.final_norm, io.hidden_out, S.hidden, S.eps);
 }
 
 // ---- producer side: the same program, streaming instead of computing ---------------------------------------------------------
 struct Producer {
-    const LLSmem& s; unsigned int* state; int lane; uint32_t seq;
-    __device__ __forceinline__ void stream(const q3t_w8& W) {
-        const int nkc = W.K >> 8;
-        int rb, re;
-        row_range(W.N >> 4, blockIdx.x, gridDim.x, rb, re);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(W.w) + (size_t)rb * nkc * Q3T_TILE_BYTES;
-        const int nt = (re - rb) * nkc;
+    unsigned int* state; int lane; uint32_t seq; int pf_dist;
+    // lanes 0..LL_PLANES-1: TMA copies into the ring; lane LL_PLANES: L2 prefetch of the same tiles, pf_dist tiles ahead
+    __device__ LL_FN void stream(const MatD& W) {
+        const LLSmem s = ll_smem();
+        const uint8_t* src = W.w + (size_t)W.rb * W.nkc * Q3T_TILE_BYTES;
+        const int nt = (W.re - W.rb) * W.nkc;
+        volatile int* issued = s.ibuf + 63;
+        if (lane == LL_PLANES) {
+            if (nt > 0) {
+                int spins = 0;
+                while ((int)seq - *issued > pf_dist)
+                    if (++spins > LL_SPIN_LIMIT) ll_fail(state, 0x500u);
+                for (int t = 0; t < nt; t += 4) {
+                    const int n = nt - t < 4 ? nt - t : 4;
+                    l2_prefetch_bulk(src + (size_t)t * Q3T_TILE_BYTES, (uint32_t)n * Q3T_TILE_BYTES);
+                }
+            }
+            seq += nt;
+            return;
+        }
         for (int t = 0; t < nt; ++t, ++seq, src += Q3T_TILE_BYTES) {
             if ((int)(seq % LL_PLANES) != lane) continue;
             const uint32_t slot = seq % LL_NSLOT, par = (seq / LL_NSLOT) & 1;
@@ -678,20 +785,20 @@ struct Producer {
             const uint32_t fb = smem_u32(&s.full[slot]);
             mbar_expect_tx(fb, Q3T_TILE_BYTES);
             tma_load_1d(smem_u32(s.ring + (size_t)slot * Q3T_TILE_BYTES), src, Q3T_TILE_BYTES, fb);
+            if (lane == 0) *issued = (int)seq;
         }
     }
-    __device__ __forceinline__ void stack(const LLStack& S) {
-        for (int l = 0; l < S.n_layers; ++l) {
-            const q3t_layer& L = S.layers[l];
-            stream(L.qkv); stream(L.o); stream(L.gate_up); stream(L.down);
-        }
+    __device__ __forceinline__ void stack(const LayerD* lay, int n_layers) {
+        for (int l = 0; l < n_layers; ++l) { stream(lay[l].qkv); stream(lay[l].o); stream(lay[l].gu); stream(lay[l].down); }
     }
 };
 
 // ---- in-kernel sampler (every CTA computes the same choice; CTA 0 records it) ------------------------------------------------
 // scores come from plain logits (previous launch) or from LL words of the head GEMV of this launch
-__device__ __forceinline__ int sample_here(const LLParams& p, const LLSmem& s, const float* plain, const u64* ll, uint32_t tag,
-                                           int V, const q3t_sampling& sp, const unsigned int* seen, int step, int g) {
+__device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint32_t tag, int V, const q3t_sampling& sp,
+                                 const unsigned int* seen, int step, int g) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
     float* sc = reinterpret_cast<float*>(s.xfrag);            // [V]  (aliases the digit planes: re-zeroed below)
     float* pe = sc + SAMPLE_MAXV;                              // [V]
@@ -720,47 +827,84 @@ __device__ __forceinline__ int sample_here(const LLParams& p, const LLSmem& s, c
     return choice;
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams p) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    LLSmem s;
-    {
-        unsigned char* q = smem_raw;
-        s.ring = q; q += (size_t)LL_NSLOT * Q3T_TILE_BYTES;
-        s.xfrag = reinterpret_cast<uint4*>(q); q += (size_t)(LL_MAXK / 64) * 512;
-        s.xsum = reinterpret_cast<float*>(q); q += (LL_MAXK / 64) * 4;
-        s.xscl = reinterpret_cast<float*>(q); q += (LL_MAXK / 64) * 4;
-        s.resid = reinterpret_cast<float*>(q); q += LL_MAXH * 4;
-        s.xnext = reinterpret_cast<float*>(q); q += LL_MAXH * 4;
-        s.tile_out = reinterpret_cast<float*>(q); q += LL_MAXT * 16 * 4;
-        s.att = reinterpret_cast<float*>(q); q += LL_ATT_FLOATS * 4;
-        s.red = reinterpret_cast<float*>(q); q += 64 * 4;
-        s.cs = reinterpret_cast<float*>(q); q += 64 * 4;
-        s.sn = reinterpret_cast<float*>(q); q += 64 * 4;
-        s.ibuf = reinterpret_cast<int*>(q); q += 64 * 4;
-        s.full = reinterpret_cast<uint64_t*>(q); q += LL_NSLOT * 8;
-        s.empty = reinterpret_cast<uint64_t*>(q);
+// one code-predictor pass: projected input -> 5 layers (-> head -> sampled code)
+__device__ __noinline__ int cp_pass(CState& st, const float* src, int pos, int g_head, int step) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
+    const int tid = threadIdx.x, Hc = p.cp.hidden, G = p.n_groups;
+    pro_plain(src, p.emb_dim);
+    const uint32_t t_proj = ++st.gen;
+    gemv_phase(st, s.hd[0], EPI_RAW, p.x_proj, nullptr, t_proj);
+    for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS) reinterpret_cast<float4*>(s.resid)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    StackIO io{p.x_proj, t_proj, g_head >= 0, nullptr};
+    stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, io);
+    if (g_head < 0) return 0;
+    const uint32_t t_head = ++st.gen;
+    float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
+    gemv_phase(st, s.hd[2 + g_head], EPI_RAW, p.x_head, lg, t_head);
+    int c = sample_here(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g_head + 1);
+    const long long fo = (long long)step * G + g_head + 1;
+    const bool rec = (blockIdx.x == 0 && tid == 0);
+    if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo] = c;
+    if (p.forced) c = p.forced[fo];
+    if (rec) {
+        p.cur_codes[g_head + 1] = c;
+        if (step < p.max_frames) p.codes[fo] = c;
     }
+    return c;
+}
+
+__device__ __forceinline__ void build_mat(MatD& d, const q3t_w8& w, int cta, int grid) {
+    d.w = reinterpret_cast<const uint8_t*>(w.w); d.bias = w.lin_bias; d.nkc = w.K >> 8; d.N = w.N;
+    const unsigned nrt = (unsigned)(w.N >> 4);
+    d.rb = (int)((nrt * (unsigned)cta) / (unsigned)grid);
+    d.re = (int)((nrt * (unsigned)(cta + 1)) / (unsigned)grid);
+}
+__device__ __forceinline__ void build_layer(LayerD& d, const q3t_layer& L, int cta, int grid) {
+    build_mat(d.qkv, L.qkv, cta, grid); build_mat(d.o, L.o, cta, grid);
+    build_mat(d.gu, L.gate_up, cta, grid); build_mat(d.down, L.down, cta, grid);
+    d.input_norm = L.input_norm; d.post_norm = L.post_norm; d.q_norm = L.q_norm; d.k_norm = L.k_norm;
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams p_in) {
+    static_assert(sizeof(LLParams) <= LL_OFF_LAY, "LLParams must fit the first KB of shared memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, cta = blockIdx.x;
+    {   // launch parameters -> shared memory (device functions read them through ll_params())
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&p_in);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(ll_smem_raw);
+        for (int i = tid; i < (int)(sizeof(LLParams) / 4); i += LL_THREADS) dst[i] = src[i];
+    }
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
+    const int G = p_in.n_groups, nA = p_in.talker.n_layers, nB = p_in.mode == LL_MODE_FRAME ? p_in.cp.n_layers : 0;
+    // descriptor tables (this CTA's row-tile ranges included)
+    if (tid < nA) build_layer(s.lay[tid], p_in.talker.layers[tid], cta, gridDim.x);
+    else if (tid < nA + nB) build_layer(s.lay[tid], p_in.cp.layers[tid - nA], cta, gridDim.x);
+    if (p_in.mode == LL_MODE_FRAME) {
+        if (tid == 64) build_mat(s.hd[0], p_in.cp_proj, cta, gridDim.x);
+        if (tid == 65) build_mat(s.hd[1], p_in.codec_head, cta, gridDim.x);
+        if (tid >= 66 && tid < 66 + G - 1) build_mat(s.hd[2 + tid - 66], p_in.cp_heads[tid - 66], cta, gridDim.x);
+    } else if (tid == 65 && p_in.head.w) build_mat(s.hd[1], p_in.head, cta, gridDim.x);
     if (tid == 0) {
         for (int i = 0; i < LL_NSLOT; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < (LL_MAXK / 64) * 32; i += LL_THREADS) s.xfrag[i] = make_uint4(0, 0, 0, 0);
+    if (tid == 0) s.ibuf[63] = 0;
     __syncthreads();
-    const int G = p.n_groups;
 
     if (warp == LL_CWARPS) {
         // =========================== producer ================================================================
-        if (lane < LL_PLANES) {
-            Producer pr{s, p.state, lane, 0u};
+        if (lane < LL_PLANES + (p.pf_dist > 0 ? 1 : 0)) {
+            Producer pr{p.state, lane, 0u, p.pf_dist};
             if (p.mode == LL_MODE_STACK) {
-                pr.stack(p.which ? p.cp : p.talker);
-                if (p.head.w) pr.stream(p.head);
+                pr.stack(s.lay, nA);
+                if (p.head.w) pr.stream(s.hd[1]);
             } else {
-                pr.stream(p.cp_proj); pr.stack(p.cp);
-                for (int g = 0; g < G - 1; ++g) { pr.stream(p.cp_proj); pr.stack(p.cp); pr.stream(p.cp_heads[g]); }
-                pr.stack(p.talker); pr.stream(p.codec_head);
+                pr.stream(s.hd[0]); pr.stack(s.lay + nA, nB);
+                for (int g = 0; g < G - 1; ++g) { pr.stream(s.hd[0]); pr.stack(s.lay + nA, nB); pr.stream(s.hd[2 + g]); }
+                pr.stack(s.lay, nA); pr.stream(s.hd[1]);
             }
         }
         return;
@@ -768,32 +912,29 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
 
     // =============================== consumers ================================================================
     CState st;
-    st.seq = 0; st.nstamp = 0;
+    st.seq = 0; st.nstamp = 0; st.red_par = 0; st.nsplit = 1; st.chunk = 128;
     st.gen = *reinterpret_cast<volatile unsigned int*>(p.state);
     LL_STAMP();
     if (p.mode == LL_MODE_STACK) {
-        const LLStack& S = p.which ? p.cp : p.talker;
         const int pos = __ldcg(p.pos);
-        for (int k4 = tid; k4 < (S.hidden >> 2); k4 += LL_CTHREADS)
+        for (int k4 = tid; k4 < (p.talker.hidden >> 2); k4 += LL_CTHREADS)
             reinterpret_cast<float4*>(s.resid)[k4] = __ldcg(reinterpret_cast<const float4*>(p.x_in) + k4);
-        cbar();
         StackIO io{nullptr, 0u, p.hidden_out != nullptr || p.head.w != nullptr, p.hidden_out};
-        stack_consume(p, s, st, S, pos, io);
+        stack_consume(st, p.talker, s.lay, pos, io);
         if (p.head.w) {
             const uint32_t t_head = ++st.gen;
-            gemv_phase(p, s, st, p.head, EPI_RAW, p.x_head, p.logits_out, t_head);
+            gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits_out, t_head);
         }
         LL_STAMP();
     } else {
         const int step = __ldcg(p.step), pos_t = __ldcg(p.pos_talker);
-        const int H = p.talker.hidden, Hc = p.cp.hidden, E = p.emb_dim;
+        const int H = p.talker.hidden, E = p.emb_dim;
         const long long fo = (long long)step * G;             // offset of this frame in forced / own / codes
         const bool rec = (cta == 0 && tid == 0);
+        const bool xon = tid < (H >> 2);
         // ---- code 0 from the talker logits of the previous launch
-        int code = sample_here(p, s, p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, 0);
-        if (rec) {
-            if (p.own_codes && step < p.max_frames) p.own_codes[fo] = code;
-        }
+        int code = sample_here(p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, 0);
+        if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo] = code;
         if (p.forced) code = p.forced[fo];
         if (rec) {
             p.cur_codes[0] = code;
@@ -802,55 +943,38 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         }
         const int code0 = code;
         LL_STAMP();
-        // ---- code predictor: position 0 = projected talker hidden
-        auto cp_pass = [&](const float* src, int src_dim, int accumulate, int pos, const q3t_w8* head, int g) -> int {
-            pro_plain(s, src, src_dim, accumulate);
-            const uint32_t t_proj = ++st.gen;
-            gemv_phase(p, s, st, p.cp_proj, EPI_RAW, p.x_proj, nullptr, t_proj);
-            for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS) reinterpret_cast<float4*>(s.resid)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
-            cbar();
-            StackIO io{p.x_proj, t_proj, head != nullptr, nullptr};
-            stack_consume(p, s, st, p.cp, pos, io);
-            if (!head) return 0;
-            const uint32_t t_head = ++st.gen;
-            float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g * p.cp_vocab : p.cp_logits) : nullptr;
-            gemv_phase(p, s, st, *head, EPI_RAW, p.x_head, lg, t_head);
-            int c = sample_here(p, s, nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g + 1);
-            if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo + g + 1] = c;
-            if (p.forced) c = p.forced[fo + g + 1];
-            if (rec) {
-                p.cur_codes[g + 1] = c;
-                if (step < p.max_frames) p.codes[fo + g + 1] = c;
-            }
-            return c;
-        };
-        cp_pass(p.hidden, H, 0, 0, nullptr, 0);
+        // ---- code predictor: position 0 = projected talker hidden, then one pass per residual codebook.
+        // The next talker input is accumulated on the way, in registers: emb0[c0] + emb1[c1] + ... in order
+        cp_pass(st, p.hidden, 0, -1, step);
         LL_STAMP();
+        float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int g = 0; g < G - 1; ++g) {
             const float* row = (g == 0 ? p.codec_embedding : p.cp_embeddings[g - 1]) + (size_t)code * E;
-            code = cp_pass(row, E, g == 0 ? 1 : 2, g + 1, &p.cp_heads[g], g);
+            if (xon) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(row) + tid);
+                if (g == 0) xn = r4; else { xn.x += r4.x; xn.y += r4.y; xn.z += r4.z; xn.w += r4.w; }
+            }
+            code = cp_pass(st, row, g + 1, g, step);
             LL_STAMP();
         }
-        // ---- next talker input: running sum (+ last code's row) + trailing text row   (order g = 0..15, then text)
+        // ---- next talker input: running sum + last code's row, then the trailing text row
         {
             const float* last = p.cp_embeddings[G - 2] + (size_t)code * E;
             const int trow = step < p.n_trailing - 1 ? step : p.n_trailing - 1;
             const float* tr = p.trailing + (size_t)trow * H;
-            for (int k4 = tid; k4 < (H >> 2); k4 += LL_CTHREADS) {
-                float4 a = reinterpret_cast<float4*>(s.xnext)[k4];
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(last) + k4);
-                const float4 c = __ldcg(reinterpret_cast<const float4*>(tr) + k4);
-                a.x = (a.x + b.x) + c.x; a.y = (a.y + b.y) + c.y; a.z = (a.z + b.z) + c.z; a.w = (a.w + b.w) + c.w;
-                reinterpret_cast<float4*>(s.resid)[k4] = a;
-                if (cta == 0) reinterpret_cast<float4*>(p.x)[k4] = a;
+            if (xon) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(last) + tid);
+                const float4 c = __ldcg(reinterpret_cast<const float4*>(tr) + tid);
+                xn.x = (xn.x + b.x) + c.x; xn.y = (xn.y + b.y) + c.y; xn.z = (xn.z + b.z) + c.z; xn.w = (xn.w + b.w) + c.w;
+                reinterpret_cast<float4*>(s.resid)[tid] = xn;
+                if (cta == 0) reinterpret_cast<float4*>(p.x)[tid] = xn;
             }
-            cbar();
         }
         // ---- talker decode step
         StackIO io{nullptr, 0u, true, p.hidden};
-        stack_consume(p, s, st, p.talker, pos_t, io);
+        stack_consume(st, p.talker, s.lay, pos_t, io);
         const uint32_t t_head = ++st.gen;
-        gemv_phase(p, s, st, p.codec_head, EPI_RAW, p.x_head, p.logits, t_head);
+        gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits, t_head);
         LL_STAMP();
         // state other CTAs read at the start of the launch is only updated here, after the last all-to-all exchange
         if (rec) {
@@ -877,6 +1001,8 @@ static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
     Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
     Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
+    Q3T_REQUIRE(st.max_pages <= 64 * (grid / st.n_kv_heads < LL_MAXSPLIT ? grid / st.n_kv_heads : LL_MAXSPLIT),
+                "frame_ll: context too long for the per-CTA page-id table");
     const int qkv_n = (st.n_heads + 2 * st.n_kv_heads) * st.head_dim;
     const int n_max = 2 * st.inter > qkv_n ? 2 * st.inter : qkv_n;
     const long long t1 = ((long long)(n_max / 16) + grid - 1) / grid * (st.hidden / 256);
@@ -886,54 +1012,45 @@ static int check_stack(const q3t_stack& st, int grid) {
 }
 
 // exchange-buffer layout inside the caller's workspace (64-bit words)
+struct LLSizes { long long qkv, attn, hid, act; };
+static LLSizes ll_sizes(const q3t_stack* t, const q3t_stack* c) {
+    LLSizes z = {0, 0, 0, 0};
+    const q3t_stack* ss[2] = {t, c};
+    for (int i = 0; i < 2; ++i) {
+        if (!ss[i]) continue;
+        const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
+        const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
+        z.qkv = q > z.qkv ? q : z.qkv; z.attn = a > z.attn ? a : z.attn;
+        z.hid = ss[i]->hidden > z.hid ? ss[i]->hidden : z.hid; z.act = ss[i]->inter > z.act ? ss[i]->inter : z.act;
+    }
+    return z;
+}
+static long long up16(long long v) { return (v + 15) / 16 * 16; }
 static long long ll_words(const q3t_stack* t, const q3t_stack* c, int head_max) {
-    long long w = 0;
-    const q3t_stack* ss[2] = {t, c};
-    long long qkv = 0, attn = 0, hid = 0, act = 0;
-    for (int i = 0; i < 2; ++i) {
-        if (!ss[i]) continue;
-        const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
-        qkv = q > qkv ? q : qkv;
-        const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
-        attn = a > attn ? a : attn;
-        hid = ss[i]->hidden > hid ? ss[i]->hidden : hid;
-        act = ss[i]->inter > act ? ss[i]->inter : act;
-    }
-    w = qkv + attn + 3 * hid + act + head_max + 64;
-    return (w + 15) / 16 * 16;
+    const LLSizes z = ll_sizes(t, c);
+    return up16(z.qkv) + up16(z.attn) + 3 * up16(z.hid) + up16(z.act) + up16(head_max) + 64;
 }
-
-static void carve(LLParams& p, void* work, const q3t_stack* t, const q3t_stack* c, int head_max) {
-    long long qkv = 0, attn = 0, hid = 0, act = 0;
-    const q3t_stack* ss[2] = {t, c};
-    for (int i = 0; i < 2; ++i) {
-        if (!ss[i]) continue;
-        const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
-        qkv = q > qkv ? q : qkv;
-        const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
-        attn = a > attn ? a : attn;
-        hid = ss[i]->hidden > hid ? ss[i]->hidden : hid;
-        act = ss[i]->inter > act ? ss[i]->inter : act;
-    }
-    auto up = [](long long v) { return (v + 15) / 16 * 16; };
+static void carve(LLParams& p, void* work, const q3t_stack* t, const q3t_stack* c) {
+    const LLSizes z = ll_sizes(t, c);
     u64* w = (u64*)work;
-    p.x_qkv = w; w += up(qkv);
-    p.x_attn = w; w += up(attn);
-    p.x_o = w; w += up(hid);
-    p.x_down = w; w += up(hid);
-    p.x_proj = w; w += up(hid);
-    p.x_act = w; w += up(act);
+    p.x_qkv = w; w += up16(z.qkv);
+    p.x_attn = w; w += up16(z.attn);
+    p.x_o = w; w += up16(z.hid);
+    p.x_down = w; w += up16(z.hid);
+    p.x_proj = w; w += up16(z.hid);
+    p.x_act = w; w += up16(z.act);
     p.x_head = w;
-    (void)head_max;
 }
 
-static int launch_ll(const LLParams& p, cudaStream_t stream) {
+static int launch_ll(LLParams& p, cudaStream_t stream) {
+    static int pf = -1;
+    if (pf < 0) { const char* e = getenv("Q3T_LL_PF"); pf = e ? atoi(e) : 0; }
+    p.pf_dist = pf;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(frame_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM_BYTES);
         attr_set = true;
     }
-    static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(num_sms()); cfg.blockDim = dim3(LL_THREADS); cfg.dynamicSmemBytes = LL_SMEM_BYTES; cfg.stream = stream;
@@ -949,13 +1066,14 @@ static int launch_ll(const LLParams& p, cudaStream_t stream) {
 int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream) {
     const int grid = num_sms();
     if (int rc = check_stack(a->stack, grid)) return rc;
+    Q3T_REQUIRE(a->stack.n_layers <= LL_MAXLAYERS, "stack_pass: too many layers");
     Q3T_REQUIRE(a->ll_work && a->ll_state, "stack_pass: workspace missing");
     if (a->head.w) Q3T_REQUIRE(a->head.N % 16 == 0 && a->head.K == a->stack.hidden, "stack_pass: head shape");
     LLParams p;
     memset(&p, 0, sizeof(p));
-    p.mode = LL_MODE_STACK; p.which = 0;
+    p.mode = LL_MODE_STACK;
     fill_stack(p.talker, a->stack);
-    carve(p, a->ll_work, &a->stack, nullptr, a->head.w ? a->head.N : 0);
+    carve(p, a->ll_work, &a->stack, nullptr);
     Q3T_REQUIRE(ll_words(&a->stack, nullptr, a->head.w ? a->head.N : 0) * 8 <= a->ll_work_bytes, "stack_pass: workspace too small");
     p.state = a->ll_state; p.timing = a->timing;
     p.pos = a->pos; p.x_in = a->x_in; p.hidden_out = a->hidden_out; p.logits_out = a->logits_out; p.head = a->head;
@@ -968,17 +1086,20 @@ int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream) {
     if (int rc = check_stack(f->talker, grid)) return rc;
     if (int rc = check_stack(f->cp, grid)) return rc;
     Q3T_REQUIRE(f->B == 1, "frame_ll: batch 1 only");
+    Q3T_REQUIRE(f->talker.n_layers + f->cp.n_layers <= LL_MAXLAYERS && f->talker.n_layers <= 64 && f->n_groups + 1 <= LL_MAXHEADS,
+                "frame_ll: too many layers / code groups");
     Q3T_REQUIRE(f->ll_work && f->ll_state && f->cp_heads_dev && f->cp_embeddings_dev, "frame_ll: workspace / device tables missing");
     Q3T_REQUIRE(f->talker_vocab <= SAMPLE_MAXV && f->cp_vocab <= SAMPLE_MAXV && f->talker_vocab % 16 == 0 && f->cp_vocab % 16 == 0,
                 "frame_ll: vocabulary size");
-    Q3T_REQUIRE(f->cp_proj.K == f->talker.hidden && f->cp_proj.N == f->cp.hidden, "frame_ll: cp_proj shape (embedding width must equal the talker hidden size)");
+    Q3T_REQUIRE(f->cp_proj.K == f->talker.hidden && f->cp_proj.N == f->cp.hidden,
+                "frame_ll: cp_proj shape (embedding width must equal the talker hidden size)");
     const int head_max = f->talker_vocab > f->cp_vocab ? f->talker_vocab : f->cp_vocab;
     Q3T_REQUIRE(ll_words(&f->talker, &f->cp, head_max) * 8 <= f->ll_work_bytes, "frame_ll: workspace too small");
     LLParams p;
     memset(&p, 0, sizeof(p));
     p.mode = LL_MODE_FRAME;
     fill_stack(p.talker, f->talker); fill_stack(p.cp, f->cp);
-    carve(p, f->ll_work, &f->talker, &f->cp, head_max);
+    carve(p, f->ll_work, &f->talker, &f->cp);
     p.state = f->ll_state; p.timing = f->ll_timing;
     p.codec_head = f->codec_head; p.cp_proj = f->cp_proj; p.cp_heads = f->cp_heads_dev;
     p.codec_embedding = f->codec_embedding; p.cp_embeddings = f->cp_embeddings_dev;

@@ -182,6 +182,7 @@ class TalkerEngine:
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.use_graphs = True
         self.launches_per_frame = None
+        self.launches: Dict[str, int] = {}
 
     # ---- configuration ---------------------------------------------------------------------------
     def set_sampling(self, do_sample: bool = False, temperature: float = 0.9, top_k: int = 50, top_p: float = 1.0,
@@ -275,8 +276,9 @@ class TalkerEngine:
             with torch.cuda.graph(g):
                 fn()
             self._graphs[key] = g
+            self.launches[key] = int(self.lib.q3t_launch_count() - n0)
             if key == "frame":
-                self.launches_per_frame = int(self.lib.q3t_launch_count() - n0)
+                self.launches_per_frame = self.launches[key]
         torch.cuda.synchronize()
 
     def _run(self, key: str):

@@ -66,7 +66,8 @@ def test_w8_gemv_prologues_epilogues(cuda):
     o.lin_bias = 0
     gu = torch.randn(1, 2 * k, generator=g)
     ref = torch.nn.functional.silu(((torch.nn.functional.silu(gu[:, :k]) * gu[:, k:]).double() @ wd.double().T))
-    gud = gu.to(cuda)
+    # device layout of a fused gate/up output: blocks of 8 gate values followed by the matching 8 up values
+    gud = torch.cat([gu[:, :k].reshape(1, -1, 8), gu[:, k:].reshape(1, -1, 8)], 2).reshape(1, 2 * k).contiguous().to(cuda)
     y = torch.empty(1, n, device=cuda)
     a = L.GemvArgs()
     a.w, a.M, a.prologue, a.act = o, 1, L.PRO_SWIGLU, L.ACT_SILU

@@ -5,7 +5,7 @@ from oracle import qwen3_tts_oracle as O
 from qwen3_tts_b200 import config as Cfg
 from qwen3_tts_b200.model import Model
 from qwen3_tts_b200.weights import make_weights
-from test_gpu_pipeline import _text_ids, _safe_frames
+from test_gpu_pipeline import _text_ids
 cfg = Cfg.small("custom_voice"); ws = make_weights(cfg, seed=0, head_std=0.2)
 model = Model(cfg, ws, "cuda", max_frames=64, max_ctx=256, max_trailing=64)
 oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
@@ -14,7 +14,7 @@ vec = torch.randn(cfg.talker.hidden_size, generator=torch.Generator().manual_see
 pre, tr = oracle.build_prefill(ids, streaming=True, speaker_vec=vec)
 n = 14
 codes_o, rec = oracle.generate(pre, tr, n, record=True)
-print("safe", _safe_frames(rec), "talker margins", [round(m, 4) for m in rec["margins"]])
+print("talker margins", [round(m, 4) for m in rec["margins"]])
 cpm = [float((torch.topk(c, 2, -1).values[:, 0] - torch.topk(c, 2, -1).values[:, 1]).min()) for c in rec["cp_logits"]]
 print("cp min margins", [round(m, 4) for m in cpm])
 e = model.engine

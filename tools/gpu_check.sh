@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU-box pass: parity tests, bench, ncu launch list + one full capture of the dominant kernel.
 # usage: tools/gpu_check.sh <tag> [kernel-regex]
-tag="${1:-run}"; kre="${2:-stack_pass}"
+tag="${1:-run}"; kre="${2:-frame_ll}"
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi_$tag.txt 2>&1
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_$tag.log
