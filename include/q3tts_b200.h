@@ -72,6 +72,29 @@ typedef struct {
 
 int q3t_w8_gemv(const q3t_gemv_args* a, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * W8 GEMM on the tcgen05 tensor cores (replaces mx.quantized_matmul, qmm path: batched decode, prefill)
+ *   y[m, :] = epilogue( W8 . prologue(x[m, :]) ),  m < M (any M >= 1), N % 128 == 0, K % 256 == 0
+ * Same prologues / gather / epilogue as q3t_w8_gemv; operands are rounded to bf16, accumulation is fp32 in TMEM.
+ * swiglu_out != 0: W is a fused gate/up matrix with rows interleaved in blocks of 8; the kernel writes
+ *   y[m, 8j + r] = silu(gate[8j + r]) * up[8j + r]   (N/2 values per row) and ignores act / resid.
+ * xb: bf16 scratch of at least M*K elements (the prologue's output, consumed by the GEMM).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    q3t_w8 w;
+    int M;
+    int prologue;
+    const float* x;  long long x_stride;
+    const float* norm_w;  float eps;
+    const int* gather_idx;  int gather_idx_stride;  long long gather_row_stride;
+    int act;  int swiglu_out;
+    const float* resid;  long long resid_stride;
+    float* y;  long long y_stride;
+    void* xb;
+} q3t_gemm_args;
+
+int q3t_w8_gemm(const q3t_gemm_args* a, void* stream);
+
 /* RMSNorm rows: y[m,:] = x[m,:] * rsqrt(mean(x^2)+eps) * w            (mx.fast.rms_norm) */
 int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, void* stream);
 

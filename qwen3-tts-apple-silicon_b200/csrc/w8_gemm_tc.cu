@@ -1,0 +1,344 @@
+// W8 (affine, group 64) dequant-fused GEMM on the 5th-generation tensor cores (tcgen05 + TMEM) for sm_100a:
+//     Y[m, n] = epilogue( sum_k  X[m, k] * dequant(W8)[n, k] )          M = tokens (batch-64 decode, prefill), N = features
+// Replaces mx.quantized_matmul (qmm path: batched decode and prefill) of the reference stack.
+//
+// Shape of the problem: W is streamed from HBM exactly once per launch, so at M = 64 the kernel is HBM-bound and at
+// prefill sizes tensor-bound.  W plays the MMA "A" operand (128 output features per CTA = eight 16-row W8 tiles), the
+// activations are the "B" operand (up to 256 tokens per CTA), the fp32 accumulator D[128 features x tokens] lives in TMEM.
+//   warp 0      : producer - cp.async.bulk (TMA, no tensor map: W8 tiles are contiguous 4352-byte records) into a 2-stage
+//                 ring of raw tiles, one stage = the eight tiles of one 256-wide K chunk
+//   warp 1      : allocates TMEM; one elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M=128, N=tokens,
+//                 K=16 per instruction, four per 64-wide K block) and commits to mbarriers
+//   warps 2..9  : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout
+//                 (warp w owns row tile w; codes are fragment-ordered in HBM, every lane converts 32 codes per block:
+//                 byte -> fp32 by the 2^23 trick, one FFMA with the group scale/bias, cvt.rn.bf16x2, 8-byte stores),
+//                 (b) copy the matching activation block (bf16, prepared by act_prep_kernel) into the B operand layout,
+//                 then fence.proxy.async + mbarrier arrive;  (c) warps 2..5 run the epilogue: tcgen05.ld (32 lanes x 32
+//                 columns) -> bias / SiLU / SwiGLU pair / residual -> coalesced fp32 stores.
+// Numerics: bf16 operands, fp32 accumulation (BASELINE.json: "logits within 1e-2 relative (bf16)"); the batch-1/2 GEMV
+// (w8_gemv.cu, frame_ll.cu) stays exact-integer.
+#include "common.cuh"
+#include "../../include/q3tts_b200.h"
+
+namespace q3t {
+
+constexpr int TC_THREADS = 320;                 // 10 warps
+constexpr int TC_DQ_WARPS = 8;
+constexpr int TC_BM = 128;                      // features per CTA (MMA M)
+constexpr int TC_BN_MAX = 256;                  // tokens per CTA (MMA N)
+constexpr int TC_BK = 64;                       // K per operand stage (= one quantisation group = one 128-byte swizzle row)
+constexpr int TC_STAGES = 3;
+constexpr int TC_RAW_STAGES = 2;
+constexpr int TC_RAW_BYTES = 8 * Q3T_TILE_BYTES;            // 34 816
+constexpr int TC_A_BYTES = TC_BM * 128;                      // 16 384
+constexpr int TC_B_BYTES = TC_BN_MAX * 128;                  // 32 768
+constexpr int TC_OFF_A = 0;
+constexpr int TC_OFF_B = TC_OFF_A + TC_STAGES * TC_A_BYTES;  // 49 152
+constexpr int TC_OFF_RAW = TC_OFF_B + TC_STAGES * TC_B_BYTES;   // 147 456
+constexpr int TC_OFF_BAR = TC_OFF_RAW + TC_RAW_STAGES * TC_RAW_BYTES;   // 217 088
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;      // + barriers + slack for the 1024-byte alignment of the base
+
+struct GemmParams {
+    const uint8_t* w; int N, K;                 // W8 tiles [N/16][K/256]
+    const __nv_bfloat16* xb; long long xb_stride;   // activations [M, K] bf16
+    int M;
+    const float* lin_bias; int act; int swiglu;     // epilogue
+    const float* resid; long long resid_stride;
+    float* y; long long y_stride;
+    int bn;                                     // tokens per CTA (multiple of 16, <= 256)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "TC_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TC_DONE;\n"
+        "bra TC_WAIT;\n"
+        "TC_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_tma_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory operand descriptor: 8-row groups are 1024 bytes apart (SBO), version 1 (sm_100)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmParams p) {
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
+    uint64_t* full_ab = bars;                        // [TC_STAGES]   dequant + B copy done   (8 warp arrivals)
+    uint64_t* empty_ab = bars + TC_STAGES;           // [TC_STAGES]   MMA done with the stage (tcgen05.commit)
+    uint64_t* full_raw = bars + 2 * TC_STAGES;       // [TC_RAW_STAGES] TMA landed
+    uint64_t* empty_raw = full_raw + TC_RAW_STAGES;  // [TC_RAW_STAGES] 8 warp arrivals
+    uint64_t* tmem_full = empty_raw + TC_RAW_STAGES; // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nb = blockIdx.x, m0 = blockIdx.y * p.bn;
+    const int nkc = p.K >> 8, nkb = p.K >> 6;
+    const int bn = p.bn;
+
+    if (tid == 0) {
+        for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_ab[i]), TC_DQ_WARPS); tc_mbar_init(tc_smem_u32(&empty_ab[i]), 1); }
+        for (int i = 0; i < TC_RAW_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_raw[i]), 1); tc_mbar_init(tc_smem_u32(&empty_raw[i]), TC_DQ_WARPS); }
+        tc_mbar_init(tc_smem_u32(tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "n"(TC_BN_MAX) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ===================== producer: raw W8 tiles (weights do not depend on the previous kernel) =====================
+        if (lane == 0) {
+            for (int kc = 0; kc < nkc; ++kc) {
+                const int rs = kc % TC_RAW_STAGES, par = (kc / TC_RAW_STAGES) & 1;
+                tc_mbar_wait(tc_smem_u32(&empty_raw[rs]), par ^ 1);
+                const uint32_t fb = tc_smem_u32(&full_raw[rs]);
+                tc_mbar_expect_tx(fb, TC_RAW_BYTES);
+                unsigned char* dst = smem + TC_OFF_RAW + rs * TC_RAW_BYTES;
+                for (int rt = 0; rt < 8; ++rt)
+                    tc_tma_load_1d(tc_smem_u32(dst + rt * Q3T_TILE_BYTES),
+                                   p.w + ((size_t)(nb * 8 + rt) * nkc + kc) * Q3T_TILE_BYTES, Q3T_TILE_BYTES, fb);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =================================================================================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+                tc_mbar_wait(tc_smem_u32(&full_ab[st]), par);
+                tc_fence_after();
+                const uint64_t a_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_A + st * TC_A_BYTES));
+                const uint64_t b_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES));
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)      // 16 bf16 = 32 bytes = 2 descriptor units along K
+                    tc_mma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                tc_commit(tc_smem_u32(&empty_ab[st]));     // frees the stage once these MMAs have read it
+            }
+            tc_commit(tc_smem_u32(tmem_full));              // accumulator complete
+        }
+    } else {
+        // ===================== dequant + activation copy (8 warps), then epilogue (first 4 of them) =======================
+        const int dw = warp - 2;                  // row tile of this warp inside the 128-row block
+        const int dt = tid - 64;                  // 0..255
+        const int g = lane >> 2, t = lane & 3;
+        pdl_wait();                               // activations come from the previous kernel
+        for (int kb = 0; kb < nkb; ++kb) {
+            const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+            const int kc = kb >> 2, j4 = kb & 3, rs = kc % TC_RAW_STAGES, rpar = (kc / TC_RAW_STAGES) & 1;
+            tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
+            // ---- B operand: tokens m0 .. m0+bn, K block kb; 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
+            {
+                unsigned char* bdst = smem + TC_OFF_B + st * TC_B_BYTES;
+                for (int i = dt; i < bn * 8; i += TC_DQ_WARPS * 32) {
+                    const int r = i >> 3, c = i & 7;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (m0 + r < p.M) v = *reinterpret_cast<const uint4*>(p.xb + (size_t)(m0 + r) * p.xb_stride + kb * TC_BK + c * 8);
+                    *reinterpret_cast<uint4*>(bdst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
+                }
+            }
+            // ---- A operand: dequantise group j4 of this warp's raw tile
+            if (j4 == 0) tc_mbar_wait(tc_smem_u32(&full_raw[rs]), rpar);
+            {
+                const unsigned char* tile = smem + TC_OFF_RAW + rs * TC_RAW_BYTES + dw * Q3T_TILE_BYTES;
+                // scales / biases of rows g and g+8 for group j4: meta row = {4 bf16 scales, 4 bf16 biases}
+                const uint16_t* mlo = reinterpret_cast<const uint16_t*>(tile + 4096 + g * 16);
+                const uint16_t* mhi = reinterpret_cast<const uint16_t*>(tile + 4096 + (g + 8) * 16);
+                const float s_lo = __uint_as_float((uint32_t)mlo[j4] << 16), b_lo = __uint_as_float((uint32_t)mlo[4 + j4] << 16);
+                const float s_hi = __uint_as_float((uint32_t)mhi[j4] << 16), b_hi = __uint_as_float((uint32_t)mhi[4 + j4] << 16);
+                unsigned char* adst = smem + TC_OFF_A + st * TC_A_BYTES + dw * 2048;      // 16 rows = two 8-row swizzle atoms
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + j) * 512 + lane * 16);
+                    const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        // register i: row g + 8*(i&1), k = 32 j + 16 (i>>1) + 4 t + {0..3} inside the group
+                        const float sc = (i & 1) ? s_hi : s_lo, bi = (i & 1) ? b_hi : b_lo;
+                        float f[4];
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const float qf = __uint_as_float(__byte_perm(qq[i], 0x4B000000u, 0x7650 + b)) - 8388608.f;
+                            f[b] = fmaf(sc, qf, bi);
+                        }
+                        const int row8 = g;                       // row inside its 8-row atom
+                        const int chunk = 4 * j + 2 * (i >> 1) + (t >> 1);
+                        uint2 o;
+                        o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
+                        *reinterpret_cast<uint2*>(adst + (i & 1) * 1024 + row8 * 128 + ((chunk ^ row8) << 4) + (t & 1) * 8) = o;
+                    }
+                }
+            }
+            tc_fence_proxy_async();               // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) {
+                tc_mbar_arrive(tc_smem_u32(&full_ab[st]));
+                if (j4 == 3) tc_mbar_arrive(tc_smem_u32(&empty_raw[rs]));
+            }
+        }
+        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 = features of this CTA
+        if (dw < 4) {
+            tc_mbar_wait(tc_smem_u32(tmem_full), 0);
+            tc_fence_after();
+            const int lg = warp & 3;                               // TMEM lane group this warp may read
+            const int f_local = lg * 32 + lane;                    // feature inside the 128-row block
+            const int n = nb * TC_BM + f_local;
+            const float bias = p.lin_bias ? p.lin_bias[n] : 0.f;
+            for (int c0 = 0; c0 < bn; c0 += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const int m = m0 + c0 + c;                     // token (uniform across the warp)
+                    float x = __uint_as_float(v[c]) + bias;
+                    if (p.swiglu) {
+                        // fused gate/up rows: gate rows at 16j..16j+7, matching up rows 8 lanes higher
+                        const float up = __shfl_down_sync(0xffffffffu, x, 8);
+                        x = silu_f(x) * up;
+                        if (c0 + c < bn && m < p.M && (lane & 8) == 0)
+                            p.y[(size_t)m * p.y_stride + (n >> 4) * 8 + (n & 7)] = x;
+                    } else {
+                        if (p.act == Q3T_ACT_SILU) x = silu_f(x);
+                        if (c0 + c < bn && m < p.M) {
+                            if (p.resid) x += p.resid[(size_t)m * p.resid_stride + n];
+                            p.y[(size_t)m * p.y_stride + n] = x;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN_MAX) : "memory");
+    }
+}
+
+// ---- activation preparation: fp32 rows -> (RMSNorm | SwiGLU of interleaved gate/up) -> bf16 rows ------------------------
+struct PrepParams {
+    const float* x; long long x_stride; int M, K, prologue;
+    const float* norm_w; float eps;
+    const int* gather_idx; int gather_idx_stride; long long gather_row_stride;
+    __nv_bfloat16* out; long long out_stride;
+};
+
+__global__ void __launch_bounds__(256) act_prep_kernel(const PrepParams p) {
+    __shared__ float red[32];
+    pdl_wait();
+    pdl_launch_dependents();
+    const int m = blockIdx.x, tid = threadIdx.x;
+    const float* xr = p.x + (size_t)m * p.x_stride;
+    if (p.gather_idx) xr = p.x + (long long)p.gather_idx[(size_t)m * p.gather_idx_stride] * p.gather_row_stride;
+    __nv_bfloat16* o = p.out + (size_t)m * p.out_stride;
+    float rstd = 1.f;
+    if (p.prologue == Q3T_PRO_RMSNORM) {
+        float ss = 0.f;
+        for (int k = tid; k < p.K; k += 256) { const float v = xr[k]; ss += v * v; }
+        rstd = rsqrtf(block_sum(ss, red) / (float)p.K + p.eps);
+    }
+    for (int k = tid; k < p.K; k += 256) {
+        float v;
+        if (p.prologue == Q3T_PRO_SWIGLU) {
+            const int gi = ((k >> 3) << 4) + (k & 7);
+            v = silu_f(xr[gi]) * xr[gi + 8];
+        } else if (p.prologue == Q3T_PRO_RMSNORM) {
+            v = p.norm_w[k] * (xr[k] * rstd);
+        } else {
+            v = xr[k];
+        }
+        o[k] = __float2bfloat16_rn(v);
+    }
+}
+
+int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
+    Q3T_REQUIRE(a->M >= 1, "w8_gemm: M must be >= 1");
+    Q3T_REQUIRE(a->w.N % 128 == 0 && a->w.K % 256 == 0, "w8_gemm: N%128 / K%256");
+    Q3T_REQUIRE(a->xb != nullptr, "w8_gemm: bf16 activation scratch missing");
+    const int K = a->w.K;
+    // 1. activations -> bf16 (with the fused prologue)
+    PrepParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.x = a->x; pp.x_stride = a->x_stride; pp.M = a->M; pp.K = K; pp.prologue = a->prologue; pp.norm_w = a->norm_w; pp.eps = a->eps;
+    pp.gather_idx = a->gather_idx; pp.gather_idx_stride = a->gather_idx_stride; pp.gather_row_stride = a->gather_row_stride;
+    pp.out = (__nv_bfloat16*)a->xb; pp.out_stride = K;
+    launch_pdl(act_prep_kernel, dim3(a->M), dim3(256), 0, stream, pp);
+    Q3T_CHECK_LAUNCH("act_prep");
+    // 2. the GEMM
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.w = (const uint8_t*)a->w.w; p.N = a->w.N; p.K = K; p.xb = (const __nv_bfloat16*)a->xb; p.xb_stride = K; p.M = a->M;
+    p.lin_bias = a->w.lin_bias; p.act = a->act; p.swiglu = a->swiglu_out; p.resid = a->resid; p.resid_stride = a->resid_stride;
+    p.y = a->y; p.y_stride = a->y_stride;
+    int bn = (a->M + 15) / 16 * 16;
+    if (bn > TC_BN_MAX) bn = TC_BN_MAX;
+    if (bn < 16) bn = 16;
+    p.bn = bn;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(w8_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        attr_set = true;
+    }
+    static_assert(TC_SMEM_BYTES <= 227 * 1024, "w8_gemm: shared memory budget exceeded");
+    launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p);
+    Q3T_CHECK_LAUNCH("w8_gemm_tc");
+    return 0;
+}
+
+}  // namespace q3t
+
+extern "C" int q3t_w8_gemm(const q3t_gemm_args* a, void* stream) { return q3t::launch_w8_gemm(a, (cudaStream_t)stream); }

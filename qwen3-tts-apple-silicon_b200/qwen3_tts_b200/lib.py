@@ -28,6 +28,12 @@ class GemvArgs(C.Structure):
                 ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64)]
 
 
+class GemmArgs(C.Structure):
+    _fields_ = [("w", W8), ("M", i32), ("prologue", i32), ("x", vp), ("x_stride", i64), ("norm_w", vp), ("eps", f32),
+                ("gather_idx", vp), ("gather_idx_stride", i32), ("gather_row_stride", i64), ("act", i32),
+                ("swiglu_out", i32), ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64), ("xb", vp)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", vp), ("q_norm_w", vp), ("k_norm_w", vp), ("eps", f32), ("inv_freq", vp), ("kv_pool", vp),
                 ("block_tbl", vp), ("max_pages", i32), ("pos", vp), ("out", vp), ("work", vp), ("counters", vp),
@@ -82,7 +88,7 @@ class TapGemmArgs(C.Structure):
 
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
-SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_rmsnorm", "q3t_attn_decode",
+SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
            "q3t_window_attn", "q3t_snake", "q3t_clamp_pcm16"]
 
@@ -105,6 +111,7 @@ def load() -> C.CDLL:
     lib.q3t_last_error.restype = C.c_char_p
     lib.q3t_launch_count.restype = u64
     lib.q3t_w8_gemv.argtypes = [C.POINTER(GemvArgs), vp]
+    lib.q3t_w8_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.q3t_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     lib.q3t_attn_decode.argtypes = [C.POINTER(AttnArgs), vp]
     lib.q3t_sample.argtypes = [C.POINTER(SampleArgs), vp]

@@ -42,6 +42,93 @@ def test_w8_gemv_raw(cuda, n, k, m):
     assert err < 2e-6, f"rel err {err}"
 
 
+def _bf16(x):
+    return x.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 128, 256), (5, 256, 512), (64, 2048, 2048), (64, 4096, 2048), (100, 2048, 6144),
+                                   (300, 1024, 1024), (64, 3072, 2048), (17, 1024, 256)])
+def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
+    """tcgen05/TMEM W8 GEMM: exact against a reference that rounds both operands to bf16 (fp32 accumulation only),
+    and within the bf16 tolerance of BASELINE.json against the unrounded product."""
+    lib = L.load()
+    o, blob, wd = _w8(n, k, n + k + m, cuda)
+    g = torch.Generator().manual_seed(3 * m + 1)
+    x = torch.randn(m, k, generator=g) * 0.7
+    ref_bf = _bf16(x) @ _bf16(wd).T
+    ref = x.double() @ wd.double().T
+    xd = x.to(cuda)
+    y = torch.full((m, n), float("nan"), device=cuda)
+    xb = torch.empty(m * k, device=cuda, dtype=torch.bfloat16)
+    a = L.GemmArgs()
+    a.w, a.M, a.prologue = o, m, L.PRO_RAW
+    a.x, a.x_stride, a.y, a.y_stride, a.xb = xd.data_ptr(), k, y.data_ptr(), n, xb.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    yd = y.cpu().double()
+    assert torch.isfinite(yd).all()
+    assert (yd - ref_bf).abs().max() / ref_bf.abs().max() < 2e-5, "layout / accumulation error"
+    assert (yd - ref).abs().max() / ref.abs().max() < 1e-2, "bf16 tolerance"
+
+
+def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
+    lib = L.load()
+    n, k, m = 2048, 1024, 37
+    o, blob, wd = _w8(n, k, 5, cuda)
+    g = torch.Generator().manual_seed(12)
+    # RMSNorm prologue + bias + residual (in place)
+    x = torch.randn(m, k, generator=g)
+    nw = 1 + 0.1 * torch.randn(k, generator=g)
+    bias = torch.randn(n, generator=g)
+    resid = torch.randn(m, n, generator=g)
+    ref = _bf16(O.rms_norm(x, nw, 1e-6)) @ _bf16(wd).T + bias.double() + resid.double()
+    xd, nwd, bd, rd = x.to(cuda), nw.to(cuda), bias.to(cuda), resid.to(cuda)
+    xb = torch.empty(m * 2 * k, device=cuda, dtype=torch.bfloat16)
+    o.lin_bias = bd.data_ptr()
+    a = L.GemmArgs()
+    a.w, a.M, a.prologue = o, m, L.PRO_RMSNORM
+    a.x, a.x_stride, a.norm_w, a.eps = xd.data_ptr(), k, nwd.data_ptr(), 1e-6
+    a.resid, a.resid_stride, a.y, a.y_stride, a.xb = rd.data_ptr(), n, rd.data_ptr(), n, xb.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    assert (rd.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+    # SwiGLU prologue (interleaved gate/up input) + SiLU epilogue
+    o.lin_bias = 0
+    gu = torch.randn(m, 2 * k, generator=g)
+    act = torch.nn.functional.silu(gu[:, :k]) * gu[:, k:]
+    ref = torch.nn.functional.silu(_bf16(act) @ _bf16(wd).T)
+    gud = torch.cat([gu[:, :k].reshape(m, -1, 8), gu[:, k:].reshape(m, -1, 8)], 2).reshape(m, 2 * k).contiguous().to(cuda)
+    y = torch.empty(m, n, device=cuda)
+    a = L.GemmArgs()
+    a.w, a.M, a.prologue, a.act = o, m, L.PRO_SWIGLU, L.ACT_SILU
+    a.x, a.x_stride, a.y, a.y_stride, a.xb = gud.data_ptr(), 2 * k, y.data_ptr(), n, xb.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+    # SwiGLU OUTPUT epilogue: fused gate/up matrix with rows interleaved in blocks of 8
+    half = n // 2
+    wg, wu = wd[:half], wd[half:]
+    idx = torch.arange(half).view(-1, 8)
+    perm = torch.cat([idx, idx + half], 1).reshape(-1)
+    q, s, b = quantize_w8(wd)            # wd is already on the W8 grid: quantising again is (nearly) lossless
+    wd2 = dequantize_w8(q, s, b)
+    o2 = L.W8()
+    blob2 = pack_w8(q[perm].contiguous().to(cuda), s[perm].contiguous().to(cuda), b[perm].contiguous().to(cuda))
+    o2.w, o2.N, o2.K = blob2.data_ptr(), n, k
+    xr = torch.randn(m, k, generator=g)
+    gate = _bf16(xr) @ _bf16(wd2[:half]).T
+    up = _bf16(xr) @ _bf16(wd2[half:]).T
+    ref = torch.nn.functional.silu(gate) * up
+    y = torch.empty(m, half, device=cuda)
+    xrd = xr.to(cuda)
+    a = L.GemmArgs()
+    a.w, a.M, a.prologue, a.swiglu_out = o2, m, L.PRO_RAW, 1
+    a.x, a.x_stride, a.y, a.y_stride, a.xb = xrd.data_ptr(), k, y.data_ptr(), half, xb.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
+    torch.cuda.synchronize()
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+
+
 def test_w8_gemv_prologues_epilogues(cuda):
     lib = L.load()
     n, k = 2048, 1024
