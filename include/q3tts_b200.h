@@ -118,6 +118,9 @@ typedef struct {
     float* out;
     float* work; int* counters;
     int B, H, Hkv, D, nsplit;
+    int mode;                 /* 0 = fused decode step; 1 = only write K/V of every row (prefill pass 1, use nsplit = 1);
+                                 2 = attention only, K/V of the row itself already in the cache (prefill pass 2) */
+    const int* seq_of_row;    /* optional [B]: block-table row of launch row b (prefill rows of one sequence share pages) */
 } q3t_attn_args;
 
 int q3t_attn_decode(const q3t_attn_args* a, void* stream);
@@ -236,12 +239,28 @@ typedef struct {
     const float* trailing; /* [B, n_trailing, H]; row min(step, n_trailing-1) is added (last row = tts_pad) */
     int n_trailing;
     const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
+    void* gemm_xb;         /* bf16 scratch [B, max K] for the tcgen05 GEMM (used when B > 2), or NULL */
     /* persistent-kernel path (used when use_mega != 0 and B == 1): the whole frame is ONE launch (csrc/frame_ll.cu) */
     int use_mega;
     const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */
     void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
     unsigned long long* ll_timing;  /* optional profiling stamps, or NULL */
 } q3t_frame_args;
+
+/* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).
+ * x [M, H] is the residual stream (in: prompt embeddings; out: last-layer output, pre final norm); pos[m] = position of
+ * row m in its sequence, seq_of_row[m] = its sequence (block-table row).  Workspaces: qkv [M, (H+2Hkv)*D], attn [M, H*D],
+ * gu [M, 2*inter] fp32; xb bf16 [M, max(hidden, inter)].  Fills the KV cache of every layer. */
+typedef struct {
+    const q3t_frame_args* f;
+    int M;
+    float* x; const int* pos; const int* seq_of_row;
+    float* qkv; float* attn; float* gu; void* xb;
+    float* attn_work; int* attn_counters;    /* >= M*Hkv*(H/Hkv)*(D+2) floats, M*Hkv ints (zeroed) */
+} q3t_prefill_args;
+int q3t_talker_prefill(const q3t_prefill_args* a, void* stream);
+/* final RMSNorm of `x` [B, H] -> `hidden`, codec head -> `logits` (the tail of a talker step) */
+int q3t_talker_tail(const q3t_frame_args* f, void* stream);
 
 /* one talker forward for the token currently in `x` (prefill token or decode step), logits optional */
 int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream);

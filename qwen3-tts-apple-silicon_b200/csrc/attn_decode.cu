@@ -22,6 +22,8 @@ struct AttnParams {
     const int* pos;
     float* out; float* work; int* counters;
     int B, H, Hkv, nsplit;
+    int mode;                 // 0 fused decode, 1 write K/V of the row only, 2 attention only (K/V already in the cache)
+    const int* seq_of_row;    // optional: block-table row of launch row b (prefill: many rows share one sequence)
 };
 
 template <int EPL> struct KvVec;
@@ -48,12 +50,12 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
 
     const int kvh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int* btbl = p.block_tbl + (size_t)b * p.max_pages;
+    const int* btbl = p.block_tbl + (size_t)(p.seq_of_row ? p.seq_of_row[b] : b) * p.max_pages;
     const size_t page_elems = (size_t)2 * p.Hkv * Q3T_KV_PAGE * D;
     const size_t head_off = (size_t)kvh * Q3T_KV_PAGE * D;
     const size_t v_off = (size_t)p.Hkv * Q3T_KV_PAGE * D;
     pdl_launch_dependents();
-    {   // before waiting for the QKV GEMV: pull this CTA's K/V pages towards L2.  `pos` may still be one step
+    if (p.mode != 1) {   // before waiting for the QKV GEMV: pull this CTA's K/V pages towards L2.  `pos` may still be one step
         // stale here (it only steers a prefetch); the authoritative read happens after pdl_wait().
         const int ctx_h = __ldcg(p.pos + b) + 1;
         int ch = (ctx_h + p.nsplit - 1) / p.nsplit;
@@ -81,7 +83,8 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
     if (s0 < s1) {
         for (int vi = warp; vi < REP + 2; vi += 4) {
             const bool is_q = vi < REP, is_k = vi == REP;
-            if (!is_q && !owner) continue;
+            if (!is_q && (!owner || p.mode == 2)) continue;
+            if (is_q && p.mode == 1) continue;
             const float* src = is_q ? row + (size_t)(kvh * REP + vi) * D
                                     : (is_k ? row + (size_t)(p.H + kvh) * D : row + (size_t)(p.H + p.Hkv + kvh) * D);
             float x[E];
@@ -117,6 +120,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
             }
         }
     }
+    if (p.mode == 1) return;
     __syncthreads();
 
     // ---- stage 2: stream the slice --------------------------------------------------------------
@@ -232,7 +236,7 @@ int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream) {
     p.qkv = a->qkv; p.q_norm_w = a->q_norm_w; p.k_norm_w = a->k_norm_w; p.eps = a->eps; p.inv_freq = a->inv_freq;
     p.kv_pool = (__nv_bfloat16*)a->kv_pool; p.block_tbl = a->block_tbl; p.max_pages = a->max_pages; p.pos = a->pos;
     p.out = a->out; p.work = a->work; p.counters = a->counters; p.B = a->B; p.H = a->H; p.Hkv = a->Hkv;
-    p.nsplit = a->nsplit;
+    p.nsplit = a->nsplit; p.mode = a->mode; p.seq_of_row = a->seq_of_row;
     const int rep = a->H / a->Hkv;
     if (a->D == 128 && rep == 2) return launch_attn_t<128, 2>(p, stream);
     if (a->D == 128 && rep == 1) return launch_attn_t<128, 1>(p, stream);

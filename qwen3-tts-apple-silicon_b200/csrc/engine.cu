@@ -8,6 +8,7 @@
 namespace q3t {
 
 int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream);
+int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream);
 int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream);
 int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
 int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream);
@@ -65,10 +66,19 @@ int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float
 
 #define Q3T_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
-// y[b0..b0+M) rows through one W8 matrix, two rows per launch
+// rows through one W8 matrix: B <= 2 -> exact-integer GEMV (two rows per launch); more rows -> tcgen05 GEMM (bf16 operands)
+static void* g_xb = nullptr;    // bf16 scratch of the call in flight (set by the entry points below)
 static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
                      const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
                      float* y, long long ys, cudaStream_t s) {
+    if (B > 2 && g_xb && w.N % 128 == 0) {
+        q3t_gemm_args a;
+        memset(&a, 0, sizeof(a));
+        a.w = w; a.M = B; a.prologue = prologue; a.x = x; a.x_stride = xs; a.norm_w = norm_w; a.eps = eps;
+        a.gather_idx = gidx; a.gather_idx_stride = gidx_stride; a.gather_row_stride = grow; a.act = act;
+        a.resid = resid; a.resid_stride = rs; a.y = y; a.y_stride = ys; a.xb = g_xb;
+        return launch_w8_gemm(&a, s);
+    }
     for (int b0 = 0; b0 < B; b0 += 2) {
         q3t_gemv_args a;
         memset(&a, 0, sizeof(a));
@@ -180,12 +190,55 @@ static int frame(const q3t_frame_args* f, cudaStream_t s) {
     return talker_step(f, 1, 1, s);
 }
 
+// ---- talker prefill as GEMMs over all prompt tokens of all sequences (tcgen05 path) -------------------------------------
+static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
+    const q3t_frame_args* f = a->f;
+    const q3t_stack& st = f->talker;
+    const int M = a->M, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim, qkvd = qd + 2 * kvd;
+    Q3T_REQUIRE(M >= 1 && a->x && a->pos && a->seq_of_row && a->qkv && a->attn && a->gu && a->xb, "talker_prefill: arguments");
+    g_xb = a->xb;
+    for (int l = 0; l < st.n_layers; ++l) {
+        const q3t_layer& L = st.layers_host[l];
+        Q3T_TRY(gemv_rows(L.qkv, M, Q3T_PRO_RMSNORM, a->x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->qkv, qkvd, s));
+        q3t_attn_args t;
+        memset(&t, 0, sizeof(t));
+        t.qkv = a->qkv; t.q_norm_w = L.q_norm; t.k_norm_w = L.k_norm; t.eps = st.eps; t.inv_freq = st.inv_freq;
+        t.kv_pool = (char*)st.kv_pool + (long long)l * st.kv_layer_stride_bytes;
+        t.block_tbl = st.block_tbl; t.max_pages = st.max_pages; t.pos = a->pos; t.out = a->attn; t.work = a->attn_work;
+        t.counters = a->attn_counters; t.B = M; t.H = st.n_heads; t.Hkv = st.n_kv_heads; t.D = st.head_dim;
+        t.seq_of_row = a->seq_of_row;
+        t.nsplit = 1; t.mode = 1;                    // pass 1: K/V rows of every prompt token into the cache
+        Q3T_TRY(launch_attn_decode(&t, s));
+        t.mode = 2;                                  // pass 2: causal attention of every row over its prefix
+        Q3T_TRY(launch_attn_decode(&t, s));
+        Q3T_TRY(gemv_rows(L.o, M, Q3T_PRO_RAW, a->attn, qd, nullptr, 0.f, nullptr, 0, 0, 0, a->x, hid, a->x, hid, s));
+        Q3T_TRY(gemv_rows(L.gate_up, M, Q3T_PRO_RMSNORM, a->x, hid, L.post_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->gu,
+                          2 * st.inter, s));
+        Q3T_TRY(gemv_rows(L.down, M, Q3T_PRO_SWIGLU, a->gu, 2 * st.inter, nullptr, 0.f, nullptr, 0, 0, 0, a->x, hid, a->x, hid, s));
+    }
+    return 0;
+}
+
+static int talker_tail(const q3t_frame_args* f, cudaStream_t s) {
+    const q3t_stack& t = f->talker;
+    g_xb = f->gemm_xb;
+    Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
+    return gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->logits,
+                     f->talker_vocab, s);
+}
+
 }  // namespace q3t
 
 extern "C" int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, void* stream) {
     return q3t::launch_rmsnorm(x, w, y, M, H, eps, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream) {
+    q3t::g_xb = f->gemm_xb;
     return q3t::talker_step(f, want_logits, 0, (cudaStream_t)stream);
 }
-extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) { return q3t::frame(f, (cudaStream_t)stream); }
+extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) {
+    q3t::g_xb = f->gemm_xb;
+    return q3t::frame(f, (cudaStream_t)stream);
+}
+extern "C" int q3t_talker_prefill(const q3t_prefill_args* a, void* stream) { return q3t::talker_prefill(a, (cudaStream_t)stream); }
+extern "C" int q3t_talker_tail(const q3t_frame_args* f, void* stream) { return q3t::talker_tail(f, (cudaStream_t)stream); }

@@ -12,11 +12,13 @@
 //   warps 2..9  : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout
 //                 (warp w owns row tile w; codes are fragment-ordered in HBM, every lane converts 32 codes per block:
 //                 byte -> fp32 by the 2^23 trick, one FFMA with the group scale/bias, cvt.rn.bf16x2, 8-byte stores),
-//                 (b) copy the matching activation block (bf16, prepared by act_prep_kernel) into the B operand layout,
-//                 then fence.proxy.async + mbarrier arrive;  (c) warps 2..5 run the epilogue: tcgen05.ld (32 lanes x 32
+//                 then fence.proxy.async + mbarrier arrive; the matching activation block (bf16, prepared by
+//                 act_prep_kernel) is a 2-D TMA tensor-map load with hardware SWIZZLE_128B issued by a second producer lane;
+//                 (c) warps 2..5 run the epilogue: tcgen05.ld (32 lanes x 32
 //                 columns) -> bias / SiLU / SwiGLU pair / residual -> coalesced fp32 stores.
 // Numerics: bf16 operands, fp32 accumulation (BASELINE.json: "logits within 1e-2 relative (bf16)"); the batch-1/2 GEMV
 // (w8_gemv.cu, frame_ll.cu) stays exact-integer.
+#include <cuda.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
@@ -98,7 +100,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_x) {
     extern __shared__ unsigned char tc_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC_OFF_BAR);
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     const int bn = p.bn;
 
     if (tid == 0) {
-        for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_ab[i]), TC_DQ_WARPS); tc_mbar_init(tc_smem_u32(&empty_ab[i]), 1); }
+        for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_ab[i]), TC_DQ_WARPS + 1); tc_mbar_init(tc_smem_u32(&empty_ab[i]), 1); }
         for (int i = 0; i < TC_RAW_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_raw[i]), 1); tc_mbar_init(tc_smem_u32(&empty_raw[i]), TC_DQ_WARPS); }
         tc_mbar_init(tc_smem_u32(tmem_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     pdl_launch_dependents();
 
     if (warp == 0) {
-        // ===================== producer: raw W8 tiles (weights do not depend on the previous kernel) =====================
+        // ===================== producers: lane 0 raw W8 tiles (weights do not depend on the previous kernel),
+        //                       lane 1 activation blocks (2-D tensor map, hardware 128-byte swizzle, OOB rows = 0) =============
         if (lane == 0) {
             for (int kc = 0; kc < nkc; ++kc) {
                 const int rs = kc % TC_RAW_STAGES, par = (kc / TC_RAW_STAGES) & 1;
@@ -142,6 +145,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 for (int rt = 0; rt < 8; ++rt)
                     tc_tma_load_1d(tc_smem_u32(dst + rt * Q3T_TILE_BYTES),
                                    p.w + ((size_t)(nb * 8 + rt) * nkc + kc) * Q3T_TILE_BYTES, Q3T_TILE_BYTES, fb);
+            }
+        } else if (lane == 1) {
+            pdl_wait();                           // the bf16 activations come from the previous kernel
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+                tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
+                const uint32_t fb = tc_smem_u32(&full_ab[st]);
+                tc_mbar_expect_tx(fb, (uint32_t)bn * 128u);
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
+                               "r"(kb * TC_BK), "r"(m0), "r"(fb) : "memory");
             }
         }
     } else if (warp == 1) {
@@ -164,23 +178,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     } else {
         // ===================== dequant + activation copy (8 warps), then epilogue (first 4 of them) =======================
         const int dw = warp - 2;                  // row tile of this warp inside the 128-row block
-        const int dt = tid - 64;                  // 0..255
         const int g = lane >> 2, t = lane & 3;
         pdl_wait();                               // activations come from the previous kernel
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
             const int kc = kb >> 2, j4 = kb & 3, rs = kc % TC_RAW_STAGES, rpar = (kc / TC_RAW_STAGES) & 1;
             tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
-            // ---- B operand: tokens m0 .. m0+bn, K block kb; 16-byte chunk c of row r lands at chunk (c ^ (r & 7))
-            {
-                unsigned char* bdst = smem + TC_OFF_B + st * TC_B_BYTES;
-                for (int i = dt; i < bn * 8; i += TC_DQ_WARPS * 32) {
-                    const int r = i >> 3, c = i & 7;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (m0 + r < p.M) v = *reinterpret_cast<const uint4*>(p.xb + (size_t)(m0 + r) * p.xb_stride + kb * TC_BK + c * 8);
-                    *reinterpret_cast<uint4*>(bdst + (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4)) = v;
-                }
-            }
             // ---- A operand: dequantise group j4 of this warp's raw tile
             if (j4 == 0) tc_mbar_wait(tc_smem_u32(&full_raw[rs]), rpar);
             {
@@ -334,7 +337,29 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
         attr_set = true;
     }
     static_assert(TC_SMEM_BYTES <= 227 * 1024, "w8_gemm: shared memory budget exceeded");
-    launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p);
+    // 2-D tensor map of the bf16 activations [M, K]: box = 64 K-elements (128 bytes) x bn tokens, SWIZZLE_128B, zero fill
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+            snprintf(g_err, sizeof(g_err), "w8_gemm: cuTensorMapEncodeTiled is not available");
+            return 3;
+        }
+        encode = (EncodeFn)fn;
+    }
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)a->M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->xb, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "w8_gemm: cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
+    launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p, tmap);
     Q3T_CHECK_LAUNCH("w8_gemm_tc");
     return 0;
 }

@@ -178,6 +178,11 @@ class TalkerEngine:
         self.ll_state = torch.zeros(4, **i32)
         fa.ll_work, fa.ll_work_bytes, fa.ll_state, fa.ll_timing = self.keep(self.ll_work), nbytes, self.keep(self.ll_state), 0
         fa.use_mega = int(use_mega and self.B == 1)
+        # tcgen05 GEMM path (more than two rows per contraction): bf16 activation scratch
+        kmax = max(t.hidden_size, t.intermediate_size, c.hidden_size, c.intermediate_size, t.q_dim, c.q_dim)
+        self.gemm_xb = torch.empty(max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
+        fa.gemm_xb = self.keep(self.gemm_xb)
+        self.gemm_prefill = self.B > 2
         self.set_sampling()
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.use_graphs = True
@@ -307,12 +312,44 @@ class TalkerEngine:
         tr = trailing.to(self.dev, torch.float32)
         self.trailing[:, :n_tr] = tr
         self.trailing[:, n_tr:] = tr[:, -1:]
-        off = torch.tensor([Lmax - l for l in lengths], device=self.dev, dtype=torch.int32)
-        for tkn in range(Lmax):
-            self.pos.copy_((tkn - off).clamp_(min=0))
-            self.x.copy_(embeds[:, tkn])
-            self._run("step_logits" if tkn == Lmax - 1 else "step")
+        if self.gemm_prefill:
+            self._prefill_gemm(embeds, lengths)
+        else:
+            off = torch.tensor([Lmax - l for l in lengths], device=self.dev, dtype=torch.int32)
+            for tkn in range(Lmax):
+                self.pos.copy_((tkn - off).clamp_(min=0))
+                self.x.copy_(embeds[:, tkn])
+                self._run("step_logits" if tkn == Lmax - 1 else "step")
         self.pos.copy_(torch.tensor(lengths, device=self.dev, dtype=torch.int32))
+
+    def _prefill_gemm(self, embeds: torch.Tensor, lengths: Sequence[int]):
+        """All prompt tokens of all sequences as ONE set of GEMM rows per layer (tcgen05 W8 GEMM), no padding rows:
+        row m = (sequence, position).  Two attention passes per layer: write every K/V row, then causal attention."""
+        t = self.cfg.talker
+        B, Lmax, H = embeds.shape
+        dev = self.dev
+        rows = torch.cat([embeds[b, Lmax - l:] for b, l in enumerate(lengths)], 0).contiguous()
+        M = rows.shape[0]
+        pos = torch.cat([torch.arange(l, dtype=torch.int32) for l in lengths]).to(dev)
+        seq = torch.cat([torch.full((l,), b, dtype=torch.int32) for b, l in enumerate(lengths)]).to(dev)
+        qkvd, rep = t.q_dim + 2 * t.kv_dim, t.num_heads // t.num_kv_heads
+        f32 = dict(device=dev, dtype=torch.float32)
+        qkv = torch.empty(M, qkvd, **f32)
+        attn = torch.empty(M, t.q_dim, **f32)
+        gu = torch.empty(M, 2 * t.intermediate_size, **f32)
+        xb = torch.empty(M * max(t.hidden_size, t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)
+        work = torch.empty(M * t.num_kv_heads * rep * (t.head_dim + 2), **f32)
+        counters = torch.zeros(M * t.num_kv_heads, device=dev, dtype=torch.int32)
+        a = L.PrefillArgs()
+        a.f, a.M = C.pointer(self.fa), M
+        a.x, a.pos, a.seq_of_row = rows.data_ptr(), pos.data_ptr(), seq.data_ptr()
+        a.qkv, a.attn, a.gu, a.xb = qkv.data_ptr(), attn.data_ptr(), gu.data_ptr(), xb.data_ptr()
+        a.attn_work, a.attn_counters = work.data_ptr(), counters.data_ptr()
+        L.check(self.lib.q3t_talker_prefill(C.byref(a), L.stream_ptr()), "talker_prefill")
+        last = torch.tensor([sum(lengths[:b + 1]) - 1 for b in range(B)], device=dev)
+        self.x.copy_(rows[last])
+        L.check(self.lib.q3t_talker_tail(C.byref(self.fa), L.stream_ptr()), "talker_tail")
+        torch.cuda.synchronize()          # the temporaries above must outlive the enqueued kernels
 
     def generate(self, n_frames: int, check_every: int = 16) -> torch.Tensor:
         """Runs up to n_frames frames (stops early once every sequence sampled EOS). Returns codes [B, T, G]."""

@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", vp), ("q_norm_w", vp), ("k_norm_w", vp), ("eps", f32), ("inv_freq", vp), ("kv_pool", vp),
                 ("block_tbl", vp), ("max_pages", i32), ("pos", vp), ("out", vp), ("work", vp), ("counters", vp),
-                ("B", i32), ("H", i32), ("Hkv", i32), ("D", i32), ("nsplit", i32)]
+                ("B", i32), ("H", i32), ("Hkv", i32), ("D", i32), ("nsplit", i32), ("mode", i32), ("seq_of_row", vp)]
 
 
 class Sampling(C.Structure):
@@ -72,8 +72,13 @@ class FrameArgs(C.Structure):
                 ("keep_cp_logits", i32), ("xc", vp), ("qkv", vp), ("attn", vp), ("gu", vp), ("attn_work", vp),
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
-                ("n_trailing", i32), ("forced_codes", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
+                ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
                 ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp)]
+
+
+class PrefillArgs(C.Structure):
+    _fields_ = [("f", C.POINTER(FrameArgs)), ("M", i32), ("x", vp), ("pos", vp), ("seq_of_row", vp), ("qkv", vp), ("attn", vp),
+                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp)]
 
 
 class StackPassArgs(C.Structure):
@@ -89,7 +94,7 @@ class TapGemmArgs(C.Structure):
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode",
-           "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
+           "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
            "q3t_window_attn", "q3t_snake", "q3t_clamp_pcm16"]
 
 _lib = None
@@ -120,6 +125,8 @@ def load() -> C.CDLL:
     lib.q3t_ll_work_bytes.restype = i64
     lib.q3t_talker_step.argtypes = [C.POINTER(FrameArgs), i32, vp]
     lib.q3t_frame.argtypes = [C.POINTER(FrameArgs), vp]
+    lib.q3t_talker_prefill.argtypes = [C.POINTER(PrefillArgs), vp]
+    lib.q3t_talker_tail.argtypes = [C.POINTER(FrameArgs), vp]
     lib.q3t_rvq_gather_sum.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.q3t_tapgemm.argtypes = [C.POINTER(TapGemmArgs), vp]
     lib.q3t_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]

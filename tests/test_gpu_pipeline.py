@@ -164,6 +164,39 @@ def test_batch2_rows_are_independent(cuda):
         _assert_greedy_codes_match(codes[b, :6], co, rec, min_exact_frames=1)
 
 
+def test_batched_tcgen05_path_matches_oracle(cuda):
+    """More than two rows per contraction run on the tcgen05 W8 GEMM (bf16 operands): ragged GEMM prefill (two attention
+    passes per layer) + batched decode.  Logits within the bf16 tolerance of BASELINE.json; greedy codes equal to the
+    oracle's up to a near-tie."""
+    from qwen3_tts_b200.engine import TalkerEngine
+    cfg = Cfg.small("voice_design")
+    ws = make_weights(cfg, seed=5, head_std=0.2)
+    oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
+    lens = (6, 11, 9, 14, 7)
+    prompts = [oracle.build_prefill(_text_ids(cfg, n, 30 + i), instruct_ids=[1 + i, 2, 3]) for i, n in enumerate(lens)]
+    B = len(prompts)
+    Ls = [p.shape[0] for p, _ in prompts]
+    Lm = max(Ls)
+    emb = torch.zeros(B, Lm, cfg.talker.hidden_size)
+    for b, (p, _) in enumerate(prompts):
+        emb[b, Lm - Ls[b]:] = p
+    e = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=32, max_ctx=128)
+    assert e.gemm_prefill
+    e.set_sampling(do_sample=False)
+    e.prefill(emb, Ls, torch.stack([t for _, t in prompts]))
+    logits0 = e.logits.clone().cpu()
+    codes = e.generate(6).cpu().long()
+    for b, (pp, tt) in enumerate(prompts):
+        co, rec = oracle.generate(pp, tt, 6, record=True)
+        assert _rel(logits0[b], rec["talker_logits"][0]) < LOGIT_RTOL, f"prefill logits of sequence {b}"
+        diff = codes[b] != co
+        if diff.any():
+            f = int(diff.any(1).nonzero()[0]); g = int(diff[f].nonzero()[0])
+            lg = rec["talker_logits"][f] if g == 0 else rec["cp_logits"][f][g - 1]
+            gap = float(lg[int(co[f, g])] - lg[int(codes[b, f, g])])
+            assert 0 <= gap <= LOGIT_RTOL * float(lg.abs().max()), f"sequence {b} frame {f} group {g}: gap {gap:.3e}"
+
+
 def test_rvq_gather_is_bit_exact(small_setup):
     cfg, ws, model, oracle = small_setup
     g = torch.Generator().manual_seed(7)
