@@ -91,6 +91,8 @@ typedef struct {
     const float* resid;  long long resid_stride;
     float* y;  long long y_stride;
     void* xb;
+    /* optional split-K workspace (decode-sized M): partial sums [splits][M][N] fp32 + zero-initialised counters [1024] */
+    float* splitk_ws;  long long splitk_ws_floats;  int* splitk_counters;
 } q3t_gemm_args;
 
 int q3t_w8_gemm(const q3t_gemm_args* a, void* stream);
@@ -240,6 +242,7 @@ typedef struct {
     int n_trailing;
     const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
     void* gemm_xb;         /* bf16 scratch [B, max K] for the tcgen05 GEMM (used when B > 2), or NULL */
+    float* gemm_ws; long long gemm_ws_floats; int* gemm_counters;   /* split-K workspace of the GEMM (optional) */
     /* persistent-kernel path (used when use_mega != 0 and B == 1): the whole frame is ONE launch (csrc/frame_ll.cu) */
     int use_mega;
     const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */

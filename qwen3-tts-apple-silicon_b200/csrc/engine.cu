@@ -68,6 +68,7 @@ int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float
 
 // rows through one W8 matrix: B <= 2 -> exact-integer GEMV (two rows per launch); more rows -> tcgen05 GEMM (bf16 operands)
 static void* g_xb = nullptr;    // bf16 scratch of the call in flight (set by the entry points below)
+static float* g_ws = nullptr; static long long g_ws_floats = 0; static int* g_counters = nullptr;
 static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
                      const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
                      float* y, long long ys, cudaStream_t s) {
@@ -77,6 +78,7 @@ static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long 
         a.w = w; a.M = B; a.prologue = prologue; a.x = x; a.x_stride = xs; a.norm_w = norm_w; a.eps = eps;
         a.gather_idx = gidx; a.gather_idx_stride = gidx_stride; a.gather_row_stride = grow; a.act = act;
         a.resid = resid; a.resid_stride = rs; a.y = y; a.y_stride = ys; a.xb = g_xb;
+        a.splitk_ws = g_ws; a.splitk_ws_floats = g_ws_floats; a.splitk_counters = g_counters;
         return launch_w8_gemm(&a, s);
     }
     for (int b0 = 0; b0 < B; b0 += 2) {
@@ -196,7 +198,7 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
     const q3t_stack& st = f->talker;
     const int M = a->M, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim, qkvd = qd + 2 * kvd;
     Q3T_REQUIRE(M >= 1 && a->x && a->pos && a->seq_of_row && a->qkv && a->attn && a->gu && a->xb, "talker_prefill: arguments");
-    g_xb = a->xb;
+    g_xb = a->xb; g_ws = nullptr; g_ws_floats = 0; g_counters = nullptr;
     for (int l = 0; l < st.n_layers; ++l) {
         const q3t_layer& L = st.layers_host[l];
         Q3T_TRY(gemv_rows(L.qkv, M, Q3T_PRO_RMSNORM, a->x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->qkv, qkvd, s));
@@ -221,7 +223,7 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
 
 static int talker_tail(const q3t_frame_args* f, cudaStream_t s) {
     const q3t_stack& t = f->talker;
-    g_xb = f->gemm_xb;
+    g_xb = f->gemm_xb; g_ws = f->gemm_ws; g_ws_floats = f->gemm_ws_floats; g_counters = f->gemm_counters;
     Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
     return gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->logits,
                      f->talker_vocab, s);
@@ -233,11 +235,11 @@ extern "C" int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int 
     return q3t::launch_rmsnorm(x, w, y, M, H, eps, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream) {
-    q3t::g_xb = f->gemm_xb;
+    q3t::g_xb = f->gemm_xb; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
     return q3t::talker_step(f, want_logits, 0, (cudaStream_t)stream);
 }
 extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) {
-    q3t::g_xb = f->gemm_xb;
+    q3t::g_xb = f->gemm_xb; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
     return q3t::frame(f, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_prefill(const q3t_prefill_args* a, void* stream) { return q3t::talker_prefill(a, (cudaStream_t)stream); }

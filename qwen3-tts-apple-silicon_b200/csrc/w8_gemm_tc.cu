@@ -9,7 +9,7 @@
 //                 ring of raw tiles, one stage = the eight tiles of one 256-wide K chunk
 //   warp 1      : allocates TMEM; one elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M=128, N=tokens,
 //                 K=16 per instruction, four per 64-wide K block) and commits to mbarriers
-//   warps 2..9  : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout
+//   warps 2..17 : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout
 //                 (warp w owns row tile w; codes are fragment-ordered in HBM, every lane converts 32 codes per block:
 //                 byte -> fp32 by the 2^23 trick, one FFMA with the group scale/bias, cvt.rn.bf16x2, 8-byte stores),
 //                 then fence.proxy.async + mbarrier arrive; the matching activation block (bf16, prepared by
@@ -24,8 +24,8 @@
 
 namespace q3t {
 
-constexpr int TC_THREADS = 320;                 // 10 warps
-constexpr int TC_DQ_WARPS = 8;
+constexpr int TC_DQ_WARPS = 16;                 // two warps per 16-row weight tile (one 32-wide K half each)
+constexpr int TC_THREADS = 64 + TC_DQ_WARPS * 32;   // 18 warps
 constexpr int TC_BM = 128;                      // features per CTA (MMA M)
 constexpr int TC_BN_MAX = 256;                  // tokens per CTA (MMA N)
 constexpr int TC_BK = 64;                       // K per operand stage (= one quantisation group = one 128-byte swizzle row)
@@ -48,6 +48,8 @@ struct GemmParams {
     const float* resid; long long resid_stride;
     float* y; long long y_stride;
     int bn;                                     // tokens per CTA (multiple of 16, <= 256)
+    int splits;                                 // split-K factor (gridDim.z); > 1 needs ws + counters
+    float* ws; int* counters;                   // [splits][M][N] partial sums, one arrival counter per (n block, m block)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------------------------------
@@ -99,6 +101,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return r;
 }
 
+#ifdef TC_TIMING
+#define TC_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); reinterpret_cast<unsigned long long*>(p.ws)[i] = t_; } } while (0)
+#else
+#define TC_STAMP(i) do { } while (0)
+#endif
+
 // ---- the kernel ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmParams p, const __grid_constant__ CUtensorMap tmap_x) {
     extern __shared__ unsigned char tc_smem_raw[];
@@ -112,9 +120,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) TC_STAMP(0);
     const int nb = blockIdx.x, m0 = blockIdx.y * p.bn;
-    const int nkc = p.K >> 8, nkb = p.K >> 6;
     const int bn = p.bn;
+    // split-K: this CTA contracts the 256-wide chunks [kc_lo, kc_hi)
+    const int nkc_all = p.K >> 8;
+    const int kc_lo = (nkc_all * (int)blockIdx.z) / p.splits, kc_hi = (nkc_all * ((int)blockIdx.z + 1)) / p.splits;
+    const int nkc = kc_hi - kc_lo, nkb = nkc * 4;
 
     if (tid == 0) {
         for (int i = 0; i < TC_STAGES; ++i) { tc_mbar_init(tc_smem_u32(&full_ab[i]), TC_DQ_WARPS + 1); tc_mbar_init(tc_smem_u32(&empty_ab[i]), 1); }
@@ -131,6 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     pdl_launch_dependents();
+    if (tid == 0) TC_STAMP(1);
 
     if (warp == 0) {
         // ===================== producers: lane 0 raw W8 tiles (weights do not depend on the previous kernel),
@@ -144,10 +157,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 unsigned char* dst = smem + TC_OFF_RAW + rs * TC_RAW_BYTES;
                 for (int rt = 0; rt < 8; ++rt)
                     tc_tma_load_1d(tc_smem_u32(dst + rt * Q3T_TILE_BYTES),
-                                   p.w + ((size_t)(nb * 8 + rt) * nkc + kc) * Q3T_TILE_BYTES, Q3T_TILE_BYTES, fb);
+                                   p.w + ((size_t)(nb * 8 + rt) * nkc_all + kc_lo + kc) * Q3T_TILE_BYTES, Q3T_TILE_BYTES, fb);
             }
         } else if (lane == 1) {
             pdl_wait();                           // the bf16 activations come from the previous kernel
+            TC_STAMP(2);
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
                 tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 tc_mbar_expect_tx(fb, (uint32_t)bn * 128u);
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                              ::"r"(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
-                               "r"(kb * TC_BK), "r"(m0), "r"(fb) : "memory");
+                               "r"((kc_lo * 4 + kb) * TC_BK), "r"(m0), "r"(fb) : "memory");
             }
         }
     } else if (warp == 1) {
@@ -165,6 +179,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
             for (int kb = 0; kb < nkb; ++kb) {
                 const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
                 tc_mbar_wait(tc_smem_u32(&full_ab[st]), par);
+                if (kb == 0) TC_STAMP(3);
                 tc_fence_after();
                 const uint64_t a_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_A + st * TC_A_BYTES));
                 const uint64_t b_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES));
@@ -174,10 +189,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 tc_commit(tc_smem_u32(&empty_ab[st]));     // frees the stage once these MMAs have read it
             }
             tc_commit(tc_smem_u32(tmem_full));              // accumulator complete
+            TC_STAMP(4);
         }
     } else {
         // ===================== dequant + activation copy (8 warps), then epilogue (first 4 of them) =======================
-        const int dw = warp - 2;                  // row tile of this warp inside the 128-row block
+        const int dw = (warp - 2) >> 1;           // row tile of this warp pair inside the 128-row block
+        const int jh = (warp - 2) & 1;            // which 32-wide half of the 64-wide K block this warp converts
         const int g = lane >> 2, t = lane & 3;
         pdl_wait();                               // activations come from the previous kernel
         for (int kb = 0; kb < nkb; ++kb) {
@@ -194,8 +211,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 const float s_lo = __uint_as_float((uint32_t)mlo[j4] << 16), b_lo = __uint_as_float((uint32_t)mlo[4 + j4] << 16);
                 const float s_hi = __uint_as_float((uint32_t)mhi[j4] << 16), b_hi = __uint_as_float((uint32_t)mhi[4 + j4] << 16);
                 unsigned char* adst = smem + TC_OFF_A + st * TC_A_BYTES + dw * 2048;      // 16 rows = two 8-row swizzle atoms
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                {
+                    const int j = jh;
                     const uint4 q = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + j) * 512 + lane * 16);
                     const uint32_t qq[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
@@ -223,49 +240,117 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                 if (j4 == 3) tc_mbar_arrive(tc_smem_u32(&empty_raw[rs]));
             }
         }
-        // ---- epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 = features of this CTA
-        if (dw < 4) {
-            tc_mbar_wait(tc_smem_u32(tmem_full), 0);
-            tc_fence_after();
-            const int lg = warp & 3;                               // TMEM lane group this warp may read
-            const int f_local = lg * 32 + lane;                    // feature inside the 128-row block
-            const int n = nb * TC_BM + f_local;
-            const float bias = p.lin_bias ? p.lin_bias[n] : 0.f;
-            for (int c0 = 0; c0 < bn; c0 += 32) {
-                uint32_t v[32];
-                const uint32_t taddr = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0;
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-                      "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-                      "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-                      "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // ---- epilogue.  Warps 2..5 own TMEM lanes 32*(warp%4)..+31 (= features of this CTA): they move the accumulator
+        // to shared memory (the raw-tile ring is free by now) as [token][feature]; then ALL 16 warps of this group write
+        // token rows with float4 stores.  One store per (feature, token) from four warps - the obvious epilogue - spends
+        // ~25 dependent 64-bit address instructions per element on a single warp per scheduler (0.1 us per token, measured).
+        constexpr int STG_LD = TC_BM + 4;                          // padded row: 528 bytes, 16-byte aligned
+        constexpr int STG_TOK = 128;                               // tokens per staging pass (128 x 132 x 4 = 67 584 B)
+        static_assert(STG_TOK * STG_LD * 4 <= TC_RAW_STAGES * TC_RAW_BYTES, "staging tile must fit the raw ring");
+        float* stg = reinterpret_cast<float*>(smem + TC_OFF_RAW);
+        const int dt = tid - 64;                                   // 0..511
+        const int n0 = nb * TC_BM;
+        bool finish = true;
+        for (int t0 = 0; t0 < bn; t0 += STG_TOK) {
+            const int nt = bn - t0 < STG_TOK ? bn - t0 : STG_TOK;
+            if (warp < 6) {
+                if (t0 == 0) { tc_mbar_wait(tc_smem_u32(tmem_full), 0); if (tid == 64) TC_STAMP(5); tc_fence_after(); }
+                const int lg = warp & 3, f_local = lg * 32 + lane;
+                const uint32_t tbase = tmem_d + ((uint32_t)(lg * 32) << 16) + (uint32_t)t0;
+#pragma unroll 1
+                for (int c0 = 0; c0 < nt; c0 += 8) {
+                    uint32_t v[8];
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                                 : "r"(tbase + (uint32_t)c0));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float* d = stg + c0 * STG_LD + f_local;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const int m = m0 + c0 + c;                     // token (uniform across the warp)
-                    float x = __uint_as_float(v[c]) + bias;
-                    if (p.swiglu) {
-                        // fused gate/up rows: gate rows at 16j..16j+7, matching up rows 8 lanes higher
-                        const float up = __shfl_down_sync(0xffffffffu, x, 8);
-                        x = silu_f(x) * up;
-                        if (c0 + c < bn && m < p.M && (lane & 8) == 0)
-                            p.y[(size_t)m * p.y_stride + (n >> 4) * 8 + (n & 7)] = x;
-                    } else {
-                        if (p.act == Q3T_ACT_SILU) x = silu_f(x);
-                        if (c0 + c < bn && m < p.M) {
-                            if (p.resid) x += p.resid[(size_t)m * p.resid_stride + n];
-                            p.y[(size_t)m * p.y_stride + n] = x;
+                    for (int c = 0; c < 8; ++c) d[c * STG_LD] = __uint_as_float(v[c]);
+                }
+            }
+            asm volatile("bar.sync 3, 512;" ::: "memory");
+            if (p.splits > 1) {
+                // split-K: publish the partial tile; the LAST split to arrive (per output tile) sums all partials in split
+                // order (deterministic, no float atomics) and applies the epilogue
+                float* wsz = p.ws + (size_t)blockIdx.z * p.M * p.N;
+                for (int i = dt; i < nt * 32; i += 512) {
+                    const int tok = i >> 5, q4 = i & 31, m = m0 + t0 + tok;
+                    if (m < p.M) __stcg(reinterpret_cast<float4*>(wsz + (size_t)m * p.N + n0) + q4, *reinterpret_cast<const float4*>(stg + tok * STG_LD + 4 * q4));
+                }
+                __threadfence();
+                asm volatile("bar.sync 3, 512;" ::: "memory");
+                if (dt == 0) {
+                    int* cnt = p.counters + blockIdx.y * gridDim.x + blockIdx.x;
+                    const int prev = atomicAdd(cnt, 1);
+                    *tmem_slot = (prev == p.splits - 1) ? 1u : 0u;             // (the TMEM base is already in registers)
+                    if (prev == p.splits - 1) *cnt = 0;                          // re-arm for the next launch
+                }
+                asm volatile("bar.sync 3, 512;" ::: "memory");
+                finish = (*tmem_slot != 0u);
+                if (finish) __threadfence();
+            }
+            if (finish) {
+                const size_t zstride = (size_t)p.M * p.N;
+                if (p.swiglu) {
+                    // fused gate/up rows: gate rows at 16j..16j+7, matching up rows at 16j+8..16j+15 -> N/2 activations per token
+                    for (int i = dt; i < nt * 16; i += 512) {
+                        const int tok = i >> 4, j = (i & 15) >> 1, h = i & 1, m = m0 + t0 + tok;
+                        if (m >= p.M) continue;
+                        const int fg = 16 * j + 4 * h;                   // gate features fg..fg+3, up features fg+8..fg+11
+                        float4 g, u;
+                        if (p.splits == 1) {
+                            g = *reinterpret_cast<const float4*>(stg + tok * STG_LD + fg);
+                            u = *reinterpret_cast<const float4*>(stg + tok * STG_LD + fg + 8);
+                        } else {
+                            g = make_float4(0.f, 0.f, 0.f, 0.f); u = g;
+                            const float* src = p.ws + (size_t)m * p.N + n0 + fg;
+                            for (int z = 0; z < p.splits; ++z, src += zstride) {
+                                const float4 a = __ldcg(reinterpret_cast<const float4*>(src)), b = __ldcg(reinterpret_cast<const float4*>(src + 8));
+                                g.x += a.x; g.y += a.y; g.z += a.z; g.w += a.w; u.x += b.x; u.y += b.y; u.z += b.z; u.w += b.w;
+                            }
                         }
+                        if (p.lin_bias) {
+                            const float4 bg = *reinterpret_cast<const float4*>(p.lin_bias + n0 + fg), bu = *reinterpret_cast<const float4*>(p.lin_bias + n0 + fg + 8);
+                            g.x += bg.x; g.y += bg.y; g.z += bg.z; g.w += bg.w; u.x += bu.x; u.y += bu.y; u.z += bu.z; u.w += bu.w;
+                        }
+                        const float4 o = make_float4(silu_f(g.x) * u.x, silu_f(g.y) * u.y, silu_f(g.z) * u.z, silu_f(g.w) * u.w);
+                        *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + (n0 >> 1) + 8 * j + 4 * h) = o;
+                    }
+                } else {
+                    for (int i = dt; i < nt * 32; i += 512) {
+                        const int tok = i >> 5, q4 = i & 31, m = m0 + t0 + tok;
+                        if (m >= p.M) continue;
+                        float4 x;
+                        if (p.splits == 1) {
+                            x = *reinterpret_cast<const float4*>(stg + tok * STG_LD + 4 * q4);
+                        } else {
+                            x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            const float* src = p.ws + (size_t)m * p.N + n0 + 4 * q4;
+                            for (int z = 0; z < p.splits; ++z, src += zstride) {
+                                const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+                                x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+                            }
+                        }
+                        if (p.lin_bias) {
+                            const float4 b = *reinterpret_cast<const float4*>(p.lin_bias + n0 + 4 * q4);
+                            x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+                        }
+                        if (p.act == Q3T_ACT_SILU) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
+                        if (p.resid) {
+                            const float4 r = *reinterpret_cast<const float4*>(p.resid + (size_t)m * p.resid_stride + n0 + 4 * q4);
+                            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+                        }
+                        *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + n0 + 4 * q4) = x;
                     }
                 }
             }
-            tc_fence_before();
+            asm volatile("bar.sync 3, 512;" ::: "memory");
         }
+        if (warp < 6) { tc_fence_before(); if (tid == 64) TC_STAMP(6); }
     }
     __syncthreads();
+    if (tid == 0) TC_STAMP(7);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TC_BN_MAX) : "memory");
@@ -331,6 +416,17 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     if (bn > TC_BN_MAX) bn = TC_BN_MAX;
     if (bn < 16) bn = 16;
     p.bn = bn;
+    // split-K for decode-sized problems: fill the machine when N/128 CTAs would leave most SMs idle
+    p.splits = 1; p.ws = (float*)a->splitk_ws; p.counters = a->splitk_counters;
+    {
+        const int nkc = K / 256, nblk = p.N / TC_BM;
+        if (a->splitk_ws && a->splitk_counters && a->M <= bn && nblk <= 1024) {
+            int best = 1;
+            for (int d = 2; d <= 8 && d <= nkc; ++d)
+                if (nkc % d == 0 && nblk * d <= 160 && (long long)d * a->M * p.N <= a->splitk_ws_floats) best = d;
+            p.splits = best;
+        }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(w8_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
@@ -359,7 +455,7 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->xb, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "w8_gemm: cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
-    launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p, tmap);
+    launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn, p.splits), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p, tmap);
     Q3T_CHECK_LAUNCH("w8_gemm_tc");
     return 0;
 }

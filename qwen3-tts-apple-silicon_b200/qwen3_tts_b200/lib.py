@@ -31,7 +31,8 @@ class GemvArgs(C.Structure):
 class GemmArgs(C.Structure):
     _fields_ = [("w", W8), ("M", i32), ("prologue", i32), ("x", vp), ("x_stride", i64), ("norm_w", vp), ("eps", f32),
                 ("gather_idx", vp), ("gather_idx_stride", i32), ("gather_row_stride", i64), ("act", i32),
-                ("swiglu_out", i32), ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64), ("xb", vp)]
+                ("swiglu_out", i32), ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64), ("xb", vp),
+                ("splitk_ws", vp), ("splitk_ws_floats", i64), ("splitk_counters", vp)]
 
 
 class AttnArgs(C.Structure):
@@ -72,7 +73,7 @@ class FrameArgs(C.Structure):
                 ("keep_cp_logits", i32), ("xc", vp), ("qkv", vp), ("attn", vp), ("gu", vp), ("attn_work", vp),
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
-                ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
+                ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("gemm_ws", vp), ("gemm_ws_floats", i64), ("gemm_counters", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
                 ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp)]
 
 

@@ -69,6 +69,20 @@ def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
     assert torch.isfinite(yd).all()
     assert (yd - ref_bf).abs().max() / ref_bf.abs().max() < 2e-5, "layout / accumulation error"
     assert (yd - ref).abs().max() / ref.abs().max() < 1e-2, "bf16 tolerance"
+    # split-K (decode-sized problems): partial tiles summed in split order by the last CTA to arrive; twice, to check
+    # that the arrival counters re-arm themselves and that the result is bit-reproducible
+    ws = torch.empty(8 * m * n, device=cuda)
+    cnt = torch.zeros(1024, device=cuda, dtype=torch.int32)
+    a.splitk_ws, a.splitk_ws_floats, a.splitk_counters = ws.data_ptr(), ws.numel(), cnt.data_ptr()
+    outs = []
+    for _ in range(2):
+        y.fill_(float("nan"))
+        L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm split-K")
+        torch.cuda.synchronize()
+        outs.append(y.clone())
+    assert torch.equal(outs[0], outs[1])
+    assert int(cnt.abs().sum()) == 0
+    assert (outs[0].cpu().double() - ref_bf).abs().max() / ref_bf.abs().max() < 2e-5, "split-K"
 
 
 def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
