@@ -8,6 +8,7 @@
 // (x upsampling phases for transposed convs, whose output [T, s*Cout] IS the time-major [T*s, Cout] tensor).
 // Round-1 implementation runs the contraction on the FP32 pipe with fused bias / LayerScale / residual /
 // SnakeBeta / GELU / SwiGLU epilogues; the tcgen05 implicit-GEMM version replaces `tapgemm_kernel` only.
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
@@ -242,10 +243,20 @@ extern "C" int q3t_rvq_gather_sum(const int* codes, const float* const* tables_h
     return 0;
 }
 
+namespace q3t { int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream); }
+
 extern "C" int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream) {
     Q3T_REQUIRE(a->taps >= 1 && a->taps <= 8, "tapgemm: taps in [1,8]");
     Q3T_REQUIRE(a->Cin % 4 == 0, "tapgemm: Cin % 4");
     Q3T_REQUIRE(a->act != Q3T_ACT_SWIGLU_PAIR || (a->up * a->Cout) % 2 == 0, "tapgemm: SWIGLU_PAIR needs even N");
+    {   // tensor-core implicit GEMM (tcgen05, TF32) for every eligible layer; Q3T_CODEC_TC=0 forces the FP32-pipe kernel
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("Q3T_CODEC_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
+        if (use_tc && (long long)a->B * a->T_out_rows > 0) {
+            const int rc = q3t::launch_tapgemm_tc(a, (cudaStream_t)stream);
+            if (rc >= 0) return rc;
+        }
+    }
     TapGemmParams p;
     p.A = a->A; p.B = a->B; p.T_in = a->T_in; p.Cin = a->Cin; p.W = a->W; p.bias = a->bias; p.taps = a->taps;
     for (int i = 0; i < 8; ++i) p.shift[i] = a->shift[i];

@@ -1,0 +1,253 @@
+// Causal tap-GEMM of the speech-tokenizer decoder on the 5th-generation tensor cores (tcgen05, kind::tf32, TMEM):
+// conv1d / conv_transpose1d / linear of the codec as an IMPLICIT GEMM.
+//     out[b, t, n] = epi( sum_{tap} sum_{ci} A[b, t + shift_tap, ci] * W[tap][n][ci] ),   rows outside [0, T_in) read as zero
+// Replaces mx.conv1d / mx.conv_transpose1d / matmul of the reference stack for every layer with Cin % 32 == 0 (everything
+// but the 96->1 output conv), with the same fused epilogues as the FP32-pipe kernel in codec.cu.
+//
+//   * no im2col and no padded copies: the activation operand of tap j is the SAME [B, T, Cin] tensor fetched through a 3-D
+//     TMA tensor map at time coordinate t0 + shift_j; rows before 0 / past T_in are the tensor map's zero fill, which IS the
+//     causal left padding (and the right trim of the transposed convs);
+//   * operands stay fp32 in HBM/L2 (the codec is fp32 end to end); the tensor core reads them as TF32 (kind::tf32, 10-bit
+//     mantissa, fp32 accumulate in TMEM).  Weights are rounded to TF32 once at load and the epilogue rounds what it stores
+//     (cvt.rna.tf32), so the hardware's truncation never sees low mantissa bits -> unbiased 2^-11 rounding per operand;
+//   * MMA tile 128 rows (time) x 128 columns (channels) x 32 (Cin slice = one 128-byte swizzle row), 3-stage TMA ring,
+//     96 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's MMAs;
+//   * epilogue: 4 warps move the accumulator TMEM -> shared memory, then all 16 epilogue warps apply bias / LayerScale /
+//     residual / SnakeBeta / GELU / SiLU / SwiGLU-pair and store coalesced rows.
+#include <cuda.h>
+#include "common.cuh"
+#include "../../include/q3tts_b200.h"
+
+namespace q3t {
+
+constexpr int TT_EPI_WARPS = 16;
+constexpr int TT_THREADS = 64 + TT_EPI_WARPS * 32;      // producer warp, MMA warp, 16 epilogue warps
+constexpr int TT_BM = 128, TT_BN = 128, TT_BK = 32;
+constexpr int TT_STAGES = 3;
+constexpr int TT_A_BYTES = TT_BM * 128, TT_B_BYTES = TT_BN * 128;     // 16 KB each
+constexpr int TT_STAGE_BYTES = TT_A_BYTES + TT_B_BYTES;
+constexpr int TT_OFF_BAR = TT_STAGES * TT_STAGE_BYTES;                 // 98 304
+constexpr int TT_SMEM_BYTES = TT_OFF_BAR + 128 + 1024;                 // + barriers + alignment slack
+constexpr int TT_STG_LD = TT_BN + 1;                                   // staging tile [128 rows][129]: conflict-free both ways
+static_assert(TT_BM * TT_STG_LD * 4 <= TT_OFF_BAR, "staging tile must fit the operand ring");
+
+struct TapTcParams {
+    int B, T_in, Cin, taps, shift[8], N, Cout, rows, tiles_per_item;
+    const float* bias; const float* scale; const float* resid;
+    float* out_raw; float* out_act; int act; const float* act_a; const float* act_b;
+};
+
+__device__ __forceinline__ uint32_t tt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tt_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tt_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tt_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "TT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra TT_DONE;\n"
+        "bra TT_WAIT;\n"
+        "TT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint64_t tt_smem_desc(uint32_t saddr) {      // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ float tt_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float tt_round_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcParams p, const __grid_constant__ CUtensorMap tm_a,
+                                                                    const __grid_constant__ CUtensorMap tm_w) {
+    extern __shared__ unsigned char tt_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tt_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TT_OFF_BAR);
+    uint64_t* empty = full + TT_STAGES;
+    uint64_t* tmem_full = empty + TT_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.x / p.tiles_per_item, t0 = (blockIdx.x % p.tiles_per_item) * TT_BM, n0 = blockIdx.y * TT_BN;
+    const int nkb = p.Cin / TT_BK, nst = p.taps * nkb;
+
+    if (tid == 0) {
+        for (int i = 0; i < TT_STAGES; ++i) { tt_mbar_init(tt_smem_u32(&full[i]), 1); tt_mbar_init(tt_smem_u32(&empty[i]), 1); }
+        tt_mbar_init(tt_smem_u32(tmem_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tt_smem_u32(tmem_slot)), "n"(TT_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== producer: A through the 3-D map at (ci, t0 + shift, b), W through the 2-D map ==========
+            int s = 0;
+            for (int tap = 0; tap < p.taps; ++tap) {
+                const int ta = t0 + p.shift[tap];
+                for (int kb = 0; kb < nkb; ++kb, ++s) {
+                    const int st = s % TT_STAGES, par = (s / TT_STAGES) & 1;
+                    tt_mbar_wait(tt_smem_u32(&empty[st]), par ^ 1);
+                    const uint32_t fb = tt_smem_u32(&full[st]);
+                    tt_mbar_expect_tx(fb, TT_STAGE_BYTES);
+                    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                                 ::"r"(tt_smem_u32(smem + st * TT_STAGE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_a)),
+                                   "r"(kb * TT_BK), "r"(ta), "r"(b), "r"(fb) : "memory");
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(tt_smem_u32(smem + st * TT_STAGE_BYTES + TT_A_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_w)),
+                                   "r"(kb * TT_BK), "r"(tap * p.N + n0), "r"(fb) : "memory");
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===================== MMA issuer: kind::tf32, M = 128, N = 128, K = 8 per instruction ========================
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TT_BN >> 3) << 17) | ((uint32_t)(TT_BM >> 4) << 24);
+            for (int s = 0; s < nst; ++s) {
+                const int st = s % TT_STAGES, par = (s / TT_STAGES) & 1;
+                tt_mbar_wait(tt_smem_u32(&full[st]), par);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t a_desc = tt_smem_desc(tt_smem_u32(smem + st * TT_STAGE_BYTES));
+                const uint64_t b_desc = tt_smem_desc(tt_smem_u32(smem + st * TT_STAGE_BYTES + TT_A_BYTES));
+#pragma unroll
+                for (int k = 0; k < TT_BK / 8; ++k) {     // 8 tf32 = 32 bytes = 2 descriptor units along K
+                    const uint32_t acc = (s | k) != 0;
+                    asm volatile(
+                        "{\n.reg .pred p;\n"
+                        "setp.ne.b32 p, %4, 0;\n"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                        ::"r"(tmem_d), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"(acc) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tt_smem_u32(&empty[st])) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tt_smem_u32(tmem_full)) : "memory");
+        }
+    } else {
+        // ===================== epilogue =====================================================================================
+        float* stg = reinterpret_cast<float*>(smem);               // the operand ring is free once the accumulator is complete
+        const int dt = tid - 64;
+        tt_mbar_wait(tt_smem_u32(tmem_full), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (warp < 6) {
+            const int lg = warp & 3, r_local = lg * 32 + lane;     // TMEM lane = output row (time step) of this tile
+            const uint32_t tbase = tmem_d + ((uint32_t)(lg * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < TT_BN; c0 += 8) {
+                uint32_t v[8];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                             : "r"(tbase + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float* d = stg + r_local * TT_STG_LD + c0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) d[c] = __uint_as_float(v[c]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        const int ncols = p.N - n0 < TT_BN ? p.N - n0 : TT_BN;
+        const int nrows = p.rows - t0 < TT_BM ? p.rows - t0 : TT_BM;
+        const long long m_base = (long long)b * p.rows + t0;       // global output row of local row 0
+        if (p.out_act && p.act == Q3T_ACT_SWIGLU_PAIR) {
+            const int hp = ncols >> 1;
+            for (int i = dt; i < nrows * hp; i += TT_EPI_WARPS * 32) {
+                const int r = i / hp, j = i - r * hp;
+                float v[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int n = n0 + 2 * j + q, c = n % p.Cout;
+                    float x = stg[r * TT_STG_LD + 2 * j + q];
+                    if (p.bias) x += p.bias[c];
+                    if (p.scale) x *= p.scale[c];
+                    if (p.resid) x += p.resid[(m_base + r) * p.N + n];
+                    if (p.out_raw) p.out_raw[(m_base + r) * p.N + n] = tt_round_tf32(x);
+                    v[q] = x;
+                }
+                p.out_act[(m_base + r) * (p.N / 2) + ((n0 + 2 * j) >> 1)] = tt_round_tf32(silu_f(v[0]) * v[1]);
+            }
+        } else {
+            for (int i = dt; i < nrows * ncols; i += TT_EPI_WARPS * 32) {
+                const int r = i / ncols, j = i - r * ncols;
+                const int n = n0 + j, c = n % p.Cout;
+                float x = stg[r * TT_STG_LD + j];
+                if (p.bias) x += p.bias[c];
+                if (p.scale) x *= p.scale[c];
+                if (p.resid) x += p.resid[(m_base + r) * p.N + n];
+                if (p.out_raw) p.out_raw[(m_base + r) * p.N + n] = tt_round_tf32(x);
+                if (p.out_act) {
+                    if (p.act == Q3T_ACT_SNAKE) { const float sn = sinf(x * p.act_a[c]); x = x + p.act_b[c] * (sn * sn); }
+                    else if (p.act == Q3T_ACT_GELU) x = tt_gelu_erf(x);
+                    else if (p.act == Q3T_ACT_SILU) x = silu_f(x);
+                    p.out_act[(m_base + r) * p.N + n] = tt_round_tf32(x);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "n"(TT_BN) : "memory");
+    }
+}
+
+typedef CUresult (*TtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// returns 0 on success, > 0 on error, -1 when the shape is not eligible (caller falls back to the FP32-pipe kernel)
+int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream) {
+    const int N = a->up * a->Cout;
+    if (a->Cin % TT_BK != 0 || N % 16 != 0 || N < 32) return -1;
+    const long long Mtot = (long long)a->B * a->T_out_rows;
+    if (Mtot < 64 || a->T_in < 1) return -1;
+    static TtEncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return -1;
+        encode = (TtEncodeFn)fn;
+    }
+    CUtensorMap tm_a, tm_w;
+    {
+        const cuuint64_t gdim[3] = {(cuuint64_t)a->Cin, (cuuint64_t)a->T_in, (cuuint64_t)a->B};
+        const cuuint64_t gstr[2] = {(cuuint64_t)a->Cin * 4, (cuuint64_t)a->T_in * a->Cin * 4};
+        const cuuint32_t box[3] = {TT_BK, TT_BM, 1}, es[3] = {1, 1, 1};
+        if (encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a->A, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
+    }
+    {
+        const cuuint64_t gdim[2] = {(cuuint64_t)a->Cin, (cuuint64_t)a->taps * N};
+        const cuuint64_t gstr[1] = {(cuuint64_t)a->Cin * 4};
+        const cuuint32_t box[2] = {TT_BK, TT_BN}, es[2] = {1, 1};
+        if (encode(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a->W, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
+    }
+    TapTcParams p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.T_in = a->T_in; p.Cin = a->Cin; p.taps = a->taps;
+    for (int i = 0; i < 8; ++i) p.shift[i] = a->shift[i];
+    p.N = N; p.Cout = a->Cout; p.rows = a->T_out_rows; p.tiles_per_item = (a->T_out_rows + TT_BM - 1) / TT_BM;
+    p.bias = a->bias; p.scale = a->scale; p.resid = a->resid; p.out_raw = a->out_raw; p.out_act = a->out_act; p.act = a->act;
+    p.act_a = a->act_a; p.act_b = a->act_b;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(a->B * p.tiles_per_item), (unsigned)((N + TT_BN - 1) / TT_BN));
+    tapgemm_tc_kernel<<<grid, TT_THREADS, TT_SMEM_BYTES, stream>>>(p, tm_a, tm_w);
+    Q3T_CHECK_LAUNCH("tapgemm_tc");
+    return 0;
+}
+
+}  // namespace q3t

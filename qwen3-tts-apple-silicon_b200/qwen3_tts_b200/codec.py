@@ -22,6 +22,10 @@ class _Tap:
 
     def __init__(self, W: torch.Tensor, bias: Optional[torch.Tensor], shifts: List[int], up: int, cout: int,
                  rows_delta: int = 0):
+        # weights are rounded to TF32 (10-bit mantissa, round-to-nearest-even) once: the tcgen05 tap-GEMM reads its
+        # operands as TF32 by truncation, so pre-rounded weights make that truncation exact (csrc/tapgemm_tc.cu)
+        Wi = W.contiguous().view(torch.int32)
+        W = ((Wi + 0x0FFF + ((Wi >> 13) & 1)) & ~0x1FFF).view(torch.float32)
         self.W, self.bias, self.shifts, self.up, self.cout, self.rows_delta = W.contiguous(), bias, shifts, up, cout, rows_delta
         self.taps, self.cin = W.shape[0], W.shape[2]
 
