@@ -163,6 +163,48 @@ def workload_config(args):
             "l2": "inputs larger than L2: 1.5 GB of weights stream per token vs 126 MB L2", "parallelism": f"replica x{args.gpus}"}
 
 
+def bs64_leg(cfg, args, world, dist, timed):
+    """64 lock-step utterances per GPU: 300-token prompts (256 text + 32 instruct + control), B64_FRAMES frames each."""
+    from qwen3_tts_b200.codec import CodecDecoder
+    from qwen3_tts_b200.engine import TalkerEngine
+    from qwen3_tts_b200.weights import make_weights
+    B, Lp, T = 64, 300, args.bs64_frames
+    ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False)
+    eng = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=T + 8, max_ctx=((Lp + T + 24) // 16) * 16, attn_nsplit=4)
+    codec = CodecDecoder(cfg, ws, "cuda")
+    del ws
+    eng.set_sampling(do_sample=False)
+    emb = torch.randn(B, Lp, cfg.talker.hidden_size, device="cuda") * 0.02
+    emb_host = emb.cpu().pin_memory()
+    state = {}
+
+    def step_dev():
+        eng.prefill(emb, None, None)
+        codes = eng.generate(T, check_every=0)
+        return codec.decode(codes.transpose(1, 2).contiguous())
+
+    def step_e2e():
+        eng.prefill(emb_host.cuda(non_blocking=True), None, None)
+        codes = eng.generate(T, check_every=0)
+        return codec.decode(codes.transpose(1, 2).contiguous()).cpu()
+
+    step_dev()
+    ms, wav = timed(step_dev, max(1, min(args.steps, 2)))
+    ms_e2e, wav_h = timed(step_e2e, 1)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    a, b, c, d = ev(), ev(), ev(), ev()
+    a.record(); eng.prefill(emb, None, None); b.record(); codes = eng.generate(T, check_every=0); c.record()
+    codec.decode(codes.transpose(1, 2).contiguous()); d.record(); torch.cuda.synchronize()
+    audio_s = B * T * 0.08
+    return {"value": world * audio_s / (ms / 1e3), "unit": UNIT, "batch_per_gpu": B, "prompt_tokens": Lp, "frames": T,
+            "e2e": {"value": world * audio_s / (ms_e2e / 1e3), "h2d_bytes_per_step": int(emb_host.numel() * 4),
+                    "d2h_bytes_per_step": int(wav_h.numel() * 4)},
+            "ms_prefill": a.elapsed_time(b), "ms_per_frame": b.elapsed_time(c) / T, "ms_codec": c.elapsed_time(d),
+            "launches_per_frame": eng.launches_per_frame,
+            "note": "greedy, random-init; talker/CP contractions on the tcgen05 W8 GEMM (bf16 operands), codec convolutions on the "
+                    "tcgen05 TF32 tap-GEMM; prefill counted inside the timed region"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +215,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=4)
     ap.add_argument("--cpu-frames", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bs64", action="store_true")
+    ap.add_argument("--bs64-frames", type=int, default=96)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
@@ -264,6 +308,11 @@ def main():
     step_b, w_b, kv_b = talker_step_bytes(cfg, L0 + FRAMES // 2)
     peak, peak_src = peaks()
     achieved = step_b / (ms_tok / 1e3) / 1e9
+    traffic = None                       # dram read+write bytes of the same launch from the committed ncu --set full capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_full_frame_ll_talker_step.json")))["traffic_bytes"]
+    except Exception:
+        pass
     launches_step = e.launches_per_frame
     # launches inside one timed step: L0 prefill token steps + FRAMES frames + the codec (counted at graph capture)
     per_tok = e.launches.get("step", 0)
@@ -276,9 +325,15 @@ def main():
             "gpu_launches": int(gpu_launches), "launches_per_frame": launches_step,
             "roofline": {"bound": "hbm", "kernel": "frame_ll_kernel, stack mode (talker decode step = ONE persistent launch: 28 layers + final norm + codec head)",
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_8TBps": achieved / 8000.0, "traffic": None, "bytes_per_step": step_b, "weight_bytes": w_b,
+                         "frac_of_8TBps": achieved / 8000.0, "traffic": traffic,
+                         "traffic_source": "profiles/r01_ncu_full_frame_ll_talker_step.json (ncu --set full, ctx=300)", "bytes_per_step": step_b, "weight_bytes": w_b,
                          "kv_bytes": kv_b, "us_per_talker_step": ms_tok * 1e3, "ctx": L0 + FRAMES // 2},
             "clocks": clk.summary(), "frames_per_s": world * FRAMES / (ms_dev / 1e3), "audio_samples": int(wav.numel())}
+    if not args.no_bs64:
+        # ---- batch-64 serving leg (BASELINE config 4 shapes): tcgen05 GEMM prefill + batched frame graph + batched codec
+        del model, e
+        torch.cuda.empty_cache()
+        line["bs64"] = bs64_leg(cfg, args, world, dist, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, detail = cpu_oracle_rtfx(args.size, args.cpu_frames)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",

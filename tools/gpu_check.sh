@@ -8,7 +8,7 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&
 tail -3 gpurun_out/pytest_$tag.log
 timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_$tag.log 2>&1; echo "bench rc=$?" >> gpurun_out/bench_$tag.log
 tail -2 gpurun_out/bench_$tag.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:q3t --csv --log-file gpurun_out/launches_$tag.csv python tools/ncu_step.py > gpurun_out/ncu_list_$tag.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"frame_ll|w8_gem|attn_decode|sample_kernel|advance|next_input|rmsnorm|tapgemm|dwconv|window_attn|snake|clamp|rvq|rope|act_prep" --csv --log-file gpurun_out/launches_$tag.csv python tools/ncu_step.py > gpurun_out/ncu_list_$tag.log 2>&1
 echo "ncu list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:$kre -s 1 -c 1 -o gpurun_out/full_$tag -f python tools/ncu_step.py > gpurun_out/ncu_full_$tag.log 2>&1
 echo "ncu full rc=$?"
