@@ -34,7 +34,10 @@ typedef unsigned long long u64;
 constexpr int LL_CWARPS = 16;
 constexpr int LL_CTHREADS = LL_CWARPS * 32;      // 512 consumers
 constexpr int LL_THREADS = LL_CTHREADS + 32;     // + producer warp
-constexpr int LL_NSLOT = 32;                     // ring slots of one 4352-byte tile
+#ifndef LL_NSLOT_N
+#define LL_NSLOT_N 32
+#endif
+constexpr int LL_NSLOT = LL_NSLOT_N;             // ring slots of one 4352-byte tile
 constexpr int LL_PLANES = 4;                     // producer lanes issuing TMA copies
 constexpr int LL_MAXK = 6144;                    // largest contraction length (talker intermediate size)
 constexpr int LL_MAXH = 2048;                    // largest hidden size (one float4 per consumer thread)
@@ -64,6 +67,8 @@ struct LLParams {
     unsigned int* state;                         // [0] tag base (persists across launches), [1] error code
     unsigned long long* timing;                  // optional [grid][LL_NSTAMP]
     int pf_dist;                                 // L2 prefetch distance in tiles ahead of the TMA cursor (0 = off)
+    int fine;                                    // sub-phase profiling stamps (Q3T_LL_FINE=1)
+    int att_chunk, att_maxsplit;                 // attention geometry: smallest chunk (tokens) and most splits per kv head
     // ---- stack mode
     int which;                                   // 0 = talker stack, 1 = code-predictor stack
     const int* pos; const float* x_in; float* hidden_out; float* logits_out; q3t_w8 head;
@@ -81,7 +86,7 @@ struct LLParams {
 // ---- PTX helpers ------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));   // per-SM cycle counter: exact for durations inside one CTA
     return t;
 }
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -269,12 +274,14 @@ struct CState {
     int red_par;            // parity of the double-buffered block-reduction scratch
 };
 
-#ifdef LL_FINE
-#define LL_FSTAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP) p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = gtimer(); } while (0)
-#else
-#define LL_FSTAMP() do { } while (0)
-#endif
-#define LL_STAMP() do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP) p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = gtimer(); } while (0)
+// Profiling stamps (thread 0 of every CTA): {id : 20 bits | clock64 cycles of this SM : 44 bits}.  ids < 32 mark phase ends
+// and are always written when a timing buffer is given; ids >= 32 are sub-phase marks, written when Q3T_LL_FINE=1.
+#define LL_STAMP(id) do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP && ((id) < 32 || p.fine)) \
+    p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = ((unsigned long long)(id) << 44) | (gtimer() & ((1ull << 44) - 1)); } while (0)
+enum { ST_START = 0, ST_QKV_PRO = 1, ST_QKV = 2, ST_ATTN = 3, ST_O_PRO = 4, ST_O = 5, ST_GU_PRO = 6, ST_GU = 7, ST_DOWN_PRO = 8,
+       ST_DOWN = 9, ST_END = 10, ST_SAMPLE = 11, ST_CP_PASS = 12,
+       ST_F_POLL = 32, ST_F_TILES = 34, ST_F_GBAR = 35, ST_F_ATT_A = 36, ST_F_ATT_B = 37, ST_F_ATT_C = 38, ST_F_ATT_D = 39,
+       ST_F_ATT_E = 40, ST_F_ATT_F = 41, ST_F_ATT_G = 42, ST_F_MERGE = 43 };
 
 // block sum over the 512 consumer threads; `red` is double buffered by `parity`, so one barrier per call is enough
 __device__ __forceinline__ float cblock_sum(float v, float* red, int parity) {
@@ -369,7 +376,9 @@ __device__ LL_FN void gemv_phase(CState& st, const MatD& W, int epi, u64* ll_out
         kc += kstep; if (kc >= nkc) kc -= nkc;
     }
     st.seq += nt;
+    LL_STAMP(ST_F_TILES);
     cbar();
+    LL_STAMP(ST_F_GBAR);
     // rows: four lanes per output row add every fourth k-chunk, two shuffles finish the sum (fixed order); a warp
     // covers 8 rows per iteration.  SwiGLU tiles hold gate rows 0..7 and the matching up rows 8..15 (weights interleaved
     // at load): slots 0..3 of a warp take gate rows, slots 4..7 the matching up rows, paired with one more shuffle.
@@ -413,6 +422,7 @@ __device__ LL_FN void pro_norm(CState& st, const u64* ll_add, uint32_t tag_add, 
             reinterpret_cast<float4*>(s.resid)[tid] = v;
         }
     }
+    LL_STAMP(ST_F_POLL);
     const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     st.red_par ^= 1;
     const float rstd = rsqrtf(cblock_sum(ss, s.red, st.red_par) / (float)H + eps);
@@ -425,7 +435,7 @@ __device__ LL_FN void pro_norm(CState& st, const u64* ll_add, uint32_t tag_add, 
 }
 
 // LL words (already activated values) -> digits; K <= LL_MAXK
-__device__ LL_FN void pro_ll(const u64* ll, uint32_t tag, int K) {
+__device__ LL_FN void pro_ll(CState& st, const u64* ll, uint32_t tag, int K) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
@@ -434,6 +444,7 @@ __device__ LL_FN void pro_ll(const u64* ll, uint32_t tag, int K) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) { const int k4 = tid + i * LL_CTHREADS; on[i] = k4 < K4; pp[i] = ll + 4 * (size_t)k4; }
     ll_ld4n<NV>(pp, on, tag, v, p.state);
+    LL_STAMP(ST_F_POLL);
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         if (on[i]) emit_digits(s, v[i], tid + i * LL_CTHREADS, lane);
@@ -449,7 +460,7 @@ __device__ LL_FN void pro_plain(const float* x, int K) {
 }
 
 // attention partial records of every split -> merged head outputs -> digits  (input of the O projection)
-__device__ LL_FN void pro_attn(const u64* ll_attn, uint32_t tag, int q_dim, int nsplit) {
+__device__ LL_FN void pro_attn(CState& st, const u64* ll_attn, uint32_t tag, int q_dim, int nsplit) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, K4 = q_dim >> 2;
@@ -489,6 +500,7 @@ __device__ LL_FN void pro_attn(const u64* ll_attn, uint32_t tag, int q_dim, int 
                 M = Mn;
             }
         }
+        LL_STAMP(ST_F_MERGE);
         const float il = 1.f / L;
         emit_digits(s, make_float4(A.x * il, A.y * il, A.z * il, A.w * il), k4, lane);
     }
@@ -496,11 +508,11 @@ __device__ LL_FN void pro_attn(const u64* ll_attn, uint32_t tag, int q_dim, int 
 }
 
 // ---- attention geometry (uniform over the grid) -----------------------------------------------------------------------------
-__device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int& chunk, int& nsplit) {
+__device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int chunk_min, int split_max, int& chunk, int& nsplit) {
     int maxsplit = grid / n_kv;
-    if (maxsplit > LL_MAXSPLIT) maxsplit = LL_MAXSPLIT;
+    if (maxsplit > split_max) maxsplit = split_max;
     if (maxsplit < 1) maxsplit = 1;
-    chunk = 64;
+    chunk = chunk_min;
     if (ctx > chunk * maxsplit) {
         chunk = (ctx + maxsplit - 1) / maxsplit;
         chunk = (chunk + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE * Q3T_KV_PAGE;
@@ -546,7 +558,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             vreg[i] = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
         }
     }
-    LL_FSTAMP();   // A: preload issued
+    LL_STAMP(ST_F_ATT_A);   // A: preload issued
     // 2. q heads of this kv head (+ k, v of the new token on the split that owns it)
     if (warp < REP + 2) {
         const bool is_q = warp < REP, is_k = warp == REP;
@@ -556,7 +568,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             const int page_new = owner ? s.pages[(pos - s0) / Q3T_KV_PAGE] : 0;
             const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
             const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
-            LL_FSTAMP();   // B: q words arrived
+            LL_STAMP(ST_F_ATT_B);   // B: q words arrived
             float x[4] = {xv.x, xv.y, xv.z, xv.w};
             if (is_q || is_k) {
                 const float nw[4] = {nw4.x, nw4.y, nw4.z, nw4.w};
@@ -586,9 +598,9 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             }
         }
     }
-    LL_FSTAMP();   // C: q normalised, rotated, stored
+    LL_STAMP(ST_F_ATT_C);   // C: q normalised, rotated, stored
     cbar();
-    LL_FSTAMP();   // D: barrier
+    LL_STAMP(ST_F_ATT_D);   // D: barrier
     // 3. online softmax per half-warp (one token per half-warp per iteration)
     float m_run[REP], l_run[REP], acc[REP][EPL], qr[REP][EPL];
 #pragma unroll
@@ -643,7 +655,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
         }
         step(tok, kr, vr);
     }
-    LL_FSTAMP();   // E: scores + online softmax done
+    LL_STAMP(ST_F_ATT_E);   // E: scores + online softmax done
     // 4. merge the two half-warps of a warp, then the 16 warps through shared memory
 #pragma unroll
     for (int r = 0; r < REP; ++r) {
@@ -663,9 +675,9 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             if (sl == 0) { part_s[(warp * REP + r) * LL_REC + D] = m_run[r]; part_s[(warp * REP + r) * LL_REC + D + 1] = l_run[r]; }
         }
     }
-    LL_FSTAMP();   // F: half-warp merge stored
+    LL_STAMP(ST_F_ATT_F);   // F: half-warp merge stored
     cbar();
-    LL_FSTAMP();   // G: barrier
+    LL_STAMP(ST_F_ATT_G);   // G: barrier
     for (int i = tid; i < REP * D; i += LL_CTHREADS) {
         const int r = i / D, d = i % D;
         // 48 independent shared-memory loads, then a max tree and 16 independent exponentials
@@ -710,7 +722,7 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
         sincosf((float)pos * S.inv_freq[tid], &sn, &cs);
         s.cs[tid] = cs; s.sn[tid] = sn;
     }
-    attn_geometry(pos + 1, S.n_kv, gridDim.x, st.chunk, st.nsplit);
+    attn_geometry(pos + 1, S.n_kv, gridDim.x, p.att_chunk, p.att_maxsplit, st.chunk, st.nsplit);
     if ((int)blockIdx.x < S.n_kv * st.nsplit) {
         // page ids of this CTA's attention chunk: constant during the pass, so no attention phase starts with a
         // dependent block-table load in front of its K/V loads
@@ -724,33 +736,33 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
         const LayerD& L = lay[l];
         // ---- QKV
         pro_norm(st, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
-        LL_STAMP();
+        LL_STAMP(ST_QKV_PRO);
         const uint32_t t_qkv = ++st.gen;
         gemv_phase(st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
-        LL_STAMP();
+        LL_STAMP(ST_QKV);
         // ---- attention (first n_kv*nsplit CTAs)
         const uint32_t t_att = ++st.gen;
         if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
         else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
-        LL_STAMP();
+        LL_STAMP(ST_ATTN);
         // ---- O projection
-        pro_attn(p.x_attn, t_att, q_dim, st.nsplit);
-        LL_STAMP();
+        pro_attn(st, p.x_attn, t_att, q_dim, st.nsplit);
+        LL_STAMP(ST_O_PRO);
         const uint32_t t_o = ++st.gen;
         gemv_phase(st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
-        LL_STAMP();
+        LL_STAMP(ST_O);
         // ---- gate/up (+ SwiGLU in the epilogue)
         pro_norm(st, p.x_o, t_o, L.post_norm, nullptr, S.hidden, S.eps);
-        LL_STAMP();
+        LL_STAMP(ST_GU_PRO);
         const uint32_t t_act = ++st.gen;
         gemv_phase(st, L.gu, EPI_SWIGLU, p.x_act, nullptr, t_act);
-        LL_STAMP();
+        LL_STAMP(ST_GU);
         // ---- down
-        pro_ll(p.x_act, t_act, S.inter);
-        LL_STAMP();
+        pro_ll(st, p.x_act, t_act, S.inter);
+        LL_STAMP(ST_DOWN_PRO);
         const uint32_t t_down = ++st.gen;
         gemv_phase(st, L.down, EPI_RAW, p.x_down, nullptr, t_down);
-        LL_STAMP();
+        LL_STAMP(ST_DOWN);
         add = p.x_down; add_tag = t_down;
     }
     if (io.want_final) pro_norm(st, add, add_tag, S.final_norm, io.hidden_out, S.hidden, S.eps);
@@ -914,7 +926,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
     CState st;
     st.seq = 0; st.nstamp = 0; st.red_par = 0; st.nsplit = 1; st.chunk = 128;
     st.gen = *reinterpret_cast<volatile unsigned int*>(p.state);
-    LL_STAMP();
+    LL_STAMP(ST_START);
     if (p.mode == LL_MODE_STACK) {
         const int pos = __ldcg(p.pos);
         for (int k4 = tid; k4 < (p.talker.hidden >> 2); k4 += LL_CTHREADS)
@@ -925,7 +937,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
             const uint32_t t_head = ++st.gen;
             gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits_out, t_head);
         }
-        LL_STAMP();
+        LL_STAMP(ST_END);
     } else {
         const int step = __ldcg(p.step), pos_t = __ldcg(p.pos_talker);
         const int H = p.talker.hidden, E = p.emb_dim;
@@ -942,11 +954,11 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
             if (p.done && code == p.talker_sp.eos_id) p.done[0] = 1;
         }
         const int code0 = code;
-        LL_STAMP();
+        LL_STAMP(ST_SAMPLE);
         // ---- code predictor: position 0 = projected talker hidden, then one pass per residual codebook.
         // The next talker input is accumulated on the way, in registers: emb0[c0] + emb1[c1] + ... in order
         cp_pass(st, p.hidden, 0, -1, step);
-        LL_STAMP();
+        LL_STAMP(ST_CP_PASS);
         float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int g = 0; g < G - 1; ++g) {
             const float* row = (g == 0 ? p.codec_embedding : p.cp_embeddings[g - 1]) + (size_t)code * E;
@@ -955,7 +967,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 if (g == 0) xn = r4; else { xn.x += r4.x; xn.y += r4.y; xn.z += r4.z; xn.w += r4.w; }
             }
             code = cp_pass(st, row, g + 1, g, step);
-            LL_STAMP();
+            LL_STAMP(ST_CP_PASS);
         }
         // ---- next talker input: running sum + last code's row, then the trailing text row
         {
@@ -975,7 +987,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         stack_consume(st, p.talker, s.lay, pos_t, io);
         const uint32_t t_head = ++st.gen;
         gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits, t_head);
-        LL_STAMP();
+        LL_STAMP(ST_END);
         // state other CTAs read at the start of the launch is only updated here, after the last all-to-all exchange
         if (rec) {
             *p.pos_talker = pos_t + 1; *p.step = step + 1;
@@ -994,6 +1006,20 @@ static void fill_stack(LLStack& d, const q3t_stack& st) {
     d.kv_pool = (__nv_bfloat16*)st.kv_pool; d.kv_layer_stride = st.kv_layer_stride_bytes / 2; d.block_tbl = st.block_tbl;
 }
 
+// run-time tunables (profiling aids; the defaults are what the committed measurements use)
+struct LLTune { int pf, fine, chunk, msplit; };
+static const LLTune& ll_tune() {
+    static LLTune t = {-1, 0, 64, LL_MAXSPLIT};
+    if (t.pf < 0) {
+        const char* e;
+        t.pf = (e = getenv("Q3T_LL_PF")) ? atoi(e) : 0;
+        t.fine = (e = getenv("Q3T_LL_FINE")) ? atoi(e) : 0;
+        if ((e = getenv("Q3T_LL_CHUNK"))) { t.chunk = atoi(e); t.chunk = t.chunk < 16 ? 16 : (t.chunk + 15) / 16 * 16; }
+        if ((e = getenv("Q3T_LL_MAXSPLIT"))) { t.msplit = atoi(e); t.msplit = t.msplit < 1 ? 1 : (t.msplit > LL_MAXSPLIT ? LL_MAXSPLIT : t.msplit); }
+    }
+    return t;
+}
+
 static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.layers_dev != nullptr, "frame_ll: layers_dev missing");
     Q3T_REQUIRE(st.head_dim == 128, "frame_ll: head_dim must be 128");
@@ -1001,7 +1027,7 @@ static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
     Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
     Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
-    Q3T_REQUIRE(st.max_pages <= 64 * (grid / st.n_kv_heads < LL_MAXSPLIT ? grid / st.n_kv_heads : LL_MAXSPLIT),
+    Q3T_REQUIRE(st.max_pages <= 64 * (grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit),
                 "frame_ll: context too long for the per-CTA page-id table");
     const int qkv_n = (st.n_heads + 2 * st.n_kv_heads) * st.head_dim;
     const int n_max = 2 * st.inter > qkv_n ? 2 * st.inter : qkv_n;
@@ -1043,9 +1069,8 @@ static void carve(LLParams& p, void* work, const q3t_stack* t, const q3t_stack* 
 }
 
 static int launch_ll(LLParams& p, cudaStream_t stream) {
-    static int pf = -1;
-    if (pf < 0) { const char* e = getenv("Q3T_LL_PF"); pf = e ? atoi(e) : 0; }
-    p.pf_dist = pf;
+    const LLTune& t = ll_tune();
+    p.pf_dist = t.pf; p.fine = t.fine; p.att_chunk = t.chunk; p.att_maxsplit = t.msplit;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(frame_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM_BYTES);

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libq3tts_b200.so")
+# Q3T_LIB selects another build of the same library (kernel-tuning experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("Q3T_LIB") or os.path.join(_HERE, "libq3tts_b200.so")
 
 TILE_BYTES = 4352
 KV_PAGE = 16
