@@ -216,15 +216,15 @@ _MODE_BY_FOLDER = {"customvoice": "custom_voice", "voicedesign": "voice_design",
 def load_model(model_path: str, device: str = "cuda", **kw) -> Model:
     """Drop-in for `mlx_audio.tts.utils.load_model(model_path)` (reference io.py:111-112).
 
-    Reads `<model_path>/config.json` when present.  Real `mlx-community/*-8bit` safetensors are a 'next' row
-    (SURVEY 8f-1): a directory holding `model.safetensors` raises ValueError (which the reference reports as
-    "Failed to load model", io.py:115-117); a directory without weights gets seeded random-init weights of the
-    architecture its config/folder names (the offline parity/benchmark set-up)."""
+    Reads `<model_path>/config.json` when present.  A directory holding `model.safetensors` (the `mlx-community/*-8bit`
+    layout the reference downloads, io.py:42-52) is read by `mlx_loader.load_mlx_checkpoint` - the affine 8-bit codes are
+    taken as they are; a malformed checkpoint raises ValueError/OSError, which the reference reports as "Failed to load
+    model" (io.py:115-117).  A directory without weights gets seeded random-init weights of the architecture its
+    config/folder names (the offline parity/benchmark set-up)."""
     if not os.path.isdir(model_path):
         raise OSError(f"model directory not found: {model_path}")
-    if os.path.exists(os.path.join(model_path, "model.safetensors")) or \
-            os.path.exists(os.path.join(model_path, "model.safetensors.index.json")):
-        raise ValueError("loading MLX-quantised safetensors is not implemented yet in the B200 backend")
+    has_ckpt = os.path.exists(os.path.join(model_path, "model.safetensors")) or \
+        os.path.exists(os.path.join(model_path, "model.safetensors.index.json"))
     cj = os.path.join(model_path, "config.json")
     meta = {}
     if os.path.exists(cj):
@@ -235,5 +235,9 @@ def load_model(model_path: str, device: str = "cuda", **kw) -> Model:
     size = meta.get("b200_size", "full")
     cfg = ModelConfig.from_dict(meta["b200_config"]) if "b200_config" in meta else getattr(cfgmod, size)(mode)
     cfg.tts_model_type = mode
-    ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False)
+    if has_ckpt:
+        from .mlx_loader import load_mlx_checkpoint
+        ws = load_mlx_checkpoint(model_path, cfg, device=device)
+    else:
+        ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False)
     return Model(cfg, ws, device, model_path=model_path, **kw)

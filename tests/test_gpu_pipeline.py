@@ -252,3 +252,24 @@ def test_generate_audio_writes_audio_000_wav(small_setup, tmp_path):
     with wave.open(str(tmp_path / "audio_000.wav")) as w:
         assert w.getframerate() == 24000 and w.getnchannels() == 1 and w.getsampwidth() == 2
         assert w.getnframes() == cfg.codec.out_len(5)
+
+
+def test_mlx_checkpoint_folder_loads_and_generates_identical_codes(small_setup, tmp_path):
+    """`load_model(<folder with model.safetensors>)` (reference io.py:111-112) reads the MLX affine 8-bit
+    layout; the engine built from it must produce exactly the codes of the engine built from the in-memory store."""
+    from qwen3_tts_b200 import mlx_loader as ML
+    from qwen3_tts_b200.model import load_model
+    cfg, ws, model, oracle = small_setup
+    d = tmp_path / "models" / "Qwen3-TTS-12Hz-small-CustomVoice-8bit"
+    d.mkdir(parents=True)
+    ML.export_mlx_checkpoint(ws, str(d), extra_config={"b200_config": cfg.to_dict(), "tts_model_type": "custom_voice"})
+    m2 = load_model(str(d), max_frames=64, max_ctx=256, max_trailing=64)
+    ids = _text_ids(cfg, 9, 5)
+    outs = []
+    for m in (model, m2):
+        m.engine.set_sampling(do_sample=False)
+        pre, tr = m.build_prefill(ids, speaker="ryan", language="english")
+        outs.append(m.generate_codes(pre, tr, 10).cpu())
+    assert torch.equal(outs[0], outs[1])
+    wav1, wav2 = model.decode(outs[0].cuda()), m2.decode(outs[1].cuda())
+    assert torch.equal(wav1, wav2)
