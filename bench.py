@@ -287,6 +287,9 @@ def main():
     n_codec0 = lib.q3t_launch_count()
     model.decode(e.codes[0, :FRAMES])
     codec_launches = int(lib.q3t_launch_count() - n_codec0)
+    n_pre0 = lib.q3t_launch_count()                   # prompt rows on the tcgen05 GEMM (eager launches, counted by the library)
+    e.prefill(prefill[None], None, trailing[None])
+    prefill_launches = int(lib.q3t_launch_count() - n_pre0)
     with ClockSampler(local) as clk:
         ms_dev, wav = timed(step_device, args.steps)
         # talker decode step alone (the north-star roofline): graph of one token at ctx ~ L0 + FRAMES/2
@@ -314,9 +317,10 @@ def main():
     except Exception:
         pass
     launches_step = e.launches_per_frame
-    # launches inside one timed step: L0 prefill token steps + FRAMES frames + the codec (counted at graph capture)
-    per_tok = e.launches.get("step", 0)
-    gpu_launches = args.steps * (L0 * per_tok + FRAMES * (launches_step or 0) + codec_launches)
+    # launches inside one timed step: prefill + FRAMES frames (counted at graph capture) + the codec
+    if prefill_launches == 0:                          # token-by-token prefill replays the captured step graph
+        prefill_launches = L0 * e.launches.get("step", 0)
+    gpu_launches = args.steps * (prefill_launches + FRAMES * (launches_step or 0) + codec_launches)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "w8a32(f32 accumulate)",
             "data": "synthetic", "config": workload_config(args),

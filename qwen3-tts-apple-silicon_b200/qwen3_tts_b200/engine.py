@@ -42,7 +42,7 @@ class TalkerEngine:
 
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", batch: int = 1, max_frames: int = 512,
                  max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1,
-                 use_mega: bool = True):
+                 use_mega: bool = True, prefill: str = "auto", prefill_gemm_rows: int = 32):
         self.lib = L.load()
         self.cfg, self.dev, self.B = cfg, torch.device(device), batch
         self.max_frames, self.max_ctx, self.max_trailing = max_frames, max_ctx, max_trailing
@@ -186,7 +186,11 @@ class TalkerEngine:
         self.gemm_ws = torch.empty(8 * max(B, 1) * nmax, **f32)
         self.gemm_counters = torch.zeros(1024, **i32)
         fa.gemm_ws, fa.gemm_ws_floats, fa.gemm_counters = self.keep(self.gemm_ws), self.gemm_ws.numel(), self.keep(self.gemm_counters)
-        self.gemm_prefill = self.B > 2
+        # prompt rows go through the tcgen05 W8 GEMM (bf16 operands, the logit tolerance of BASELINE.json) when there are
+        # enough of them; "decode" pins the token-by-token path through the decode kernels (exact-integer contractions)
+        assert prefill in ("auto", "gemm", "decode")
+        self.prefill_mode, self.prefill_gemm_rows = prefill, prefill_gemm_rows
+        self.gemm_prefill = self.B > 2 or prefill == "gemm"
         self.set_sampling()
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
         self.use_graphs = True
@@ -316,7 +320,7 @@ class TalkerEngine:
         tr = trailing.to(self.dev, torch.float32)
         self.trailing[:, :n_tr] = tr
         self.trailing[:, n_tr:] = tr[:, -1:]
-        if self.gemm_prefill:
+        if self.prefill_mode != "decode" and (self.gemm_prefill or sum(lengths) >= self.prefill_gemm_rows):
             self._prefill_gemm(embeds, lengths)
         else:
             off = torch.tensor([Lmax - l for l in lengths], device=self.dev, dtype=torch.int32)

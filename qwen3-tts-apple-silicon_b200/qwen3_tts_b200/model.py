@@ -68,14 +68,15 @@ def _load_tokenizer(path: Optional[str], cfg: ModelConfig):
 
 class Model:
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", model_path: Optional[str] = None,
-                 max_frames: int = 2048, max_ctx: int = 4096, batch: int = 1, max_trailing: int = 1024):
+                 max_frames: int = 2048, max_ctx: int = 4096, batch: int = 1, max_trailing: int = 1024,
+                 prefill: str = "auto"):
         if not torch.cuda.is_available():
             raise RuntimeError("qwen3_tts_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.cfg = cfg
         self.sample_rate = cfg.codec.sample_rate
         self.device = device
         self.engine = TalkerEngine(cfg, ws, device, batch=batch, max_frames=max_frames, max_ctx=max_ctx,
-                                   max_trailing=max_trailing)
+                                   max_trailing=max_trailing, prefill=prefill)
         self.codec = CodecDecoder(cfg, ws, device)
         self.tokenizer = _load_tokenizer(model_path, cfg)
 

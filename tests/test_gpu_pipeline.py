@@ -51,7 +51,8 @@ def small_setup(cuda):
     from qwen3_tts_b200.model import Model
     cfg = Cfg.small("custom_voice")
     ws = make_weights(cfg, seed=0, head_std=0.2)
-    model = Model(cfg, ws, "cuda", max_frames=64, max_ctx=256, max_trailing=64)
+    # prefill="decode": these tests pin the exact-integer decode kernels; the GEMM prefill has its own tests below
+    model = Model(cfg, ws, "cuda", max_frames=64, max_ctx=256, max_trailing=64, prefill="decode")
     oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
     return cfg, ws, model, oracle
 
@@ -75,7 +76,7 @@ def test_teacher_forced_logits_and_argmax(small_setup):
     n = 12
     codes_o, rec = oracle.generate(pre, tr, n, record=True)
     e = model.engine
-    e2 = type(e)(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=256, keep_cp_logits=True)
+    e2 = type(e)(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=256, keep_cp_logits=True, prefill="decode")
     e2.set_sampling(do_sample=False)
     e2.set_forced(codes_o[None])
     e2.use_graphs = False
@@ -155,7 +156,7 @@ def test_batch2_rows_are_independent(cuda):
     Lm = max(La, Lb)
     emb = torch.zeros(2, Lm, cfg.talker.hidden_size)
     emb[0, Lm - La:], emb[1, Lm - Lb:] = pa, pb           # right-aligned
-    e = TalkerEngine(cfg, ws, "cuda", batch=2, max_frames=32, max_ctx=128)
+    e = TalkerEngine(cfg, ws, "cuda", batch=2, max_frames=32, max_ctx=128, prefill="decode")
     e.set_sampling(do_sample=False)
     e.prefill(emb, [La, Lb], torch.stack([ta, tb]))
     codes = e.generate(8).cpu().long()
@@ -273,3 +274,36 @@ def test_mlx_checkpoint_folder_loads_and_generates_identical_codes(small_setup, 
     assert torch.equal(outs[0], outs[1])
     wav1, wav2 = model.decode(outs[0].cuda()), m2.decode(outs[1].cuda())
     assert torch.equal(wav1, wav2)
+
+
+def test_batch1_prompt_on_the_gemm_matches_oracle(cuda):
+    """Batch 1 in the product configuration: the prompt rows go through the tcgen05 W8 GEMM (prefill="auto", >= 32 rows),
+    the frames through the persistent kernel.  Logits within the bf16 tolerance of BASELINE.json, codes equal to the
+    oracle's up to a near-tie, and the K/V rows the prefill leaves behind within bf16 rounding of the exact path's."""
+    from qwen3_tts_b200.engine import TalkerEngine
+    cfg = Cfg.small("custom_voice")
+    ws = make_weights(cfg, seed=11, head_std=0.2)
+    oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
+    pre, tr = oracle.build_prefill(_text_ids(cfg, 40, 77), instruct_ids=[3, 4, 5, 6], speaker="ryan", language="english")
+    assert pre.shape[0] >= 32
+    e = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=32, max_ctx=256)
+    e.set_sampling(do_sample=False)
+    n0 = e.lib.q3t_launch_count()
+    e.prefill(pre[None], None, tr[None])
+    assert e.lib.q3t_launch_count() - n0 > 0 and not e.gemm_prefill      # eager GEMM launches, chosen by the row count
+    logits0 = e.logits.clone().cpu()
+    kv_gemm = e.talker_stack.kv_pool                                       # keep-alive handle only
+    codes = e.generate(6).cpu().long()[0]
+    co, rec = oracle.generate(pre, tr, 6, record=True)
+    assert _rel(logits0[0], rec["talker_logits"][0]) < LOGIT_RTOL
+    diff = codes != co
+    if diff.any():
+        f = int(diff.any(1).nonzero()[0]); g = int(diff[f].nonzero()[0])
+        lg = rec["talker_logits"][f] if g == 0 else rec["cp_logits"][f][g - 1]
+        gap = float(lg[int(co[f, g])] - lg[int(codes[f, g])])
+        assert 0 <= gap <= LOGIT_RTOL * float(lg.abs().max()), f"frame {f} group {g}: gap {gap:.3e}"
+    # same prompt through the decode kernels: first logits agree within the tolerance as well
+    e2 = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=32, max_ctx=256, prefill="decode")
+    e2.set_sampling(do_sample=False)
+    e2.prefill(pre[None], None, tr[None])
+    assert _rel(logits0[0], e2.logits.cpu()[0]) < LOGIT_RTOL
