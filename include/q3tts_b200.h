@@ -93,6 +93,10 @@ typedef struct {
     void* xb;
     /* optional split-K workspace (decode-sized M): partial sums [splits][M][N] fp32 + zero-initialised counters [1024] */
     float* splitk_ws;  long long splitk_ws_floats;  int* splitk_counters;
+    /* optional bf16 chaining between kernels (saves the fp32 round trip and the prologue launch):
+     *   x_bf16: the input rows are ALREADY bf16 [M, K] contiguous (prologue must be Q3T_PRO_RAW, x is ignored);
+     *   y_bf16: the epilogue writes bf16 rows [M, N] (or [M, N/2] with swiglu_out) contiguous INSTEAD of fp32 y. */
+    const void* x_bf16;  void* y_bf16;
 } q3t_gemm_args;
 
 int q3t_w8_gemm(const q3t_gemm_args* a, void* stream);
@@ -123,6 +127,7 @@ typedef struct {
     int mode;                 /* 0 = fused decode step; 1 = only write K/V of every row (prefill pass 1, use nsplit = 1);
                                  2 = attention only, K/V of the row itself already in the cache (prefill pass 2) */
     const int* seq_of_row;    /* optional [B]: block-table row of launch row b (prefill rows of one sequence share pages) */
+    void* out_bf16;           /* optional [B, H*D] bf16: written INSTEAD of `out` (feeds q3t_w8_gemm.x_bf16 directly) */
 } q3t_attn_args;
 
 int q3t_attn_decode(const q3t_attn_args* a, void* stream);
@@ -248,6 +253,7 @@ typedef struct {
     const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */
     void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
     unsigned long long* ll_timing;  /* optional profiling stamps, or NULL */
+    void* gemm_xb2;        /* optional second bf16 scratch [B, max K]: attention output and SwiGLU activations stay bf16 */
 } q3t_frame_args;
 
 /* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).

@@ -20,7 +20,7 @@ struct AttnParams {
     __nv_bfloat16* kv_pool;
     const int* block_tbl; int max_pages;
     const int* pos;
-    float* out; float* work; int* counters;
+    float* out; __nv_bfloat16* out_bf16; float* work; int* counters;
     int B, H, Hkv, nsplit;
     int mode;                 // 0 fused decode, 1 write K/V of the row only, 2 attention only (K/V already in the cache)
     const int* seq_of_row;    // optional: block-table row of launch row b (prefill: many rows share one sequence)
@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
             L = fmaf(__ldcg(rec + D + 1), w, L);
             A = fmaf(__ldcg(rec + d), w, A);
         }
-        p.out[(size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d] = A / L;
+        const size_t oi = (size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d;
+        if (p.out_bf16) p.out_bf16[oi] = __float2bfloat16_rn(A / L);   // feeds the O-projection GEMM without an fp32 round trip
+        else p.out[oi] = A / L;
     }
     if (tid == 0) p.counters[b * p.Hkv + kvh] = 0;   // re-arm for the next launch / graph replay
 }
@@ -235,7 +237,7 @@ int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream) {
     AttnParams p;
     p.qkv = a->qkv; p.q_norm_w = a->q_norm_w; p.k_norm_w = a->k_norm_w; p.eps = a->eps; p.inv_freq = a->inv_freq;
     p.kv_pool = (__nv_bfloat16*)a->kv_pool; p.block_tbl = a->block_tbl; p.max_pages = a->max_pages; p.pos = a->pos;
-    p.out = a->out; p.work = a->work; p.counters = a->counters; p.B = a->B; p.H = a->H; p.Hkv = a->Hkv;
+    p.out = a->out; p.out_bf16 = (__nv_bfloat16*)a->out_bf16; p.work = a->work; p.counters = a->counters; p.B = a->B; p.H = a->H; p.Hkv = a->Hkv;
     p.nsplit = a->nsplit; p.mode = a->mode; p.seq_of_row = a->seq_of_row;
     const int rep = a->H / a->Hkv;
     if (a->D == 128 && rep == 2) return launch_attn_t<128, 2>(p, stream);

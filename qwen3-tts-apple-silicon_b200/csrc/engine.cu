@@ -2,6 +2,7 @@
 // enqueued from C++ on one stream (CUDA-graph capturable; no host round trip between the 16 sampled
 // codes of a frame).  Replaces the per-frame body of mlx_audio's `Model.generate` loop
 // (cousin driver transformers qwen3_omni_moe/modeling_qwen3_omni_moe.py:3243-3279).
+#include <stdlib.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
@@ -68,6 +69,7 @@ int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float
 
 // rows through one W8 matrix: B <= 2 -> exact-integer GEMV (two rows per launch); more rows -> tcgen05 GEMM (bf16 operands)
 static void* g_xb = nullptr;    // bf16 scratch of the call in flight (set by the entry points below)
+static void* g_xb2 = nullptr;   // second bf16 scratch: attention output / SwiGLU activations handed from kernel to kernel as bf16
 static float* g_ws = nullptr; static long long g_ws_floats = 0; static int* g_counters = nullptr;
 static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
                      const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
@@ -95,6 +97,18 @@ static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long 
     return 0;
 }
 
+// tcgen05 GEMM whose input rows are already bf16 (x_bf16) and / or whose output stays bf16 (y_bf16): no prologue launch
+static int gemm_bf16(const q3t_w8& w, int M, const void* x_bf16, int prologue, const float* x, long long xs, const float* norm_w,
+                     float eps, int swiglu_out, const float* resid, long long rs, float* y, long long ys, void* y_bf16,
+                     cudaStream_t s) {
+    q3t_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.w = w; a.M = M; a.prologue = prologue; a.x = x; a.x_stride = xs; a.norm_w = norm_w; a.eps = eps; a.swiglu_out = swiglu_out;
+    a.resid = resid; a.resid_stride = rs; a.y = y; a.y_stride = ys; a.xb = g_xb; a.x_bf16 = x_bf16; a.y_bf16 = y_bf16;
+    a.splitk_ws = g_ws; a.splitk_ws_floats = g_ws_floats; a.splitk_counters = g_counters;
+    return launch_w8_gemm(&a, s);
+}
+
 // one token through a dense Qwen3 stack; x [B, hidden] is updated in place (residual stream)
 static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x, const int* pos, cudaStream_t s) {
     const int B = f->B, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim;
@@ -110,7 +124,17 @@ static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x,
         a.block_tbl = st.block_tbl; a.max_pages = st.max_pages; a.pos = pos; a.out = f->attn; a.work = f->attn_work;
         a.counters = f->attn_counters; a.B = B; a.H = st.n_heads; a.Hkv = st.n_kv_heads; a.D = st.head_dim;
         a.nsplit = st.attn_nsplit;
+        // batched path: the attention output and the SwiGLU activations go from kernel to kernel as bf16 rows (the GEMM
+        // rounds its operands to bf16 anyway - bit-identical to the fp32 round trip through act_prep_kernel, two launches less)
+        const bool chain = B > 2 && g_xb && g_xb2 && L.o.N % 128 == 0 && L.gate_up.N % 128 == 0 && L.down.N % 128 == 0;
+        if (chain) a.out_bf16 = g_xb2;
         Q3T_TRY(launch_attn_decode(&a, s));
+        if (chain) {
+            Q3T_TRY(gemm_bf16(L.o, B, g_xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, nullptr, s));
+            Q3T_TRY(gemm_bf16(L.gate_up, B, nullptr, Q3T_PRO_RMSNORM, x, hid, L.post_norm, st.eps, 1, nullptr, 0, nullptr, 0, g_xb2, s));
+            Q3T_TRY(gemm_bf16(L.down, B, g_xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, nullptr, s));
+            continue;
+        }
         Q3T_TRY(gemv_rows(L.o, B, Q3T_PRO_RAW, f->attn, qd, nullptr, 0.f, nullptr, 0, 0, 0, x, hid, x, hid, s));
         Q3T_TRY(gemv_rows(L.gate_up, B, Q3T_PRO_RMSNORM, x, hid, L.post_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->gu,
                           2 * st.inter, s));
@@ -198,7 +222,7 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
     const q3t_stack& st = f->talker;
     const int M = a->M, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim, qkvd = qd + 2 * kvd;
     Q3T_REQUIRE(M >= 1 && a->x && a->pos && a->seq_of_row && a->qkv && a->attn && a->gu && a->xb, "talker_prefill: arguments");
-    g_xb = a->xb; g_ws = nullptr; g_ws_floats = 0; g_counters = nullptr;
+    g_xb = a->xb; g_xb2 = nullptr; g_ws = nullptr; g_ws_floats = 0; g_counters = nullptr;
     for (int l = 0; l < st.n_layers; ++l) {
         const q3t_layer& L = st.layers_host[l];
         Q3T_TRY(gemv_rows(L.qkv, M, Q3T_PRO_RMSNORM, a->x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->qkv, qkvd, s));
@@ -223,7 +247,7 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
 
 static int talker_tail(const q3t_frame_args* f, cudaStream_t s) {
     const q3t_stack& t = f->talker;
-    g_xb = f->gemm_xb; g_ws = f->gemm_ws; g_ws_floats = f->gemm_ws_floats; g_counters = f->gemm_counters;
+    g_xb = f->gemm_xb; g_xb2 = nullptr; g_ws = f->gemm_ws; g_ws_floats = f->gemm_ws_floats; g_counters = f->gemm_counters;
     Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
     return gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->logits,
                      f->talker_vocab, s);
@@ -235,11 +259,11 @@ extern "C" int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int 
     return q3t::launch_rmsnorm(x, w, y, M, H, eps, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream) {
-    q3t::g_xb = f->gemm_xb; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
+    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
     return q3t::talker_step(f, want_logits, 0, (cudaStream_t)stream);
 }
 extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) {
-    q3t::g_xb = f->gemm_xb; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
+    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
     return q3t::frame(f, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_prefill(const q3t_prefill_args* a, void* stream) { return q3t::talker_prefill(a, (cudaStream_t)stream); }

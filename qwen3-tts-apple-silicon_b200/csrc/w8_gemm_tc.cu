@@ -47,6 +47,7 @@ struct GemmParams {
     const float* lin_bias; int act; int swiglu;     // epilogue
     const float* resid; long long resid_stride;
     float* y; long long y_stride;
+    __nv_bfloat16* yb;                          // optional: bf16 rows [M, N] ([M, N/2] with swiglu) instead of y
     int bn;                                     // tokens per CTA (multiple of 16, <= 256)
     int splits;                                 // split-K factor (gridDim.z); > 1 needs ws + counters
     float* ws; int* counters;                   // [splits][M][N] partial sums, one arrival counter per (n block, m block)
@@ -315,7 +316,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                             g.x += bg.x; g.y += bg.y; g.z += bg.z; g.w += bg.w; u.x += bu.x; u.y += bu.y; u.z += bu.z; u.w += bu.w;
                         }
                         const float4 o = make_float4(silu_f(g.x) * u.x, silu_f(g.y) * u.y, silu_f(g.z) * u.z, silu_f(g.w) * u.w);
-                        *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + (n0 >> 1) + 8 * j + 4 * h) = o;
+                        if (p.yb) {
+                            uint2 ob; ob.x = pack_bf16x2(o.x, o.y); ob.y = pack_bf16x2(o.z, o.w);
+                            *reinterpret_cast<uint2*>(p.yb + (size_t)m * (p.N >> 1) + (n0 >> 1) + 8 * j + 4 * h) = ob;
+                        } else {
+                            *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + (n0 >> 1) + 8 * j + 4 * h) = o;
+                        }
                     }
                 } else {
                     for (int i = dt; i < nt * 32; i += 512) {
@@ -341,7 +347,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                             const float4 r = *reinterpret_cast<const float4*>(p.resid + (size_t)m * p.resid_stride + n0 + 4 * q4);
                             x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
                         }
-                        *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + n0 + 4 * q4) = x;
+                        if (p.yb) {
+                            uint2 ob; ob.x = pack_bf16x2(x.x, x.y); ob.y = pack_bf16x2(x.z, x.w);
+                            *reinterpret_cast<uint2*>(p.yb + (size_t)m * p.N + n0 + 4 * q4) = ob;
+                        } else {
+                            *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + n0 + 4 * q4) = x;
+                        }
                     }
                 }
             }
@@ -396,22 +407,25 @@ __global__ void __launch_bounds__(256) act_prep_kernel(const PrepParams p) {
 int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     Q3T_REQUIRE(a->M >= 1, "w8_gemm: M must be >= 1");
     Q3T_REQUIRE(a->w.N % 128 == 0 && a->w.K % 256 == 0, "w8_gemm: N%128 / K%256");
-    Q3T_REQUIRE(a->xb != nullptr, "w8_gemm: bf16 activation scratch missing");
+    Q3T_REQUIRE(a->xb != nullptr || a->x_bf16 != nullptr, "w8_gemm: bf16 activation scratch missing");
+    Q3T_REQUIRE(!a->x_bf16 || (a->prologue == Q3T_PRO_RAW && !a->gather_idx), "w8_gemm: x_bf16 excludes prologue / gather");
     const int K = a->w.K;
-    // 1. activations -> bf16 (with the fused prologue)
+    // 1. activations -> bf16 (with the fused prologue), unless the producer kernel already wrote bf16 rows
     PrepParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.x = a->x; pp.x_stride = a->x_stride; pp.M = a->M; pp.K = K; pp.prologue = a->prologue; pp.norm_w = a->norm_w; pp.eps = a->eps;
     pp.gather_idx = a->gather_idx; pp.gather_idx_stride = a->gather_idx_stride; pp.gather_row_stride = a->gather_row_stride;
     pp.out = (__nv_bfloat16*)a->xb; pp.out_stride = K;
-    launch_pdl(act_prep_kernel, dim3(a->M), dim3(256), 0, stream, pp);
-    Q3T_CHECK_LAUNCH("act_prep");
+    if (!a->x_bf16) {
+        launch_pdl(act_prep_kernel, dim3(a->M), dim3(256), 0, stream, pp);
+        Q3T_CHECK_LAUNCH("act_prep");
+    }
     // 2. the GEMM
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.w = (const uint8_t*)a->w.w; p.N = a->w.N; p.K = K; p.xb = (const __nv_bfloat16*)a->xb; p.xb_stride = K; p.M = a->M;
+    p.w = (const uint8_t*)a->w.w; p.N = a->w.N; p.K = K; p.xb = (const __nv_bfloat16*)(a->x_bf16 ? a->x_bf16 : a->xb); p.xb_stride = K; p.M = a->M;
     p.lin_bias = a->w.lin_bias; p.act = a->act; p.swiglu = a->swiglu_out; p.resid = a->resid; p.resid_stride = a->resid_stride;
-    p.y = a->y; p.y_stride = a->y_stride;
+    p.y = a->y; p.y_stride = a->y_stride; p.yb = (__nv_bfloat16*)a->y_bf16;
     int bn = (a->M + 15) / 16 * 16;
     if (bn > TC_BN_MAX) bn = TC_BN_MAX;
     if (bn < 16) bn = 16;
@@ -452,7 +466,7 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a->xb, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p.xb, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) { snprintf(g_err, sizeof(g_err), "w8_gemm: cuTensorMapEncodeTiled failed (%d)", (int)cr); return 3; }
     launch_pdl(w8_gemm_tc_kernel, dim3(p.N / TC_BM, (a->M + bn - 1) / bn, p.splits), dim3(TC_THREADS), (size_t)TC_SMEM_BYTES, stream, p, tmap);

@@ -182,6 +182,8 @@ class TalkerEngine:
         kmax = max(t.hidden_size, t.intermediate_size, c.hidden_size, c.intermediate_size, t.q_dim, c.q_dim)
         self.gemm_xb = torch.empty(max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
         fa.gemm_xb = self.keep(self.gemm_xb)
+        self.gemm_xb2 = torch.empty(max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
+        fa.gemm_xb2 = self.keep(self.gemm_xb2)
         nmax = max(2 * t.intermediate_size, 2 * c.intermediate_size, V, Vc, t.q_dim + 2 * t.kv_dim)
         self.gemm_ws = torch.empty(8 * max(B, 1) * nmax, **f32)
         self.gemm_counters = torch.zeros(1024, **i32)

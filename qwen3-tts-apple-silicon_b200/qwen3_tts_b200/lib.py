@@ -33,13 +33,13 @@ class GemmArgs(C.Structure):
     _fields_ = [("w", W8), ("M", i32), ("prologue", i32), ("x", vp), ("x_stride", i64), ("norm_w", vp), ("eps", f32),
                 ("gather_idx", vp), ("gather_idx_stride", i32), ("gather_row_stride", i64), ("act", i32),
                 ("swiglu_out", i32), ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64), ("xb", vp),
-                ("splitk_ws", vp), ("splitk_ws_floats", i64), ("splitk_counters", vp)]
+                ("splitk_ws", vp), ("splitk_ws_floats", i64), ("splitk_counters", vp), ("x_bf16", vp), ("y_bf16", vp)]
 
 
 class AttnArgs(C.Structure):
     _fields_ = [("qkv", vp), ("q_norm_w", vp), ("k_norm_w", vp), ("eps", f32), ("inv_freq", vp), ("kv_pool", vp),
                 ("block_tbl", vp), ("max_pages", i32), ("pos", vp), ("out", vp), ("work", vp), ("counters", vp),
-                ("B", i32), ("H", i32), ("Hkv", i32), ("D", i32), ("nsplit", i32), ("mode", i32), ("seq_of_row", vp)]
+                ("B", i32), ("H", i32), ("Hkv", i32), ("D", i32), ("nsplit", i32), ("mode", i32), ("seq_of_row", vp), ("out_bf16", vp)]
 
 
 class Sampling(C.Structure):
@@ -75,7 +75,7 @@ class FrameArgs(C.Structure):
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
                 ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("gemm_ws", vp), ("gemm_ws_floats", i64), ("gemm_counters", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
-                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp)]
+                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp), ("gemm_xb2", vp)]
 
 
 class PrefillArgs(C.Structure):

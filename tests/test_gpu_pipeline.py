@@ -307,3 +307,25 @@ def test_batch1_prompt_on_the_gemm_matches_oracle(cuda):
     e2.set_sampling(do_sample=False)
     e2.prefill(pre[None], None, tr[None])
     assert _rel(logits0[0], e2.logits.cpu()[0]) < LOGIT_RTOL
+
+
+def test_bf16_chaining_between_batched_kernels_is_bit_identical(cuda, monkeypatch):
+    """Batched path: attention output and SwiGLU activations are handed to the next GEMM as bf16 rows (no act_prep
+    launch).  The GEMM rounds its operands to bf16 either way, so logits and codes must not change by a single bit."""
+    from qwen3_tts_b200.engine import TalkerEngine
+    cfg = Cfg.small("voice_design")
+    ws = make_weights(cfg, seed=6, head_std=0.2)
+    B, Lp = 5, 12
+    torch.manual_seed(3)
+    emb = torch.randn(B, Lp, cfg.talker.hidden_size) * 0.02
+    outs = []
+    for off in (False, True):
+        if off:
+            monkeypatch.setenv("Q3T_NO_BF16_CHAIN", "1")
+        e = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=16, max_ctx=64)
+        e.set_sampling(do_sample=False)
+        e.prefill(emb, None, None)
+        codes = e.generate(5).clone()
+        outs.append((e.logits.clone(), codes, e.launches_per_frame))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert outs[0][2] < outs[1][2], "the chained path must need fewer launches per frame"
