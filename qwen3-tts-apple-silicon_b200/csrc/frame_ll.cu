@@ -46,6 +46,10 @@ constexpr int LL_MAXSPLIT = 16;                  // attention splits per kv head
 constexpr int LL_REC = 130;                      // attention record: 128 acc + m + l
 constexpr int LL_SPIN_LIMIT = 1 << 22;           // watchdog: a poll that spins this long (~1 s) aborts the launch
 constexpr int LL_NSTAMP = 2048;
+#ifndef LL_PRE_N
+#define LL_PRE_N 2
+#endif
+static_assert(LL_PRE_N * 32 * 2 * 16 * 16 <= (LL_MAXK / 64) * 512, "attention K/V staging must fit the digit-plane buffer");
 
 enum { LL_MODE_STACK = 0, LL_MODE_FRAME = 1 };
 enum { EPI_RAW = 0, EPI_SWIGLU = 1 };
@@ -524,7 +528,7 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int c
 template <int REP>
 __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
                                  uint32_t tag_qkv, u64* ll_attn, uint32_t tag_out) {
-    constexpr int D = 128, EPL = 8, PRE = 2;
+    constexpr int D = 128, EPL = 8, PRE = LL_PRE_N;
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int chunk = st.chunk, nsplit = st.nsplit;
