@@ -9,9 +9,10 @@ from qwen3_tts_b200.weights import make_weights
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 T = int(sys.argv[3]) if len(sys.argv) > 3 else 24
+NS = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 cfg = Cfg.full("voice_design")
 ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False)
-e = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=T + 8, max_ctx=((L + T + 8 + 15) // 16) * 16 + 16, attn_nsplit=4)
+e = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=T + 8, max_ctx=((L + T + 8 + 15) // 16) * 16 + 16, attn_nsplit=NS)
 e.set_sampling(do_sample=False)
 emb = torch.randn(B, L, cfg.talker.hidden_size, device="cuda") * 0.02
 ev = lambda: torch.cuda.Event(enable_timing=True)
