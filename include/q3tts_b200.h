@@ -133,6 +133,23 @@ typedef struct {
 int q3t_attn_decode(const q3t_attn_args* a, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Causal GQA attention of the PROMPT rows on the tensor cores (prefill pass 2; replaces q RMSNorm + RoPE +
+ * mx.fast.scaled_dot_product_attention over the prompt).  K/V of every row are already in the paged cache
+ * (q3t_attn_decode mode 1).  Rows are ragged: row m is position pos[m] of sequence seq_of_row[m]; `blocks` [n_blocks, 2]
+ * = (first row, row count <= 32) lists runs of consecutive rows of ONE sequence (one CTA per block and kv head).
+ * Built for D = 128 and H = 2 * Hkv.  Writes out [M, H*D] fp32, or out_bf16 [M, H*D] when given.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    const float* qkv;  const float* q_norm_w;  float eps;  const float* inv_freq;
+    const void* kv_pool;  const int* block_tbl;  int max_pages;
+    const int* pos;  const int* seq_of_row;  const int* blocks;  int n_blocks;
+    float* out;  void* out_bf16;
+    int H, Hkv, D;
+} q3t_attn_prefill_args;
+
+int q3t_attn_prefill(const q3t_attn_prefill_args* a, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * On-device sampler (replaces mx.argmax / mx.random.categorical + host-side logits processors)
  * Order of operations = HF generation: repetition penalty over the set of
  * previously generated ids, min_new_tokens EOS mask, suppress range (except eos), temperature,
@@ -266,6 +283,7 @@ typedef struct {
     float* x; const int* pos; const int* seq_of_row;
     float* qkv; float* attn; float* gu; void* xb;
     float* attn_work; int* attn_counters;    /* >= M*Hkv*(H/Hkv)*(D+2) floats, M*Hkv ints (zeroed) */
+    const int* blocks; int n_blocks;         /* optional row blocks for q3t_attn_prefill (see there); 0 = per-row decode kernel */
 } q3t_prefill_args;
 int q3t_talker_prefill(const q3t_prefill_args* a, void* stream);
 /* final RMSNorm of `x` [B, H] -> `hidden`, codec head -> `logits` (the tail of a talker step) */

@@ -11,6 +11,7 @@ namespace q3t {
 int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream);
 int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream);
 int launch_attn_decode(const q3t_attn_args* a, cudaStream_t stream);
+int launch_attn_prefill(const q3t_attn_prefill_args* a, cudaStream_t stream);
 int launch_sample(const q3t_sample_args* a, cudaStream_t stream);
 int launch_stack_pass(const q3t_stack_pass_args* a, cudaStream_t stream);
 int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream);
@@ -235,8 +236,18 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
         t.seq_of_row = a->seq_of_row;
         t.nsplit = 1; t.mode = 1;                    // pass 1: K/V rows of every prompt token into the cache
         Q3T_TRY(launch_attn_decode(&t, s));
-        t.mode = 2;                                  // pass 2: causal attention of every row over its prefix
-        Q3T_TRY(launch_attn_decode(&t, s));
+        if (a->blocks && a->n_blocks > 0 && st.head_dim == 128 && st.n_heads == 2 * st.n_kv_heads) {
+            // pass 2 on the tensor cores: 32 rows of a sequence share every K/V tile (csrc/attn_prefill.cu)
+            q3t_attn_prefill_args u;
+            memset(&u, 0, sizeof(u));
+            u.qkv = a->qkv; u.q_norm_w = L.q_norm; u.eps = st.eps; u.inv_freq = st.inv_freq; u.kv_pool = t.kv_pool;
+            u.block_tbl = st.block_tbl; u.max_pages = st.max_pages; u.pos = a->pos; u.seq_of_row = a->seq_of_row;
+            u.blocks = a->blocks; u.n_blocks = a->n_blocks; u.out = a->attn; u.H = st.n_heads; u.Hkv = st.n_kv_heads; u.D = st.head_dim;
+            Q3T_TRY(launch_attn_prefill(&u, s));
+        } else {
+            t.mode = 2;                              // pass 2: causal attention of every row over its prefix
+            Q3T_TRY(launch_attn_decode(&t, s));
+        }
         Q3T_TRY(gemv_rows(L.o, M, Q3T_PRO_RAW, a->attn, qd, nullptr, 0.f, nullptr, 0, 0, 0, a->x, hid, a->x, hid, s));
         Q3T_TRY(gemv_rows(L.gate_up, M, Q3T_PRO_RMSNORM, a->x, hid, L.post_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->gu,
                           2 * st.inter, s));

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -355,6 +356,14 @@ class TalkerEngine:
         a.x, a.pos, a.seq_of_row = rows.data_ptr(), pos.data_ptr(), seq.data_ptr()
         a.qkv, a.attn, a.gu, a.xb = qkv.data_ptr(), attn.data_ptr(), gu.data_ptr(), xb.data_ptr()
         a.attn_work, a.attn_counters = work.data_ptr(), counters.data_ptr()
+        # runs of <= 32 consecutive rows of one sequence: one CTA of the tensor-core prefill attention each
+        blocks, r0 = [], 0
+        for l in lengths:
+            blocks += [(r0 + o, min(32, l - o)) for o in range(0, l, 32)]
+            r0 += l
+        blk = torch.tensor(blocks, dtype=torch.int32, device=dev).contiguous()
+        if not os.environ.get("Q3T_PREFILL_ATTN_PER_ROW"):
+            a.blocks, a.n_blocks = blk.data_ptr(), len(blocks)
         L.check(self.lib.q3t_talker_prefill(C.byref(a), L.stream_ptr()), "talker_prefill")
         last = torch.tensor([sum(lengths[:b + 1]) - 1 for b in range(B)], device=dev)
         self.x.copy_(rows[last])

@@ -42,6 +42,12 @@ class AttnArgs(C.Structure):
                 ("B", i32), ("H", i32), ("Hkv", i32), ("D", i32), ("nsplit", i32), ("mode", i32), ("seq_of_row", vp), ("out_bf16", vp)]
 
 
+class AttnPrefillArgs(C.Structure):
+    _fields_ = [("qkv", vp), ("q_norm_w", vp), ("eps", f32), ("inv_freq", vp), ("kv_pool", vp), ("block_tbl", vp),
+                ("max_pages", i32), ("pos", vp), ("seq_of_row", vp), ("blocks", vp), ("n_blocks", i32), ("out", vp),
+                ("out_bf16", vp), ("H", i32), ("Hkv", i32), ("D", i32)]
+
+
 class Sampling(C.Structure):
     _fields_ = [("do_sample", i32), ("temperature", f32), ("top_k", i32), ("top_p", f32),
                 ("repetition_penalty", f32), ("min_new_tokens", i32), ("suppress_lo", i32), ("suppress_hi", i32),
@@ -80,7 +86,7 @@ class FrameArgs(C.Structure):
 
 class PrefillArgs(C.Structure):
     _fields_ = [("f", C.POINTER(FrameArgs)), ("M", i32), ("x", vp), ("pos", vp), ("seq_of_row", vp), ("qkv", vp), ("attn", vp),
-                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp)]
+                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp), ("blocks", vp), ("n_blocks", i32)]
 
 
 class StackPassArgs(C.Structure):
@@ -95,7 +101,7 @@ class TapGemmArgs(C.Structure):
 
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
-SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode",
+SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
            "q3t_window_attn", "q3t_snake", "q3t_clamp_pcm16"]
 

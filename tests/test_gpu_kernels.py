@@ -263,6 +263,64 @@ def test_attn_decode(cuda, pos, nsplit):
         assert torch.equal(pool_h[pg, 1, :, pos % 16].float(), v_new)
 
 
+@pytest.mark.parametrize("lens", [(1,), (33, 7, 64), (300, 17), (129, 32, 31, 65)])
+def test_attn_prefill_ragged_causal(cuda, lens):
+    """Tensor-core prompt attention (csrc/attn_prefill.cu): ragged rows of several sequences, scattered pages, blocks of <= 32
+    rows.  Reference: fp32 softmax attention over the bf16 K/V that are in the cache; q is rounded to bf16 by the kernel, so
+    the tolerance is the bf16 one of BASELINE.json (1e-2 relative), measured per row."""
+    lib = L.load()
+    H, Hkv, D, theta, eps = 4, 2, 128, 1e6, 1e-6
+    g = torch.Generator().manual_seed(sum(lens))
+    nseq, M = len(lens), sum(lens)
+    max_pages = (max(lens) + 15) // 16 + 1
+    n_pages = nseq * max_pages
+    perm = torch.randperm(n_pages, generator=g).int().reshape(nseq, max_pages)
+    qkv = torch.randn(M, (H + 2 * Hkv) * D, generator=g)
+    qn = 1 + 0.1 * torch.randn(D, generator=g)
+    kn = 1 + 0.1 * torch.randn(D, generator=g)
+    inv = 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+    pos = torch.cat([torch.arange(l, dtype=torch.int32) for l in lens])
+    seq = torch.cat([torch.full((l,), i, dtype=torch.int32) for i, l in enumerate(lens)])
+    blocks, r0 = [], 0
+    for l in lens:
+        blocks += [(r0 + o, min(32, l - o)) for o in range(0, l, 32)]
+        r0 += l
+    d = lambda t: t.to(cuda).contiguous()
+    pool_d = torch.zeros(n_pages, 2, Hkv, 16, D, dtype=torch.bfloat16, device=cuda)
+    perm_d, qkv_d, qn_d, kn_d, inv_d, pos_d, seq_d = map(d, (perm, qkv, qn, kn, inv, pos, seq))
+    blk_d = torch.tensor(blocks, dtype=torch.int32, device=cuda)
+    # pass 1 with the decode kernel: K/V (normed, rotated, bf16) of every row into the cache
+    a = L.AttnArgs()
+    a.qkv, a.q_norm_w, a.k_norm_w, a.eps, a.inv_freq = qkv_d.data_ptr(), qn_d.data_ptr(), kn_d.data_ptr(), eps, inv_d.data_ptr()
+    a.kv_pool, a.block_tbl, a.max_pages, a.pos = pool_d.data_ptr(), perm_d.data_ptr(), max_pages, pos_d.data_ptr()
+    out1 = torch.zeros(M, H * D, device=cuda)
+    work = torch.zeros(M * Hkv * (H // Hkv) * (D + 2), device=cuda)
+    cnt = torch.zeros(M * Hkv, dtype=torch.int32, device=cuda)
+    a.out, a.work, a.counters = out1.data_ptr(), work.data_ptr(), cnt.data_ptr()
+    a.B, a.H, a.Hkv, a.D, a.nsplit, a.mode, a.seq_of_row = M, H, Hkv, D, 1, 1, seq_d.data_ptr()
+    L.check(lib.q3t_attn_decode(C.byref(a), L.stream_ptr()), "attn pass 1")
+    # reference: the per-row decode kernel in attention-only mode (fp32 q) ...
+    a.mode = 2
+    L.check(lib.q3t_attn_decode(C.byref(a), L.stream_ptr()), "attn pass 2 (per row)")
+    # ... against the tensor-core kernel, fp32 and bf16 outputs
+    u = L.AttnPrefillArgs()
+    u.qkv, u.q_norm_w, u.eps, u.inv_freq = qkv_d.data_ptr(), qn_d.data_ptr(), eps, inv_d.data_ptr()
+    u.kv_pool, u.block_tbl, u.max_pages = pool_d.data_ptr(), perm_d.data_ptr(), max_pages
+    u.pos, u.seq_of_row, u.blocks, u.n_blocks = pos_d.data_ptr(), seq_d.data_ptr(), blk_d.data_ptr(), len(blocks)
+    out2 = torch.full((M, H * D), float("nan"), device=cuda)
+    u.out, u.H, u.Hkv, u.D = out2.data_ptr(), H, Hkv, D
+    L.check(lib.q3t_attn_prefill(C.byref(u), L.stream_ptr()), "attn_prefill")
+    out3 = torch.zeros(M, H * D, device=cuda, dtype=torch.bfloat16)
+    u.out, u.out_bf16 = 0, out3.data_ptr()
+    L.check(lib.q3t_attn_prefill(C.byref(u), L.stream_ptr()), "attn_prefill bf16")
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out2).all())
+    ref = out1.cpu().double()
+    err = (out2.cpu().double() - ref).abs().amax(1) / ref.abs().amax(1)
+    assert float(err.max()) < 1e-2, f"worst row {int(err.argmax())}: rel err {float(err.max()):.3e}"
+    assert torch.equal(out3.float(), out2.bfloat16().float())
+
+
 def _sample(lib, cuda, logits, sp, seen=None, step=0, uniforms=None):
     B, V = logits.shape
     lg = logits.to(cuda).contiguous()

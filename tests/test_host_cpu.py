@@ -82,14 +82,15 @@ def test_library_exports_every_declared_symbol():
     probe = r'''
     #include "q3tts_b200.h"
     #include <stdio.h>
-    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(q3t_w8), sizeof(q3t_gemv_args), sizeof(q3t_attn_args),
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(q3t_w8), sizeof(q3t_gemv_args), sizeof(q3t_attn_args),
         sizeof(q3t_sampling), sizeof(q3t_sample_args), sizeof(q3t_layer), sizeof(q3t_stack), sizeof(q3t_frame_args),
-        sizeof(q3t_tapgemm_args)); return 0; }'''
+        sizeof(q3t_tapgemm_args), sizeof(q3t_gemm_args), sizeof(q3t_attn_prefill_args), sizeof(q3t_prefill_args)); return 0; }'''
     src, exe = "/tmp/q3t_probe.c", "/tmp/q3t_probe"
     open(src, "w").write(probe)
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
     sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
-    mirrors = [L.W8, L.GemvArgs, L.AttnArgs, L.Sampling, L.SampleArgs, L.Layer, L.Stack, L.FrameArgs, L.TapGemmArgs]
+    mirrors = [L.W8, L.GemvArgs, L.AttnArgs, L.Sampling, L.SampleArgs, L.Layer, L.Stack, L.FrameArgs, L.TapGemmArgs,
+               L.GemmArgs, L.AttnPrefillArgs, L.PrefillArgs]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
 
 
