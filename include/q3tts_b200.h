@@ -284,6 +284,8 @@ typedef struct {
     float* qkv; float* attn; float* gu; void* xb;
     float* attn_work; int* attn_counters;    /* >= M*Hkv*(H/Hkv)*(D+2) floats, M*Hkv ints (zeroed) */
     const int* blocks; int n_blocks;         /* optional row blocks for q3t_attn_prefill (see there); 0 = per-row decode kernel */
+    void* xb2;                               /* optional second bf16 scratch [M, max(H*D, inter)]: attention output and SwiGLU
+                                                activations stay bf16 between kernels (needs `blocks`) */
 } q3t_prefill_args;
 int q3t_talker_prefill(const q3t_prefill_args* a, void* stream);
 /* final RMSNorm of `x` [B, H] -> `hidden`, codec head -> `logits` (the tail of a talker step) */

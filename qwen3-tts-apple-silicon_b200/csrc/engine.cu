@@ -243,7 +243,15 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
             u.qkv = a->qkv; u.q_norm_w = L.q_norm; u.eps = st.eps; u.inv_freq = st.inv_freq; u.kv_pool = t.kv_pool;
             u.block_tbl = st.block_tbl; u.max_pages = st.max_pages; u.pos = a->pos; u.seq_of_row = a->seq_of_row;
             u.blocks = a->blocks; u.n_blocks = a->n_blocks; u.out = a->attn; u.H = st.n_heads; u.Hkv = st.n_kv_heads; u.D = st.head_dim;
+            const bool chain = a->xb2 && M > 2 && L.o.N % 128 == 0 && L.gate_up.N % 128 == 0 && L.down.N % 128 == 0;
+            if (chain) { u.out = nullptr; u.out_bf16 = a->xb2; }
             Q3T_TRY(launch_attn_prefill(&u, s));
+            if (chain) {          // attention output and SwiGLU activations go on as bf16 rows (as in the decode frames)
+                Q3T_TRY(gemm_bf16(L.o, M, a->xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, a->x, hid, a->x, hid, nullptr, s));
+                Q3T_TRY(gemm_bf16(L.gate_up, M, nullptr, Q3T_PRO_RMSNORM, a->x, hid, L.post_norm, st.eps, 1, nullptr, 0, nullptr, 0, a->xb2, s));
+                Q3T_TRY(gemm_bf16(L.down, M, a->xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, a->x, hid, a->x, hid, nullptr, s));
+                continue;
+            }
         } else {
             t.mode = 2;                              // pass 2: causal attention of every row over its prefix
             Q3T_TRY(launch_attn_decode(&t, s));

@@ -362,8 +362,11 @@ class TalkerEngine:
             blocks += [(r0 + o, min(32, l - o)) for o in range(0, l, 32)]
             r0 += l
         blk = torch.tensor(blocks, dtype=torch.int32, device=dev).contiguous()
+        xb2 = torch.empty(M * max(t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)
         if not os.environ.get("Q3T_PREFILL_ATTN_PER_ROW"):
             a.blocks, a.n_blocks = blk.data_ptr(), len(blocks)
+            if not os.environ.get("Q3T_NO_BF16_CHAIN"):
+                a.xb2 = xb2.data_ptr()
         L.check(self.lib.q3t_talker_prefill(C.byref(a), L.stream_ptr()), "talker_prefill")
         last = torch.tensor([sum(lengths[:b + 1]) - 1 for b in range(B)], device=dev)
         self.x.copy_(rows[last])

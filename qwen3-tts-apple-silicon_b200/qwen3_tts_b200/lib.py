@@ -86,7 +86,7 @@ class FrameArgs(C.Structure):
 
 class PrefillArgs(C.Structure):
     _fields_ = [("f", C.POINTER(FrameArgs)), ("M", i32), ("x", vp), ("pos", vp), ("seq_of_row", vp), ("qkv", vp), ("attn", vp),
-                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp), ("blocks", vp), ("n_blocks", i32)]
+                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp), ("blocks", vp), ("n_blocks", i32), ("xb2", vp)]
 
 
 class StackPassArgs(C.Structure):
