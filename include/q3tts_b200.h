@@ -339,6 +339,11 @@ int q3t_window_attn(float* qkv, const float* inv_freq, int B, int T, int H, int 
 /* elementwise SnakeBeta on [rows, C]: a = exp(alpha), b = 1/(exp(beta)+1e-9) precomputed per channel */
 int q3t_snake(const float* x, const float* a, const float* b, long long rows, int C, float* y, void* stream);
 
+/* output convolution of the vocoder (mx.conv1d C -> 1, causal, dilation 1) fused with clamp(-1, 1):
+ * act [B, T, C] fp32 time-major, W [taps, C] (tap j reads row t - (taps-1-j)), bias [1] or NULL -> wav [B, T] */
+int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                       void* stream);
+
 /* final: clamp(x, -1, 1) and optional PCM16 conversion */
 int q3t_clamp_pcm16(const float* x, long long n, float* y, int16_t* pcm, void* stream);
 

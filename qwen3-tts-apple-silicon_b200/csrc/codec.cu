@@ -227,6 +227,41 @@ __global__ void clamp_pcm_kernel(const float* __restrict__ x, long long n, float
     if (pcm) pcm[i] = (int16_t)__float2int_rn(v * 32767.f);
 }
 
+// ---- output convolution of the vocoder: causal conv1d C -> 1 (k taps, dilation 1) + clamp(-1, 1) --------------------------
+// 672 MACs per sample against 384 bytes of input per time step: HBM-bound, not GEMM-shaped (one output channel).  A CTA
+// stages CO_TT + taps - 1 activation rows in shared memory (row stride C + 1 words: thread t reads row t + j, so the 32 lanes
+// of a warp hit 32 different banks) and every thread produces one sample; the weights are broadcast reads.
+constexpr int CO_TT = 256;
+
+__global__ void __launch_bounds__(CO_TT) conv_out_clamp_kernel(const float* __restrict__ act, int T, int C, const float* __restrict__ W,
+                                                                const float* __restrict__ bias, int taps, float* __restrict__ wav) {
+    extern __shared__ float co_s[];
+    const int ld = C + 1, nrow = CO_TT + taps - 1;
+    float* w_s = co_s + (size_t)nrow * ld;
+    const int b = blockIdx.y, t0 = blockIdx.x * CO_TT, tid = threadIdx.x;
+    const float* src = act + (size_t)b * T * C;
+    const int c4n = C >> 2;
+    for (int i = tid; i < nrow * c4n; i += CO_TT) {
+        const int r = i / c4n, c4 = i - r * c4n, t = t0 - (taps - 1) + r;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                    // rows before 0 are the causal left padding
+        if (t >= 0 && t < T) v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)t * C) + c4);
+        float* d = co_s + (size_t)r * ld + 4 * c4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    for (int i = tid; i < taps * C; i += CO_TT) w_s[i] = W[i];
+    __syncthreads();
+    const int t = t0 + tid;
+    if (t >= T) return;
+    float acc0 = bias ? bias[0] : 0.f, acc1 = 0.f;
+    for (int j = 0; j < taps; ++j) {
+        const float* a = co_s + (size_t)(tid + j) * ld;
+        const float* w = w_s + j * C;
+#pragma unroll 8
+        for (int c = 0; c < C; c += 2) { acc0 = fmaf(a[c], w[c], acc0); acc1 = fmaf(a[c + 1], w[c + 1], acc1); }
+    }
+    wav[(size_t)b * T + t] = fminf(1.f, fmaxf(-1.f, acc0 + acc1));
+}
+
 }  // namespace q3t
 
 using namespace q3t;
@@ -300,6 +335,23 @@ extern "C" int q3t_snake(const float* x, const float* a, const float* b, long lo
     if (n == 0) return 0;
     snake_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, a, b, n, C, y);
     Q3T_CHECK_LAUNCH("snake");
+    return 0;
+}
+
+extern "C" int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                                  void* stream) {
+    Q3T_REQUIRE(C % 4 == 0 && taps >= 1 && taps <= 16, "conv_out_clamp: C % 4, 1 <= taps <= 16");
+    if ((long long)B * T == 0) return 0;
+    const size_t smem = ((size_t)(CO_TT + taps - 1) * (C + 1) + (size_t)taps * C) * sizeof(float);
+    Q3T_REQUIRE(smem <= 227 * 1024, "conv_out_clamp: too many channels for one CTA");
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(conv_out_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set = smem;
+    }
+    conv_out_clamp_kernel<<<dim3((unsigned)((T + CO_TT - 1) / CO_TT), (unsigned)B), CO_TT, smem, (cudaStream_t)stream>>>(
+        act, T, C, W, bias, taps, wav);
+    Q3T_CHECK_LAUNCH("conv_out_clamp");
     return 0;
 }
 

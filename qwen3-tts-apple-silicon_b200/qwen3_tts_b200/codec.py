@@ -105,6 +105,7 @@ class CodecDecoder:
             self.blocks.append(dict(snake=snake(p + ".snake"), tconv=tconv(p + ".tconv", r), units=units))
         self.snake_out = snake("codec.dec.snake_out")
         self.conv_out = conv("codec.dec.conv_out")
+        self.conv_out_w = w["codec.dec.conv_out.weight"][0].t().contiguous()      # [taps, C] unrounded fp32 (FP32-pipe kernel)
 
     # ---- operator wrappers ---------------------------------------------------------------------------------
     def _tap(self, layer: _Tap, A: torch.Tensor, scale=None, resid=None, want_raw=True, act=L.ACT_NONE, act_ab=None):
@@ -204,8 +205,15 @@ class CodecDecoder:
                 u = u2
             if stages is not None:
                 stages[f"block{bi}"] = u
-        wav, _ = self._tap(self.conv_out, act)                              # [B, n, 1]
-        out = torch.empty(wav.shape[0], wav.shape[1], device=self.dev, dtype=torch.float32)
+        co = self.conv_out
+        Bn, Tn, Cn = act.shape
+        out = torch.empty(Bn, Tn, device=self.dev, dtype=torch.float32)
+        if co.cout == 1 and Cn % 4 == 0 and co.shifts == [-(co.taps - 1 - j) for j in range(co.taps)]:
+            # one output channel is not GEMM-shaped: dedicated HBM-bound kernel, clamp fused
+            L.check(self.lib.q3t_conv_out_clamp(act.data_ptr(), Bn, Tn, Cn, self.conv_out_w.data_ptr(), L.ptr(co.bias), co.taps,
+                                                out.data_ptr(), L.stream_ptr()), "conv_out_clamp")
+            return out
+        wav, _ = self._tap(co, act)                                         # [B, n, 1]
         L.check(self.lib.q3t_clamp_pcm16(wav.data_ptr(), wav.numel(), out.data_ptr(), 0, L.stream_ptr()), "clamp")
         return out
 

@@ -103,7 +103,7 @@ class TapGemmArgs(C.Structure):
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
-           "q3t_window_attn", "q3t_snake", "q3t_clamp_pcm16"]
+           "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_clamp_pcm16"]
 
 _lib = None
 
@@ -127,6 +127,7 @@ def load() -> C.CDLL:
     lib.q3t_w8_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.q3t_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     lib.q3t_attn_decode.argtypes = [C.POINTER(AttnArgs), vp]
+    lib.q3t_attn_prefill.argtypes = [C.POINTER(AttnPrefillArgs), vp]
     lib.q3t_sample.argtypes = [C.POINTER(SampleArgs), vp]
     lib.q3t_stack_pass.argtypes = [C.POINTER(StackPassArgs), vp]
     lib.q3t_ll_work_bytes.argtypes = [C.POINTER(Stack), C.POINTER(Stack), i32]
@@ -140,6 +141,7 @@ def load() -> C.CDLL:
     lib.q3t_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]
     lib.q3t_window_attn.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.q3t_snake.argtypes = [vp, vp, vp, i64, i32, vp, vp]
+    lib.q3t_conv_out_clamp.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp]
     lib.q3t_clamp_pcm16.argtypes = [vp, i64, vp, vp, vp]
     if lib.q3t_abi_version() != 1:
         raise Q3TError("libq3tts_b200.so ABI version mismatch")

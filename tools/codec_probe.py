@@ -15,4 +15,4 @@ wav = dec.decode(codes); torch.cuda.synchronize()
 s, f = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record(); wav = dec.decode(codes); f.record(); torch.cuda.synchronize()
 ms = s.elapsed_time(f)
-print(f"codec B={B} T={T}: {ms:.1f} ms -> {B * T * 4.96e-3 / ms:.1f} TFLOP/s, RTFx {B * T * 0.08 / (ms / 1e3):.0f}, wav {tuple(wav.shape)}")
+print(f"codec B={B} T={T}: {ms:.1f} ms -> {B * T * 4.96 / ms:.1f} TFLOP/s, RTFx {B * T * 0.08 / (ms / 1e3):.0f}, wav {tuple(wav.shape)}")
