@@ -321,6 +321,24 @@ def test_attn_prefill_ragged_causal(cuda, lens):
     assert torch.equal(out3.float(), out2.bfloat16().float())
 
 
+@pytest.mark.parametrize("B,T,C,taps", [(1, 1, 96, 7), (2, 255, 96, 7), (3, 1000, 96, 7), (1, 513, 32, 3)])
+def test_conv_out_clamp_matches_causal_conv1d(cuda, B, T, C, taps):
+    """Output convolution of the vocoder (C -> 1, causal) + clamp against torch conv1d on the left-padded signal."""
+    lib = L.load()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    act = torch.randn(B, T, C, generator=g)
+    w = torch.randn(1, C, taps, generator=g) * 0.2           # nn.Conv1d layout [Cout, Cin, k]
+    bias = torch.randn(1, generator=g) * 0.1
+    ref = torch.nn.functional.conv1d(torch.nn.functional.pad(act.transpose(1, 2).double(), (taps - 1, 0)), w.double(), bias.double())[:, 0]
+    ref = ref.clamp(-1, 1)
+    act_d, w_d, b_d = act.to(cuda), w[0].t().contiguous().to(cuda), bias.to(cuda)
+    out = torch.full((B, T), float("nan"), device=cuda)
+    L.check(lib.q3t_conv_out_clamp(act_d.data_ptr(), B, T, C, w_d.data_ptr(), b_d.data_ptr(), taps, out.data_ptr(), L.stream_ptr()), "conv_out")
+    torch.cuda.synchronize()
+    assert float((out.cpu().double() - ref).abs().max()) < 2e-5
+    assert float(out.max()) <= 1.0 and float(out.min()) >= -1.0 and bool((ref.abs() == 1).any()) == bool((out.abs() == 1).any())
+
+
 def _sample(lib, cuda, logits, sp, seen=None, step=0, uniforms=None):
     B, V = logits.shape
     lg = logits.to(cuda).contiguous()
