@@ -138,13 +138,16 @@ int q3t_attn_decode(const q3t_attn_args* a, void* stream);
  * (q3t_attn_decode mode 1).  Rows are ragged: row m is position pos[m] of sequence seq_of_row[m]; `blocks` [n_blocks, 2]
  * = (first row, row count <= 32) lists runs of consecutive rows of ONE sequence (one CTA per block and kv head).
  * Built for D = 128 and H = 2 * Hkv.  Writes out [M, H*D] fp32, or out_bf16 [M, H*D] when given.
+ * k_norm_w != NULL (with M = number of rows): pass 1 runs first in the same call - K (RMSNorm + RoPE) and V of every row
+ * are written to the cache, bit-identical to q3t_attn_decode mode 1.
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
     const float* qkv;  const float* q_norm_w;  float eps;  const float* inv_freq;
-    const void* kv_pool;  const int* block_tbl;  int max_pages;
+    void* kv_pool;  const int* block_tbl;  int max_pages;
     const int* pos;  const int* seq_of_row;  const int* blocks;  int n_blocks;
     float* out;  void* out_bf16;
     int H, Hkv, D;
+    const float* k_norm_w;  int M;
 } q3t_attn_prefill_args;
 
 int q3t_attn_prefill(const q3t_attn_prefill_args* a, void* stream);

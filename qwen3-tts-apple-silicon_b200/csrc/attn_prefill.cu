@@ -225,6 +225,52 @@ __global__ void __launch_bounds__(PF_THREADS) attn_prefill_kernel(const PrefillA
     }
 }
 
+// ---- pass 1: K (RMSNorm + RoPE) and V of every prompt row -> bf16 rows of the paged cache.  One warp per (row, kv head),
+// four dims per lane; the arithmetic (and therefore every stored bit) is the decode kernel's (attn_decode.cu, stage 1).
+__global__ void __launch_bounds__(128) kv_write_kernel(const float* __restrict__ qkv, const float* __restrict__ k_norm_w, float eps,
+                                                       const float* __restrict__ inv_freq, __nv_bfloat16* kv_pool,
+                                                       const int* __restrict__ block_tbl, int max_pages, const int* __restrict__ pos,
+                                                       const int* __restrict__ seq_of_row, int M, int H, int Hkv) {
+    constexpr int D = PF_D, E = 4;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31, m = blockIdx.x * 4 + (threadIdx.x >> 5), kvh = blockIdx.y;
+    if (m >= M) return;
+    const int p = pos[m];
+    const float* row = qkv + (size_t)m * (H + 2 * Hkv) * D;
+    const size_t page_elems = (size_t)2 * Hkv * Q3T_KV_PAGE * D;
+    __nv_bfloat16* dst = kv_pool + (size_t)block_tbl[(size_t)seq_of_row[m] * max_pages + p / Q3T_KV_PAGE] * page_elems +
+                         (size_t)kvh * Q3T_KV_PAGE * D + (size_t)(p % Q3T_KV_PAGE) * D + lane * E;
+    {   // k
+        const float* src = row + (size_t)(H + kvh) * D;
+        float x[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = src[lane * E + e];
+        float ss = 0.f;
+#pragma unroll
+        for (int e = 0; e < E; ++e) ss += x[e] * x[e];
+        ss = warp_sum(ss);
+        const float rstd = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+        for (int e = 0; e < E; ++e) x[e] = k_norm_w[lane * E + e] * (x[e] * rstd);
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            const float other = __shfl_xor_sync(0xffffffffu, x[e], 16);
+            float sn, cs;
+            sincosf((float)p * inv_freq[(lane & 15) * E + e], &sn, &cs);
+            x[e] = (lane < 16) ? (x[e] * cs - other * sn) : (x[e] * cs + other * sn);
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) dst[e] = __float2bfloat16_rn(x[e]);
+    }
+    {   // v
+        const float* src = row + (size_t)(H + Hkv + kvh) * D;
+        __nv_bfloat16* dv = dst + (size_t)Hkv * Q3T_KV_PAGE * D;
+#pragma unroll
+        for (int e = 0; e < E; ++e) dv[e] = __float2bfloat16_rn(src[lane * E + e]);
+    }
+}
+
 int launch_attn_prefill(const q3t_attn_prefill_args* a, cudaStream_t stream) {
     Q3T_REQUIRE(a->D == PF_D && a->H == 2 * a->Hkv, "attn_prefill: built for head_dim 128 and two query heads per kv head");
     Q3T_REQUIRE(a->n_blocks >= 1 && a->blocks && a->pos && a->seq_of_row && a->qkv && (a->out || a->out_bf16), "attn_prefill: arguments");
@@ -234,6 +280,12 @@ int launch_attn_prefill(const q3t_attn_prefill_args* a, cudaStream_t stream) {
     p.kv_pool = (const __nv_bfloat16*)a->kv_pool; p.block_tbl = a->block_tbl; p.max_pages = a->max_pages;
     p.pos = a->pos; p.seq_of_row = a->seq_of_row; p.blocks = a->blocks; p.out = a->out; p.out_bf16 = (__nv_bfloat16*)a->out_bf16;
     p.H = a->H; p.Hkv = a->Hkv;
+    if (a->k_norm_w) {     // pass 1 (optional): every row's K/V into the cache before any row attends
+        Q3T_REQUIRE(a->M >= 1, "attn_prefill: M rows for the K/V write");
+        launch_pdl(kv_write_kernel, dim3((a->M + 3) / 4, a->Hkv), dim3(128), 0, stream, a->qkv, a->k_norm_w, a->eps, a->inv_freq,
+                   (__nv_bfloat16*)a->kv_pool, a->block_tbl, a->max_pages, a->pos, a->seq_of_row, a->M, a->H, a->Hkv);
+        Q3T_CHECK_LAUNCH("kv_write");
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(attn_prefill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PF_SMEM);

@@ -234,15 +234,18 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
         t.block_tbl = st.block_tbl; t.max_pages = st.max_pages; t.pos = a->pos; t.out = a->attn; t.work = a->attn_work;
         t.counters = a->attn_counters; t.B = M; t.H = st.n_heads; t.Hkv = st.n_kv_heads; t.D = st.head_dim;
         t.seq_of_row = a->seq_of_row;
+        const bool tc_attn = a->blocks && a->n_blocks > 0 && st.head_dim == 128 && st.n_heads == 2 * st.n_kv_heads;
         t.nsplit = 1; t.mode = 1;                    // pass 1: K/V rows of every prompt token into the cache
-        Q3T_TRY(launch_attn_decode(&t, s));
-        if (a->blocks && a->n_blocks > 0 && st.head_dim == 128 && st.n_heads == 2 * st.n_kv_heads) {
-            // pass 2 on the tensor cores: 32 rows of a sequence share every K/V tile (csrc/attn_prefill.cu)
+        if (!tc_attn) Q3T_TRY(launch_attn_decode(&t, s));
+        if (tc_attn) {
+            // both passes in csrc/attn_prefill.cu: K/V write, then attention on the tensor cores (32 rows of a sequence share
+            // every K/V tile)
             q3t_attn_prefill_args u;
             memset(&u, 0, sizeof(u));
             u.qkv = a->qkv; u.q_norm_w = L.q_norm; u.eps = st.eps; u.inv_freq = st.inv_freq; u.kv_pool = t.kv_pool;
             u.block_tbl = st.block_tbl; u.max_pages = st.max_pages; u.pos = a->pos; u.seq_of_row = a->seq_of_row;
             u.blocks = a->blocks; u.n_blocks = a->n_blocks; u.out = a->attn; u.H = st.n_heads; u.Hkv = st.n_kv_heads; u.D = st.head_dim;
+            u.k_norm_w = L.k_norm; u.M = M;
             const bool chain = a->xb2 && M > 2 && L.o.N % 128 == 0 && L.gate_up.N % 128 == 0 && L.down.N % 128 == 0;
             if (chain) { u.out = nullptr; u.out_bf16 = a->xb2; }
             Q3T_TRY(launch_attn_prefill(&u, s));

@@ -45,7 +45,7 @@ class AttnArgs(C.Structure):
 class AttnPrefillArgs(C.Structure):
     _fields_ = [("qkv", vp), ("q_norm_w", vp), ("eps", f32), ("inv_freq", vp), ("kv_pool", vp), ("block_tbl", vp),
                 ("max_pages", i32), ("pos", vp), ("seq_of_row", vp), ("blocks", vp), ("n_blocks", i32), ("out", vp),
-                ("out_bf16", vp), ("H", i32), ("Hkv", i32), ("D", i32)]
+                ("out_bf16", vp), ("H", i32), ("Hkv", i32), ("D", i32), ("k_norm_w", vp), ("M", i32)]
 
 
 class Sampling(C.Structure):

@@ -319,6 +319,13 @@ def test_attn_prefill_ragged_causal(cuda, lens):
     err = (out2.cpu().double() - ref).abs().amax(1) / ref.abs().amax(1)
     assert float(err.max()) < 1e-2, f"worst row {int(err.argmax())}: rel err {float(err.max()):.3e}"
     assert torch.equal(out3.float(), out2.bfloat16().float())
+    # pass 1 folded into the same call (k_norm_w given): the cache must come out bit-identical to the decode kernel's mode 1
+    pool2 = torch.zeros_like(pool_d)
+    out4 = torch.full((M, H * D), float("nan"), device=cuda)
+    u.kv_pool, u.out, u.out_bf16, u.k_norm_w, u.M = pool2.data_ptr(), out4.data_ptr(), 0, kn_d.data_ptr(), M
+    L.check(lib.q3t_attn_prefill(C.byref(u), L.stream_ptr()), "attn_prefill with K/V write")
+    torch.cuda.synchronize()
+    assert torch.equal(pool2, pool_d) and torch.equal(out4, out2)
 
 
 @pytest.mark.parametrize("B,T,C,taps", [(1, 1, 96, 7), (2, 255, 96, 7), (3, 1000, 96, 7), (1, 513, 32, 3)])
