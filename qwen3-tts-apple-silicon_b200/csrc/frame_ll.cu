@@ -67,7 +67,7 @@ struct LLParams {
     int mode;
     LLStack talker, cp;
     // exchange buffers (64-bit {value, tag} words)
-    u64 *x_qkv, *x_attn, *x_o, *x_act, *x_down, *x_head, *x_proj;
+    u64 *x_qkv, *x_attn, *x_attnf, *x_o, *x_act, *x_down, *x_head, *x_proj;   // x_attnf: merged, normalised head outputs
     unsigned int* state;                         // [0] tag base (persists across launches), [1] error code
     unsigned long long* timing;                  // optional [grid][LL_NSTAMP]
     int pf_dist;                                 // L2 prefetch distance in tiles ahead of the TMA cursor (0 = off)
@@ -463,54 +463,6 @@ __device__ LL_FN void pro_plain(const float* x, int K) {
     cbar();
 }
 
-// attention partial records of every split -> merged head outputs -> digits  (input of the O projection)
-__device__ LL_FN void pro_attn(CState& st, const u64* ll_attn, uint32_t tag, int q_dim, int nsplit) {
-    const LLParams& p = ll_params();
-    const LLSmem s = ll_smem();
-    const int tid = threadIdx.x, lane = tid & 31, K4 = q_dim >> 2;
-    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) {
-        const int head = (k4 << 2) >> 7, d = (k4 << 2) & 127;
-        const u64* rec0 = ll_attn + (size_t)head * LL_MAXSPLIT * LL_REC;
-        float M = -INFINITY, L = 0.f;
-        float4 A = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int sp0 = 0; sp0 < nsplit; sp0 += 2) {
-            const bool two = sp0 + 1 < nsplit;
-            const u64* r0 = rec0 + (size_t)sp0 * LL_REC;
-            const u64* r1 = r0 + LL_REC;
-            u64 a0[4], a1[4], m0, l0, m1 = 0, l1 = 0;
-            int spins = 0;
-            for (;;) {
-                ll_ld2(r0 + d, a0[0], a0[1]); ll_ld2(r0 + d + 2, a0[2], a0[3]); ll_ld2(r0 + 128, m0, l0);
-                if (two) { ll_ld2(r1 + d, a1[0], a1[1]); ll_ld2(r1 + d + 2, a1[2], a1[3]); ll_ld2(r1 + 128, m1, l1); }
-                bool ok = ll_ok(a0[0], tag) && ll_ok(a0[1], tag) && ll_ok(a0[2], tag) && ll_ok(a0[3], tag) && ll_ok(m0, tag) && ll_ok(l0, tag);
-                if (two) ok = ok && ll_ok(a1[0], tag) && ll_ok(a1[1], tag) && ll_ok(a1[2], tag) && ll_ok(a1[3], tag) && ll_ok(m1, tag) && ll_ok(l1, tag);
-                if (ok) break;
-                if (++spins > LL_SPIN_LIMIT) ll_fail(p.state, 0x300u);
-            }
-            {
-                const float ms = ll_val(m0), Mn = fmaxf(M, ms);
-                const float c = __expf(M - Mn), w = __expf(ms - Mn);
-                L = L * c + ll_val(l0) * w;
-                A.x = A.x * c + ll_val(a0[0]) * w; A.y = A.y * c + ll_val(a0[1]) * w;
-                A.z = A.z * c + ll_val(a0[2]) * w; A.w = A.w * c + ll_val(a0[3]) * w;
-                M = Mn;
-            }
-            if (two) {
-                const float ms = ll_val(m1), Mn = fmaxf(M, ms);
-                const float c = __expf(M - Mn), w = __expf(ms - Mn);
-                L = L * c + ll_val(l1) * w;
-                A.x = A.x * c + ll_val(a1[0]) * w; A.y = A.y * c + ll_val(a1[1]) * w;
-                A.z = A.z * c + ll_val(a1[2]) * w; A.w = A.w * c + ll_val(a1[3]) * w;
-                M = Mn;
-            }
-        }
-        LL_STAMP(ST_F_MERGE);
-        const float il = 1.f / L;
-        emit_digits(s, make_float4(A.x * il, A.y * il, A.z * il, A.w * il), k4, lane);
-    }
-    cbar();
-}
-
 // ---- attention geometry (uniform over the grid) -----------------------------------------------------------------------------
 __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int chunk_min, int split_max, int& chunk, int& nsplit) {
     int maxsplit = grid / n_kv;
@@ -527,7 +479,7 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int c
 // ---- attention phase: q/k RMSNorm + RoPE + KV-page write + split-KV GQA decode attention -> LL records ----------------------
 template <int REP>
 __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
-                                 uint32_t tag_qkv, u64* ll_attn, uint32_t tag_out) {
+                                 uint32_t tag_qkv, u64* ll_attn, u64* ll_attnf, uint32_t tag_out) {
     constexpr int D = 128, EPL = 8, PRE = LL_PRE_N;
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
@@ -691,8 +643,11 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
     // every group must read as zero again (the lower halves are rewritten by the next prologue before anything reads them;
     // the barrier of that prologue orders these stores before the next tile loop)
     for (int i = tid; i < PRE * 32 * 2 * 16 / 2; i += LL_CTHREADS) s.xfrag[(i >> 4) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < REP * D; i += LL_CTHREADS) {
-        const int r = i / D, d = i % D;
+    // 5. this CTA's partial for (head r, dim d): the 16 warps merged out of shared memory
+    const bool mine = tid < REP * D;
+    const int r = tid / D, d = tid % D;
+    float M = -INFINITY, L = 0.f, A = 0.f;
+    if (mine) {
         // 48 independent shared-memory loads, then a max tree and 16 independent exponentials
         float mh[LL_CWARPS], lh[LL_CWARPS], ah[LL_CWARPS];
 #pragma unroll
@@ -700,19 +655,77 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             mh[w] = part_s[(w * REP + r) * LL_REC + D]; lh[w] = part_s[(w * REP + r) * LL_REC + D + 1];
             ah[w] = part_s[(w * REP + r) * LL_REC + d];
         }
-        float M = mh[0];
+        M = mh[0];
 #pragma unroll
         for (int w = 1; w < LL_CWARPS; ++w) M = fmaxf(M, mh[w]);
-        float L = 0.f, A = 0.f;
 #pragma unroll
         for (int w = 0; w < LL_CWARPS; ++w) {
             const float wt = (mh[w] == -INFINITY) ? 0.f : __expf(mh[w] - M);
             L = fmaf(lh[w], wt, L);
             A = fmaf(ah[w], wt, A);
         }
-        u64* rec = ll_attn + ((size_t)(kvh * REP + r) * LL_MAXSPLIT + split) * LL_REC;
-        ll_st(rec + d, A, tag_out);
-        if (d == 0) { ll_st(rec + D, M, tag_out); ll_st(rec + D + 1, L, tag_out); }
+    }
+    u64* fin = ll_attnf + (size_t)(kvh * REP + r) * D + d;
+    if (nsplit == 1) {           // the only split of its kv head: publish the normalised output directly
+        if (mine) ll_st(fin, A * (1.f / L), tag_out);
+        return;
+    }
+    if (split != 0) {            // partial record for the merger (split 0 of the same kv head)
+        if (mine) {
+            u64* rec = ll_attn + ((size_t)(kvh * REP + r) * LL_MAXSPLIT + split) * LL_REC;
+            ll_st(rec + d, A, tag_out);
+            if (d == 0) { ll_st(rec + D, M, tag_out); ll_st(rec + D + 1, L, tag_out); }
+        }
+        return;
+    }
+    // 6. merger: the records of the other splits are requested by all 512 threads at once (one 16-byte load per thread
+    //    covers four splits of two heads -> one L2 round trip at ctx <= 320), parked in the lower halves of the digit
+    //    groups (rewritten by the next prologue before anything reads them; the K/V staging above is dead), merged with
+    //    this CTA's own partial and published as plain normalised words: every consumer of the O projection then needs
+    //    ONE poll of its own float4 instead of nsplit dependent record reads of lines that 148 CTAs hammer at once.
+    //    The groups the O-projection prologue rewrites (q_dim / 64 of them) are skipped: a fast thread of this CTA may
+    //    already be writing its digits while a slow one still reads the parked records.
+    float* tmp = reinterpret_cast<float*>(s.xfrag + (S.n_heads * D / 64) * 32);
+    auto tmp_at = [&](int f) -> float& { return tmp[((f >> 6) << 7) + (f & 63)]; };
+    const int n_items = (nsplit - 1) * REP * 64;
+    for (int it0 = 0; it0 < n_items; it0 += LL_CTHREADS) {
+        const int it = it0 + tid;
+        if (it < n_items) {
+            const int spi = it / (REP * 64), rem = it - spi * (REP * 64), rr = rem >> 6, j = rem & 63;
+            const u64* rec = ll_attn + ((size_t)(kvh * REP + rr) * LL_MAXSPLIT + spi + 1) * LL_REC;
+            const bool ml = (j == 0);
+            u64 a0, a1, m0 = 0, l0 = 0;
+            ll_ld2(rec + 2 * j, a0, a1);
+            if (ml) ll_ld2(rec + D, m0, l0);
+            bool oka = false, okm = !ml;
+            int spins = 0;
+            for (;;) {
+                if (!oka) oka = ll_ok(a0, tag_out) && ll_ok(a1, tag_out);
+                if (!okm) okm = ll_ok(m0, tag_out) && ll_ok(l0, tag_out);
+                if (oka && okm) break;
+                if (++spins > LL_SPIN_LIMIT) ll_fail(p.state, 0x300u);
+                if (!oka) ll_ld2(rec + 2 * j, a0, a1);
+                if (!okm) ll_ld2(rec + D, m0, l0);
+            }
+            const int f0 = (spi * REP + rr) * LL_REC;
+            tmp_at(f0 + 2 * j) = ll_val(a0); tmp_at(f0 + 2 * j + 1) = ll_val(a1);
+            if (ml) { tmp_at(f0 + D) = ll_val(m0); tmp_at(f0 + D + 1) = ll_val(l0); }
+        }
+    }
+    LL_STAMP(ST_F_MERGE);
+    cbar();
+    if (mine) {
+        float Mx = M;
+        for (int sp = 0; sp < nsplit - 1; ++sp) Mx = fmaxf(Mx, tmp_at((sp * REP + r) * LL_REC + D));
+        const float w0 = __expf(M - Mx);
+        float Ls = L * w0, As = A * w0;
+        for (int sp = 0; sp < nsplit - 1; ++sp) {
+            const int f0 = (sp * REP + r) * LL_REC;
+            const float wt = __expf(tmp_at(f0 + D) - Mx);
+            Ls = fmaf(tmp_at(f0 + D + 1), wt, Ls);
+            As = fmaf(tmp_at(f0 + d), wt, As);
+        }
+        ll_st(fin, As * (1.f / Ls), tag_out);
     }
 }
 
@@ -755,11 +768,11 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
         LL_STAMP(ST_QKV);
         // ---- attention (first n_kv*nsplit CTAs)
         const uint32_t t_att = ++st.gen;
-        if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
-        else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, t_att);
+        if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att);
+        else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att);
         LL_STAMP(ST_ATTN);
         // ---- O projection
-        pro_attn(st, p.x_attn, t_att, q_dim, st.nsplit);
+        pro_ll(st, p.x_attnf, t_att, q_dim);
         LL_STAMP(ST_O_PRO);
         const uint32_t t_o = ++st.gen;
         gemv_phase(st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
@@ -1040,6 +1053,11 @@ static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
     Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
     Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
+    {   // parked attention records of the merger CTA must fit the digit groups the O-projection prologue leaves alone
+        const int ms = grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit;
+        Q3T_REQUIRE((LL_MAXK / 64 - st.n_heads * st.head_dim / 64) * 64 >= (ms - 1) * (st.n_heads / st.n_kv_heads) * LL_REC,
+                    "frame_ll: attention merge scratch too small for this many splits");
+    }
     Q3T_REQUIRE(st.max_pages <= 64 * (grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit),
                 "frame_ll: context too long for the per-CTA page-id table");
     const int qkv_n = (st.n_heads + 2 * st.n_kv_heads) * st.head_dim;
@@ -1051,15 +1069,17 @@ static int check_stack(const q3t_stack& st, int grid) {
 }
 
 // exchange-buffer layout inside the caller's workspace (64-bit words)
-struct LLSizes { long long qkv, attn, hid, act; };
+struct LLSizes { long long qkv, attn, qdim, hid, act; };
 static LLSizes ll_sizes(const q3t_stack* t, const q3t_stack* c) {
-    LLSizes z = {0, 0, 0, 0};
+    LLSizes z = {0, 0, 0, 0, 0};
     const q3t_stack* ss[2] = {t, c};
     for (int i = 0; i < 2; ++i) {
         if (!ss[i]) continue;
         const long long q = (long long)(ss[i]->n_heads + 2 * ss[i]->n_kv_heads) * ss[i]->head_dim;
         const long long a = (long long)ss[i]->n_heads * LL_MAXSPLIT * LL_REC;
         z.qkv = q > z.qkv ? q : z.qkv; z.attn = a > z.attn ? a : z.attn;
+        const long long qd = (long long)ss[i]->n_heads * ss[i]->head_dim;
+        z.qdim = qd > z.qdim ? qd : z.qdim;
         z.hid = ss[i]->hidden > z.hid ? ss[i]->hidden : z.hid; z.act = ss[i]->inter > z.act ? ss[i]->inter : z.act;
     }
     return z;
@@ -1067,13 +1087,14 @@ static LLSizes ll_sizes(const q3t_stack* t, const q3t_stack* c) {
 static long long up16(long long v) { return (v + 15) / 16 * 16; }
 static long long ll_words(const q3t_stack* t, const q3t_stack* c, int head_max) {
     const LLSizes z = ll_sizes(t, c);
-    return up16(z.qkv) + up16(z.attn) + 3 * up16(z.hid) + up16(z.act) + up16(head_max) + 64;
+    return up16(z.qkv) + up16(z.attn) + up16(z.qdim) + 3 * up16(z.hid) + up16(z.act) + up16(head_max) + 64;
 }
 static void carve(LLParams& p, void* work, const q3t_stack* t, const q3t_stack* c) {
     const LLSizes z = ll_sizes(t, c);
     u64* w = (u64*)work;
     p.x_qkv = w; w += up16(z.qkv);
     p.x_attn = w; w += up16(z.attn);
+    p.x_attnf = w; w += up16(z.qdim);
     p.x_o = w; w += up16(z.hid);
     p.x_down = w; w += up16(z.hid);
     p.x_proj = w; w += up16(z.hid);
