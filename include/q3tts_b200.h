@@ -220,7 +220,7 @@ typedef struct {
     void* ll_work;          /* exchange buffers, q3t_ll_work_bytes() bytes, zero-initialised once */
     long long ll_work_bytes;
     unsigned int* ll_state; /* [2] zero-initialised once: phase-tag counter (persists across launches), error code */
-    unsigned long long* timing;  /* optional [grid][2048] globaltimer stamps (profiling aid), or NULL */
+    unsigned long long* timing;  /* optional [grid][2048] clock64 stamps; written only by the -DLL_STAMPS profiling build (libq3tts_b200_prof.so), or NULL */
 } q3t_stack_pass_args;
 
 int q3t_stack_pass(const q3t_stack_pass_args* a, void* stream);
@@ -272,7 +272,7 @@ typedef struct {
     int use_mega;
     const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */
     void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
-    unsigned long long* ll_timing;  /* optional profiling stamps, or NULL */
+    unsigned long long* ll_timing;  /* optional profiling stamps (profiling build only), or NULL */
     void* gemm_xb2;        /* optional second bf16 scratch [B, max K]: attention output and SwiGLU activations stay bf16 */
 } q3t_frame_args;
 
@@ -304,7 +304,8 @@ int q3t_frame(const q3t_frame_args* f, void* stream);
  * Activations are time-major fp32 [B, T, C].
  * ------------------------------------------------------------------------------------------- */
 /* bit-exact RVQ gather + left-to-right fp32 sum: codes [B, G, T] int32, tables HOST array of G device
- * ptrs [size, dim]; groups [g_lo, g_hi) summed into out [B, T, dim] */
+ * ptrs [size, dim]; groups [g_lo, g_hi) summed into out [B, T, dim].  A code outside [0, codebook_size) (EOS / control
+ * ids in the frames a finished sequence of a lock-step batch keeps producing) contributes a zero vector. */
 int q3t_rvq_gather_sum(const int* codes, const float* const* tables_host, int B, int G, int T, int g_lo, int g_hi,
                        int dim, int codebook_size, float* out, void* stream);
 

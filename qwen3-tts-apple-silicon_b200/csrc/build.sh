@@ -19,3 +19,13 @@ done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait "$p"; done
 "$NVCC" "${ARCH[@]}" -shared --cudart static -o "$out" "${objs[@]}"
 echo "built $out"
+# profiling build of the persistent kernel (id-coded clock64 stamps compiled in; tools/ll_timing.py loads it through Q3T_LIB)
+if [ "${Q3T_BUILD_PROF:-1}" = "1" ]; then
+  pobj="$here/build/frame_ll_prof.o"
+  if [ ! -f "$pobj" ] || [ "$here/frame_ll.cu" -nt "$pobj" ] || [ "$here/common.cuh" -nt "$pobj" ] || [ "$here/sampler.cuh" -nt "$pobj" ]; then
+    "$NVCC" "${FLAGS[@]}" -DLL_STAMPS -c "$here/frame_ll.cu" -o "$pobj"
+  fi
+  pobjs=(); for o in "${objs[@]}"; do [ "$o" = "$here/build/frame_ll.o" ] && pobjs+=("$pobj") || pobjs+=("$o"); done
+  "$NVCC" "${ARCH[@]}" -shared --cudart static -o "$here/../qwen3_tts_b200/libq3tts_b200_prof.so" "${pobjs[@]}"
+  echo "built libq3tts_b200_prof.so"
+fi

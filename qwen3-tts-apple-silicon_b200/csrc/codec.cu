@@ -17,14 +17,16 @@ namespace q3t {
 // ---------------------------------------------------------------------------------- RVQ gather + sum
 struct RvqTables { const float* t[32]; };
 
+// A code outside [0, codebook_size) - the talker's EOS / control ids in the rows a finished sequence keeps producing in a
+// lock-step batch - contributes a zero vector instead of reading past the table (the caller trims those frames).
 __global__ void __launch_bounds__(128) rvq_gather_sum_kernel(const int* __restrict__ codes, RvqTables tabs, int G, int T,
-                                                             int g_lo, int g_hi, int dim, float* __restrict__ out) {
+                                                             int g_lo, int g_hi, int dim, int size, float* __restrict__ out) {
     const int bt = blockIdx.x, b = bt / T, t = bt % T;
     for (int d = threadIdx.x; d < dim; d += blockDim.x) {
         float acc = 0.f;
         for (int g = g_lo; g < g_hi; ++g) {           // left-to-right fp32 sum == the reference order (bit-exact)
             const int c = codes[((size_t)b * G + g) * T + t];
-            const float v = tabs.t[g][(size_t)c * dim + d];
+            const float v = (unsigned)c < (unsigned)size ? tabs.t[g][(size_t)c * dim + d] : 0.f;
             acc = (g == g_lo) ? v : acc + v;
         }
         out[(size_t)bt * dim + d] = acc;
@@ -268,12 +270,11 @@ using namespace q3t;
 
 extern "C" int q3t_rvq_gather_sum(const int* codes, const float* const* tables_host, int B, int G, int T, int g_lo,
                                   int g_hi, int dim, int codebook_size, float* out, void* stream) {
-    (void)codebook_size;
-    Q3T_REQUIRE(G <= 32 && g_lo >= 0 && g_hi <= G && g_lo < g_hi, "rvq_gather_sum: bad group range");
+    Q3T_REQUIRE(G <= 32 && g_lo >= 0 && g_hi <= G && g_lo < g_hi && codebook_size > 0, "rvq_gather_sum: bad group range");
     RvqTables tabs;
     for (int g = 0; g < 32; ++g) tabs.t[g] = g < G ? tables_host[g] : nullptr;
     if (B * T == 0) return 0;
-    rvq_gather_sum_kernel<<<B * T, 128, 0, (cudaStream_t)stream>>>(codes, tabs, G, T, g_lo, g_hi, dim, out);
+    rvq_gather_sum_kernel<<<B * T, 128, 0, (cudaStream_t)stream>>>(codes, tabs, G, T, g_lo, g_hi, dim, codebook_size, out);
     Q3T_CHECK_LAUNCH("rvq_gather_sum");
     return 0;
 }

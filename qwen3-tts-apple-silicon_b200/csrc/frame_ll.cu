@@ -20,8 +20,11 @@
 //   * row tiles (16 output rows x all of K) are dealt to CTAs whole, so every output element has exactly one producer and
 //     epilogues (bias, SwiGLU) run before the value is published; the residual stream is replicated per CTA in shared
 //     memory, so residual adds never touch global memory;
-//   * attention: (kv head, 128-token split) units on the first n_kv*nsplit CTAs; old K/V rows are in registers before
-//     the q/k/v words arrive; partial (m, l, acc) records are LL words merged by every consumer of the O projection.
+//   * attention: (kv head, 64-token split) units on the first n_kv*nsplit CTAs.  The chunk's K/V pages are whole 4 KB
+//     blocks of the paged cache: eight cp.async.bulk copies (one warp instruction) stage them under the QKV contraction;
+//     scores by 8 threads per token, then per warp (head, dim half, token group) softmax + P.V out of shared memory.
+//     Split 0 of every kv head merges the other splits' (m, l, acc) records (one poll round) and publishes normalised
+//     head outputs, so every consumer of the O projection polls ONE float4 instead of nsplit records of hot lines.
 // Re-use of an exchange buffer is safe without extra synchronisation because every phase is an all-to-all dependency:
 // a CTA can only be one phase ahead of the slowest CTA, and each buffer is rewritten five or more phases later.
 #include <stdlib.h>
@@ -46,10 +49,6 @@ constexpr int LL_MAXSPLIT = 16;                  // attention splits per kv head
 constexpr int LL_REC = 130;                      // attention record: 128 acc + m + l
 constexpr int LL_SPIN_LIMIT = 1 << 22;           // watchdog: a poll that spins this long (~1 s) aborts the launch
 constexpr int LL_NSTAMP = 2048;
-#ifndef LL_PRE_N
-#define LL_PRE_N 2
-#endif
-static_assert(LL_PRE_N * 32 * 2 * 16 * 16 <= (LL_MAXK / 64) * 512, "attention K/V staging must fit the digit-plane buffer");
 
 enum { LL_MODE_STACK = 0, LL_MODE_FRAME = 1 };
 enum { EPI_RAW = 0, EPI_SWIGLU = 1 };
@@ -225,6 +224,7 @@ struct LLSmem {
     int* pages;             // [64] KV page ids of this CTA's attention chunk (constant during a pass)
     uint64_t* full;         // [LL_NSLOT]
     uint64_t* empty;        // [LL_NSLOT]
+    uint64_t* kvbar;        // attention K/V staging (cp.async.bulk completion)
 };
 constexpr size_t LL_ATT_FLOATS = 4 * 128 + 16 * 2 * LL_REC;
 constexpr size_t LL_OFF_LAY = 1024;                                      // the first KB holds a copy of LLParams
@@ -243,7 +243,8 @@ constexpr size_t LL_OFF_IBUF = LL_OFF_SN + 64 * 4;
 constexpr size_t LL_OFF_PAGES = LL_OFF_IBUF + 64 * 4;
 constexpr size_t LL_OFF_FULL = LL_OFF_PAGES + 64 * 4;
 constexpr size_t LL_OFF_EMPTY = LL_OFF_FULL + LL_NSLOT * 8;
-constexpr size_t LL_SMEM_BYTES = LL_OFF_EMPTY + LL_NSLOT * 8;
+constexpr size_t LL_OFF_KVBAR = LL_OFF_EMPTY + LL_NSLOT * 8;
+constexpr size_t LL_SMEM_BYTES = LL_OFF_KVBAR + 8;
 static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
 
 __device__ __forceinline__ const LLParams& ll_params() { return *reinterpret_cast<const LLParams*>(ll_smem_raw); }
@@ -266,6 +267,7 @@ __device__ __forceinline__ LLSmem ll_smem() {
     s.pages = reinterpret_cast<int*>(b + LL_OFF_PAGES);
     s.full = reinterpret_cast<uint64_t*>(b + LL_OFF_FULL);
     s.empty = reinterpret_cast<uint64_t*>(b + LL_OFF_EMPTY);
+    s.kvbar = reinterpret_cast<uint64_t*>(b + LL_OFF_KVBAR);
     return s;
 }
 
@@ -276,16 +278,23 @@ struct CState {
     int nsplit;             // attention geometry of the current pass
     int chunk;
     int red_par;            // parity of the double-buffered block-reduction scratch
+    uint32_t kv_par;        // phase parity of the K/V staging barrier
 };
 
 // Profiling stamps (thread 0 of every CTA): {id : 20 bits | clock64 cycles of this SM : 44 bits}.  ids < 32 mark phase ends
 // and are always written when a timing buffer is given; ids >= 32 are sub-phase marks, written when Q3T_LL_FINE=1.
-#define LL_STAMP(id) do { if (p.timing && threadIdx.x == 0 && st.nstamp < LL_NSTAMP && ((id) < 32 || p.fine)) \
+// The production library is built WITHOUT the stamps (even disabled at run time they cost ~5 % of a talker step in
+// registers and branches); csrc/build.sh also builds libq3tts_b200_prof.so with -DLL_STAMPS for tools/ll_timing.py.
+#ifndef LL_STAMPS
+#define LL_STAMP(id) do { } while (0)
+#else
+#define LL_STAMP(id) do { if (p.timing && threadIdx.x == ((p.fine >> 8) << 5) && st.nstamp < LL_NSTAMP && ((id) < 32 || (p.fine & 255))) \
     p.timing[(size_t)blockIdx.x * LL_NSTAMP + st.nstamp++] = ((unsigned long long)(id) << 44) | (gtimer() & ((1ull << 44) - 1)); } while (0)
+#endif
 enum { ST_START = 0, ST_QKV_PRO = 1, ST_QKV = 2, ST_ATTN = 3, ST_O_PRO = 4, ST_O = 5, ST_GU_PRO = 6, ST_GU = 7, ST_DOWN_PRO = 8,
        ST_DOWN = 9, ST_END = 10, ST_SAMPLE = 11, ST_CP_PASS = 12,
        ST_F_POLL = 32, ST_F_TILES = 34, ST_F_GBAR = 35, ST_F_ATT_A = 36, ST_F_ATT_B = 37, ST_F_ATT_C = 38, ST_F_ATT_D = 39,
-       ST_F_ATT_E = 40, ST_F_ATT_F = 41, ST_F_ATT_G = 42, ST_F_MERGE = 43 };
+       ST_F_ATT_E = 40, ST_F_ATT_F = 41, ST_F_ATT_G = 42, ST_F_MERGE = 43, ST_F_DIG = 44 };
 
 // block sum over the 512 consumer threads; `red` is double buffered by `parity`, so one barrier per call is enough
 __device__ __forceinline__ float cblock_sum(float v, float* red, int parity) {
@@ -452,6 +461,7 @@ __device__ LL_FN void pro_ll(CState& st, const u64* ll, uint32_t tag, int K) {
 #pragma unroll
     for (int i = 0; i < NV; ++i)
         if (on[i]) emit_digits(s, v[i], tid + i * LL_CTHREADS, lane);
+    LL_STAMP(ST_F_DIG);
     cbar();
 }
 
@@ -477,10 +487,46 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int c
 }
 
 // ---- attention phase: q/k RMSNorm + RoPE + KV-page write + split-KV GQA decode attention -> LL records ----------------------
+// K/V staging: the rows of this CTA's (kv head, chunk) are whole 4 KB blocks of the paged cache ([page][k|v][head][16][128]
+// bf16), so 64 tokens are eight cp.async.bulk copies issued by ONE thread right after the QKV prologue - they land in digit
+// groups 32..95 (idle until the down projection) while the QKV contraction runs, and nobody computes an address per row.
+constexpr int LL_KV_GROUP0 = 32;                 // first digit group of the staging area (needs q_dim, hidden <= 2048)
+constexpr int LL_KV_ROUND = 64;                  // tokens staged per round (4 pages)
+static_assert((LL_MAXK / 64 - LL_KV_GROUP0) * 512 >= LL_KV_ROUND * 512, "attention K/V staging must fit the idle digit groups");
+
+__device__ __forceinline__ unsigned char* kv_stage(const LLSmem& s) { return reinterpret_cast<unsigned char*>(s.xfrag + LL_KV_GROUP0 * 32); }
+
+// lanes 0..2*npg-1 of ONE warp (all 32 lanes call): pages [pg0, pg0 + npg) of this CTA's chunk -> staging area, one 4 KB
+// block per lane, completion on s.kvbar.  One warp instruction issues all copies; the warp loses ~0.1 us.
+__device__ __forceinline__ void kv_issue(const LLSmem& s, const LLStack& S, int layer, int kvh, int pg0, int npg, int lane) {
+    if (lane >= 2 * npg) return;
+    const int pg = lane >> 1, is_v = lane & 1;
+    const size_t page_elems = (size_t)2 * S.n_kv * Q3T_KV_PAGE * 128;
+    const __nv_bfloat16* src = S.kv_pool + (size_t)layer * S.kv_layer_stride + (size_t)s.pages[pg0 + pg] * page_elems +
+                               (size_t)(is_v * S.n_kv + kvh) * Q3T_KV_PAGE * 128;
+    const uint32_t bar = smem_u32(s.kvbar), dst = smem_u32(kv_stage(s)) + pg * 8192 + is_v * 4096;
+    // generic-proxy writes to the staging area (digits, zeroing) were ordered before this thread by a block barrier
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)npg * 8192u);   // a copy that lands first only drives the tx count negative
+    tma_load_1d(dst, src, 4096, bar);
+}
+
+// called by every consumer thread after the QKV prologue of a layer (round 0 of the attention chunk)
+__device__ __forceinline__ void attn_prefetch(const CState& st, const LLStack& S, int layer, int pos) {
+    const int cta = blockIdx.x;
+    if (cta >= S.n_kv * st.nsplit || (threadIdx.x >> 5) != LL_CWARPS - 1) return;
+    const LLSmem s = ll_smem();
+    const int split = cta / S.n_kv, kvh = cta - split * S.n_kv;
+    const int s0 = split * st.chunk, s1 = min(pos + 1, s0 + st.chunk);
+    const int np = (min(s1 - s0, LL_KV_ROUND) + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE;
+    kv_issue(s, S, layer, kvh, 0, np, threadIdx.x & 31);
+}
+
 template <int REP>
 __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
                                  uint32_t tag_qkv, u64* ll_attn, u64* ll_attnf, uint32_t tag_out) {
-    constexpr int D = 128, EPL = 8, PRE = LL_PRE_N;
+    constexpr int D = 128;
+    constexpr int TG = LL_CWARPS / (2 * REP), TPG = LL_KV_ROUND / TG;   // token groups per round / tokens per group
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int chunk = st.chunk, nsplit = st.nsplit;
@@ -488,44 +534,24 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
     if (cta >= S.n_kv * nsplit) return;
     const int split = cta / S.n_kv, kvh = cta - split * S.n_kv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hw = lane >> 4, sl = lane & 15, hwid = warp * 2 + hw;
-    const int ctx = pos + 1, s0 = split * chunk, s1 = min(ctx, s0 + chunk);
+    const int ctx = pos + 1, s0 = split * chunk, s1 = min(ctx, s0 + chunk), n = s1 - s0;
     const bool owner = (pos >= s0 && pos < s1);
-    float* q_s = s.att;                           // [REP][D], pre-scaled by 1/sqrt(D)
-    float* new_s = s.att + 2 * D;                 // [2][D]: k, v of the new token as stored (bf16-rounded)
-    float* part_s = s.att + 4 * D;                // [16 warps][REP][LL_REC]
-    __nv_bfloat16* pool = S.kv_pool + (size_t)layer * S.kv_layer_stride;
-    const size_t page_elems = (size_t)2 * S.n_kv * Q3T_KV_PAGE * D;
-    const size_t head_off = (size_t)kvh * Q3T_KV_PAGE * D;
-    const size_t v_off = (size_t)S.n_kv * Q3T_KV_PAGE * D;
-    const int n_iter = (s1 - s0 + 31) >> 5;
+    float* q_s = s.att;                           // [REP][2][16][4]: q pre-scaled by 1/sqrt(D), 16-byte chunks of a K row apart
+    float* sc_s = s.att + 2 * D;                  // [REP][64] scores of the round
+    __nv_bfloat16* new_s = reinterpret_cast<__nv_bfloat16*>(s.att + 3 * D);   // [2][D]: k, v of the new token as stored
+    float* part_s = s.att + 4 * D;                // [TG][REP][D] partial outputs, then [TG][REP] partial sums, then [REP] max
+    float* lpart_s = part_s + TG * REP * D;
+    float* m_s = lpart_s + TG * REP;
+    unsigned char* kv_s = kv_stage(s);
+    const int n_rounds = (n + LL_KV_ROUND - 1) / LL_KV_ROUND;
+    const int rd_own = owner ? (pos - s0) / LL_KV_ROUND : -1;
 
-    // 1. everything that does not depend on this step's QKV output is in flight before the words are polled:
-    //    rows already in the cache, the q/k norm weights.  The rows are
-    //    staged with cp.async into the (idle) digit-plane buffer instead of registers: nothing is held live across the poll,
-    //    so nothing spills and the loads really are asynchronous (measured: -4 % per frame, -5 % per talker step at ctx >= 600
-    //    against 16-byte register preloads).  Every thread reads back only what it copied itself.
-    uint4* kv_s = s.xfrag;                         // [PRE][32 half-warps][k|v][16 lanes]
-#pragma unroll
-    for (int i = 0; i < PRE; ++i) {
-        const int tok = s0 + hwid + 32 * i;
-        if (tok < s1 && tok < pos) {
-            const __nv_bfloat16* kp = pool + (size_t)s.pages[(tok - s0) / Q3T_KV_PAGE] * page_elems + head_off +
-                                      (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
-            const uint32_t d0 = smem_u32(kv_s + ((i * 32 + hwid) * 2 + 0) * 16 + sl), d1 = smem_u32(kv_s + ((i * 32 + hwid) * 2 + 1) * 16 + sl);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0), "l"(kp) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d1), "l"(kp + v_off) : "memory");
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    LL_STAMP(ST_F_ATT_A);   // A: preload issued
-    // 2. q heads of this kv head (+ k, v of the new token on the split that owns it)
+    // 1. q heads of this kv head (+ k, v of the new token on the split that owns it)
     if (warp < REP + 2) {
         const bool is_q = warp < REP, is_k = warp == REP;
         if (is_q || owner) {
             float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (is_q || is_k) nw4 = __ldg(reinterpret_cast<const float4*>(is_q ? LD.q_norm : LD.k_norm) + lane);
-            const int page_new = owner ? s.pages[(pos - s0) / Q3T_KV_PAGE] : 0;
             const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
             const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
             LL_STAMP(ST_F_ATT_B);   // B: q words arrived
@@ -546,124 +572,114 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             }
             if (is_q) {
                 const float sc = rsqrtf((float)D);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) q_s[warp * D + lane * 4 + e] = x[e] * sc;
+                // element lane*4+k sits in 16-byte chunk lane>>1 of a K row, half lane&1 of that chunk
+                *reinterpret_cast<float4*>(q_s + warp * D + (((lane & 1) << 4) + (lane >> 1)) * 4) =
+                    make_float4(x[0] * sc, x[1] * sc, x[2] * sc, x[3] * sc);
             } else {
                 __nv_bfloat16 hb[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) { hb[e] = __float2bfloat16_rn(x[e]); new_s[(is_k ? 0 : D) + lane * 4 + e] = __bfloat162float(hb[e]); }
-                __nv_bfloat16* dst = pool + (size_t)page_new * page_elems + head_off + (is_k ? 0 : v_off) +
+                for (int e = 0; e < 4; ++e) hb[e] = __float2bfloat16_rn(x[e]);
+                const size_t page_elems = (size_t)2 * S.n_kv * Q3T_KV_PAGE * D;
+                __nv_bfloat16* dst = S.kv_pool + (size_t)layer * S.kv_layer_stride + (size_t)s.pages[(pos - s0) / Q3T_KV_PAGE] * page_elems +
+                                     (size_t)kvh * Q3T_KV_PAGE * D + (is_k ? 0 : (size_t)S.n_kv * Q3T_KV_PAGE * D) +
                                      (size_t)(pos % Q3T_KV_PAGE) * D + lane * 4;
                 *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(hb);
+                // a later pass of this launch (code predictor) reads the page back with cp.async.bulk: order the store
+                // before the async proxy (the block barriers in between order it before the issuing thread)
+                asm volatile("fence.proxy.async.global;" ::: "memory");
+                *reinterpret_cast<uint2*>(new_s + (is_k ? 0 : D) + lane * 4) = *reinterpret_cast<const uint2*>(hb);
             }
         }
     }
     LL_STAMP(ST_F_ATT_C);   // C: q normalised, rotated, stored
-    cbar();
-    LL_STAMP(ST_F_ATT_D);   // D: barrier
-    // 3. online softmax per half-warp (one token per half-warp per iteration)
-    float m_run[REP], l_run[REP], acc[REP][EPL], qr[REP][EPL];
+    // 2. rounds of 64 staged tokens: scores by 8 threads per token (both heads), then per warp (head, 64-dim half, token
+    //    group): max of the round, probabilities of the group's tokens in lanes, P.V with one shuffle per token
+    const int r_w = warp % REP, dh = (warp / REP) & 1, tg = warp / (2 * REP);
+    float m_run = -INFINITY, l_run = 0.f, acc0 = 0.f, acc1 = 0.f;
+    for (int rd = 0; rd < n_rounds; ++rd) {
+        const int nr = min(n - rd * LL_KV_ROUND, LL_KV_ROUND);          // valid tokens of this round
+        if (rd > 0 && warp == LL_CWARPS - 1) kv_issue(s, S, layer, kvh, rd * (LL_KV_ROUND / Q3T_KV_PAGE), (nr + Q3T_KV_PAGE - 1) / Q3T_KV_PAGE, lane);
+        mbar_wait(smem_u32(s.kvbar), st.kv_par, p.state, 0x600u);
+        st.kv_par ^= 1;
+        if (rd == rd_own && (warp == REP || warp == REP + 1)) {         // the new token's rows replace the stale slot;
+            const int tl = pos - s0 - rd * LL_KV_ROUND, which = warp - REP;  // every lane copies what it stored itself
+            *reinterpret_cast<uint2*>(kv_s + (tl >> 4) * 8192 + which * 4096 + (tl & 15) * 256 + lane * 8) =
+                *reinterpret_cast<const uint2*>(new_s + which * D + lane * 4);
+        }
+        LL_STAMP(ST_F_ATT_A);   // A: staged rows present
+        cbar();
+        LL_STAMP(ST_F_ATT_D);   // D: barrier
+        {
+            const int tok = tid >> 3, o = tid & 7;
+            const unsigned char* krow = kv_s + (tok >> 4) * 8192 + (tok & 15) * 256;
+            float sa[REP];
 #pragma unroll
-    for (int r = 0; r < REP; ++r) {
-        m_run[r] = -INFINITY; l_run[r] = 0.f;
+            for (int r = 0; r < REP; ++r) sa[r] = 0.f;
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) { acc[r][e] = 0.f; qr[r][e] = q_s[r * D + sl * EPL + e]; }
-    }
-    auto step = [&](int tok, uint4 kr, uint4 vr) {
-        const bool has = tok < s1;
-        float k0[EPL], v0[EPL];
-        if (has && tok == pos) {
+            for (int i = 0; i < 2; ++i) {
+                const int c = i * 8 + o;
+                const uint4 kk = *reinterpret_cast<const uint4*>(krow + c * 16);
+                const float k0 = bf16lo(kk.x), k1 = bf16hi(kk.x), k2 = bf16lo(kk.y), k3 = bf16hi(kk.y);
+                const float k4 = bf16lo(kk.z), k5 = bf16hi(kk.z), k6 = bf16lo(kk.w), k7 = bf16hi(kk.w);
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) { k0[e] = new_s[sl * EPL + e]; v0[e] = new_s[D + sl * EPL + e]; }
-        } else {
-            const uint32_t* ku = reinterpret_cast<const uint32_t*>(&kr);
-            const uint32_t* vu = reinterpret_cast<const uint32_t*>(&vr);
+                for (int r = 0; r < REP; ++r) {
+                    const float4 qa = *reinterpret_cast<const float4*>(q_s + r * D + c * 4);
+                    const float4 qb = *reinterpret_cast<const float4*>(q_s + r * D + (16 + c) * 4);
+                    sa[r] = fmaf(qa.x, k0, fmaf(qa.y, k1, fmaf(qa.z, k2, fmaf(qa.w, k3, sa[r]))));
+                    sa[r] = fmaf(qb.x, k4, fmaf(qb.y, k5, fmaf(qb.z, k6, fmaf(qb.w, k7, sa[r]))));
+                }
+            }
 #pragma unroll
-            for (int i = 0; i < EPL / 2; ++i) {
-                k0[2 * i] = bf16lo(ku[i]); k0[2 * i + 1] = bf16hi(ku[i]);
-                v0[2 * i] = bf16lo(vu[i]); v0[2 * i + 1] = bf16hi(vu[i]);
+            for (int r = 0; r < REP; ++r) {
+                sa[r] += __shfl_xor_sync(0xffffffffu, sa[r], 1);
+                sa[r] += __shfl_xor_sync(0xffffffffu, sa[r], 2);
+                sa[r] += __shfl_xor_sync(0xffffffffu, sa[r], 4);
+                if (o == 0) sc_s[r * LL_KV_ROUND + tok] = tok < nr ? sa[r] : -INFINITY;   // stale slots may hold anything
             }
         }
+        cbar();
+        LL_STAMP(ST_F_ATT_E);   // E: scores
+        {
+            float mr = fmaxf(sc_s[r_w * LL_KV_ROUND + lane], sc_s[r_w * LL_KV_ROUND + lane + 32]);
 #pragma unroll
-        for (int r = 0; r < REP; ++r) {
-            float sa = 0.f;
+            for (int o = 16; o > 0; o >>= 1) mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+            const float mn = fmaxf(m_run, mr);                           // finite: every round has a valid token
+            const float corr = __expf(m_run - mn);
+            const float pj = lane < TPG ? __expf(sc_s[r_w * LL_KV_ROUND + tg * TPG + lane] - mn) : 0.f;
+            l_run = l_run * corr + warp_sum(pj);
+            acc0 *= corr; acc1 *= corr;
+            m_run = mn;
+            const unsigned char* vcol = kv_s + 4096 + dh * 128 + lane * 4;
 #pragma unroll
-            for (int e = 0; e < EPL; ++e) sa = fmaf(qr[r][e], k0[e], sa);
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
-            if (has) {
-                const float mn = fmaxf(m_run[r], sa);
-                const float corr = __expf(m_run[r] - mn), pa = __expf(sa - mn);
-                l_run[r] = l_run[r] * corr + pa;
-#pragma unroll
-                for (int e = 0; e < EPL; ++e) acc[r][e] = fmaf(pa, v0[e], acc[r][e] * corr);
-                m_run[r] = mn;
+            for (int j = 0; j < TPG; ++j) {
+                const int t = tg * TPG + j;
+                if (t < nr) {
+                    const float pv = __shfl_sync(0xffffffffu, pj, j);
+                    const uint32_t vv = *reinterpret_cast<const uint32_t*>(vcol + (t >> 4) * 8192 + (t & 15) * 256);
+                    acc0 = fmaf(pv, bf16lo(vv), acc0);
+                    acc1 = fmaf(pv, bf16hi(vv), acc1);
+                }
             }
         }
-    };
-    asm volatile("cp.async.wait_all;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < PRE; ++i)
-        if (i < n_iter) step(s0 + hwid + 32 * i, kv_s[((i * 32 + hwid) * 2 + 0) * 16 + sl], kv_s[((i * 32 + hwid) * 2 + 1) * 16 + sl]);
-    for (int i = PRE; i < n_iter; ++i) {
-        const int tok = s0 + hwid + 32 * i;
-        uint4 kr = make_uint4(0, 0, 0, 0), vr = make_uint4(0, 0, 0, 0);
-        if (tok < s1 && tok < pos) {
-            const __nv_bfloat16* kp = pool + (size_t)s.pages[(tok - s0) / Q3T_KV_PAGE] * page_elems + head_off +
-                                      (size_t)(tok % Q3T_KV_PAGE) * D + sl * EPL;
-            kr = __ldcg(reinterpret_cast<const uint4*>(kp));
-            vr = __ldcg(reinterpret_cast<const uint4*>(kp + v_off));
-        }
-        step(tok, kr, vr);
+        if (rd + 1 < n_rounds) cbar();                                   // staged rows and scores are read
     }
-    LL_STAMP(ST_F_ATT_E);   // E: scores + online softmax done
-    // 4. merge the two half-warps of a warp, then the 16 warps through shared memory
-#pragma unroll
-    for (int r = 0; r < REP; ++r) {
-        const float mo = __shfl_xor_sync(0xffffffffu, m_run[r], 16), lo = __shfl_xor_sync(0xffffffffu, l_run[r], 16);
-        const float mn = fmaxf(m_run[r], mo);
-        const float wa = (m_run[r] == -INFINITY) ? 0.f : __expf(m_run[r] - mn), wb = (mo == -INFINITY) ? 0.f : __expf(mo - mn);
-#pragma unroll
-        for (int e = 0; e < EPL; ++e) {
-            const float ao = __shfl_xor_sync(0xffffffffu, acc[r][e], 16);
-            acc[r][e] = acc[r][e] * wa + ao * wb;
-        }
-        l_run[r] = l_run[r] * wa + lo * wb;
-        m_run[r] = mn;
-        if (hw == 0) {
-#pragma unroll
-            for (int e = 0; e < EPL; ++e) part_s[(warp * REP + r) * LL_REC + sl * EPL + e] = acc[r][e];
-            if (sl == 0) { part_s[(warp * REP + r) * LL_REC + D] = m_run[r]; part_s[(warp * REP + r) * LL_REC + D + 1] = l_run[r]; }
-        }
-    }
-    LL_STAMP(ST_F_ATT_F);   // F: half-warp merge stored
+    *reinterpret_cast<float2*>(part_s + (tg * REP + r_w) * D + dh * 64 + lane * 2) = make_float2(acc0, acc1);
+    if (dh == 0 && lane == 0) { lpart_s[tg * REP + r_w] = l_run; if (tg == 0) m_s[r_w] = m_run; }
+    LL_STAMP(ST_F_ATT_F);   // F: partial outputs stored
     cbar();
     LL_STAMP(ST_F_ATT_G);   // G: barrier
-    // every thread has read its staged rows (barrier above).  The staging area is the digit-plane buffer: lanes 16..31 of
-    // every group must read as zero again (the lower halves are rewritten by the next prologue before anything reads them;
-    // the barrier of that prologue orders these stores before the next tile loop)
-    for (int i = tid; i < PRE * 32 * 2 * 16 / 2; i += LL_CTHREADS) s.xfrag[(i >> 4) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
-    // 5. this CTA's partial for (head r, dim d): the 16 warps merged out of shared memory
+    // every thread has read its staged rows (barrier above).  The staging area is part of the digit-plane buffer: lanes
+    // 16..31 of every group must read as zero again (the lower halves are rewritten by the next prologue before anything
+    // reads them; the barrier of that prologue orders these stores before the next tile loop)
+    for (int i = tid; i < LL_KV_ROUND * 16; i += LL_CTHREADS) s.xfrag[(LL_KV_GROUP0 + (i >> 4)) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
+    // 3. this CTA's partial for (head r, dim d): the token groups summed out of shared memory (all share one max)
     const bool mine = tid < REP * D;
     const int r = tid / D, d = tid % D;
     float M = -INFINITY, L = 0.f, A = 0.f;
     if (mine) {
-        // 48 independent shared-memory loads, then a max tree and 16 independent exponentials
-        float mh[LL_CWARPS], lh[LL_CWARPS], ah[LL_CWARPS];
+        M = m_s[r];
 #pragma unroll
-        for (int w = 0; w < LL_CWARPS; ++w) {
-            mh[w] = part_s[(w * REP + r) * LL_REC + D]; lh[w] = part_s[(w * REP + r) * LL_REC + D + 1];
-            ah[w] = part_s[(w * REP + r) * LL_REC + d];
-        }
-        M = mh[0];
-#pragma unroll
-        for (int w = 1; w < LL_CWARPS; ++w) M = fmaxf(M, mh[w]);
-#pragma unroll
-        for (int w = 0; w < LL_CWARPS; ++w) {
-            const float wt = (mh[w] == -INFINITY) ? 0.f : __expf(mh[w] - M);
-            L = fmaf(lh[w], wt, L);
-            A = fmaf(ah[w], wt, A);
-        }
+        for (int g = 0; g < TG; ++g) { A += part_s[(g * REP + r) * D + d]; L += lpart_s[g * REP + r]; }
     }
     u64* fin = ll_attnf + (size_t)(kvh * REP + r) * D + d;
     if (nsplit == 1) {           // the only split of its kv head: publish the normalised output directly
@@ -762,6 +778,7 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
         const LayerD& L = lay[l];
         // ---- QKV
         pro_norm(st, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
+        attn_prefetch(st, S, l, pos);             // this layer's K/V rows stream in under the QKV contraction
         LL_STAMP(ST_QKV_PRO);
         const uint32_t t_qkv = ++st.gen;
         gemv_phase(st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
@@ -926,6 +943,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
     } else if (tid == 65 && p_in.head.w) build_mat(s.hd[1], p_in.head, cta, gridDim.x);
     if (tid == 0) {
         for (int i = 0; i < LL_NSLOT; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
+        mbar_init(smem_u32(s.kvbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < (LL_MAXK / 64) * 32; i += LL_THREADS) s.xfrag[i] = make_uint4(0, 0, 0, 0);
@@ -950,7 +968,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
 
     // =============================== consumers ================================================================
     CState st;
-    st.seq = 0; st.nstamp = 0; st.red_par = 0; st.nsplit = 1; st.chunk = 128;
+    st.seq = 0; st.nstamp = 0; st.red_par = 0; st.kv_par = 0; st.nsplit = 1; st.chunk = 128;
     st.gen = *reinterpret_cast<volatile unsigned int*>(p.state);
     LL_STAMP(ST_START);
     if (p.mode == LL_MODE_STACK) {
@@ -1051,7 +1069,7 @@ static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.head_dim == 128, "frame_ll: head_dim must be 128");
     Q3T_REQUIRE(st.n_heads == st.n_kv_heads || st.n_heads == 2 * st.n_kv_heads, "frame_ll: H/Hkv must be 1 or 2");
     Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
-    Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
+    Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_KV_GROUP0 * 64, "frame_ll: dims too large");
     Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
     {   // parked attention records of the merger CTA must fit the digit groups the O-projection prologue leaves alone
         const int ms = grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit;

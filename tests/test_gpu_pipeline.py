@@ -208,6 +208,17 @@ def test_rvq_gather_is_bit_exact(small_setup):
         _, sums = O.rvq_decode(ws.fp, cfg, codes, split=True)
         sem, ac = model.codec.rvq_sums(codes)
         assert torch.equal(sem.cpu(), sums[0]) and torch.equal(ac.cpu(), sums[1])
+    # ids outside the codebook (EOS / control ids of a finished sequence in a lock-step batch) must not read past the
+    # tables: they contribute a zero vector, every other position is unchanged
+    bad = codes.clone()
+    bad[2, 0, 5] = cfg.talker.codec_eos_id
+    bad[0, 3, 9] = -1
+    sem_b, ac_b = model.codec.rvq_sums(bad)
+    sem, ac = model.codec.rvq_sums(codes)
+    keep = torch.ones(3, codes.shape[-1], dtype=torch.bool); keep[2, 5] = False
+    assert torch.equal(sem_b.cpu()[keep], sem.cpu()[keep]) and bool((sem_b.cpu()[2, 5] == 0).all())
+    keep = torch.ones(3, codes.shape[-1], dtype=torch.bool); keep[0, 9] = False
+    assert torch.equal(ac_b.cpu()[keep], ac.cpu()[keep]) and bool(torch.isfinite(ac_b).all())
 
 
 def _snr_db(x, ref):

@@ -9,6 +9,9 @@ import sys
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# the stamps are only compiled into the profiling build (csrc/build.sh); event timings of the production library: Q3T_LL_PROD=1
+if not os.environ.get("Q3T_LIB") and not os.environ.get("Q3T_LL_PROD"):
+    os.environ["Q3T_LIB"] = os.path.join(ROOT, "qwen3-tts-apple-silicon_b200", "qwen3_tts_b200", "libq3tts_b200_prof.so")
 sys.path.insert(0, os.path.join(ROOT, "qwen3-tts-apple-silicon_b200"))
 from qwen3_tts_b200 import config as Cfg
 from qwen3_tts_b200.engine import TalkerEngine
@@ -17,7 +20,7 @@ from qwen3_tts_b200.weights import make_weights
 NAMES = {0: "start", 1: "qkv.pro", 2: "qkv.gemv", 3: "attn", 4: "o.pro", 5: "o.gemv", 6: "gu.pro", 7: "gu.gemv", 8: "down.pro",
          9: "down.gemv", 10: "end", 11: "sample", 12: "cp_pass", 32: "f.poll", 34: "f.tiles", 35: "f.gbar", 36: "f.att.A.preload",
          37: "f.att.B.qwords", 38: "f.att.C.normrope", 39: "f.att.D.bar", 40: "f.att.E.scores", 41: "f.att.F.halfmerge",
-         42: "f.att.G.bar", 43: "f.merge"}
+         42: "f.att.G.bar", 43: "f.merge", 44: "f.dig"}
 MHZ = float(os.environ.get("Q3T_SM_MHZ", "1965"))
 
 
@@ -29,9 +32,10 @@ def decode(timing, G, NST):
     return ids, ns
 
 
-def report(ids, ns, ctas, title, skip_first=9):
+def report(ids, ns, ctas, title, skip_first=9, quiet=None):
     """Duration of every interval, attributed to (coarse phase it ends in, id of the closing stamp)."""
-    print(f"--- {title}")
+    if quiet is None:
+        print(f"--- {title}")
     import collections
     for cta in ctas:
         n = int((ns[cta] > 0).sum())
@@ -67,7 +71,10 @@ def report(ids, ns, ctas, title, skip_first=9):
             tot += per_layer
             nm = NAMES.get(ph, str(ph)) + ("" if sid == ph else ":" + NAMES.get(sid, str(sid)))
             parts.append(f"{nm}={per_layer:.2f}")
-        print(f"cta {cta:3d} ({n} stamps, /{n_layers} layers): " + "  ".join(parts) + f"  | sum {tot:.2f} us")
+        if quiet is None:
+            print(f"cta {cta:3d} ({n} stamps, /{n_layers} layers): " + "  ".join(parts) + f"  | sum {tot:.2f} us")
+        else:
+            quiet[cta] = dict(p.split("=") for p in parts)
 
 
 def main():
@@ -119,6 +126,15 @@ def main():
     n0 = int((ns[0] > 0).sum())
     print(f"ctx={ctx}: talker step, CTA0 first->last stamp {(ns[0, n0 - 1] - ns[0, 0]) / 1e3:.1f} us")
     report(ids, ns, (0, 1, 7, 39, 40, 73, G - 1), f"talker step ctx={ctx} (steady-state per layer)")
+    if os.environ.get("Q3T_LL_ALL"):
+        # one compact line per CTA: who waits (large poll) and who is waited for (small poll) in every exchange
+        rows = {}
+        report(ids, ns, range(G), "", quiet=rows)
+        keys = ["qkv.pro:f.poll", "qkv.pro", "qkv.gemv:f.tiles", "qkv.gemv", "attn", "o.pro:f.poll", "o.pro", "o.gemv:f.tiles", "o.gemv",
+                "gu.pro:f.poll", "gu.pro", "gu.gemv:f.tiles", "gu.gemv:f.gbar", "gu.gemv", "down.pro:f.poll", "down.pro", "down.gemv:f.tiles", "down.gemv"]
+        print("cta " + " ".join(k.replace(":f.", ":")[-9:].rjust(9) for k in keys))
+        for cta in range(G):
+            print(f"{cta:3d} " + " ".join(rows[cta].get(k, "-").rjust(9) for k in keys))
     # CUDA-event time of back-to-back steps
     s, f = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e.fa.ll_timing = 0
