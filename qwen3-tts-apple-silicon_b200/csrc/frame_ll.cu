@@ -44,7 +44,7 @@ constexpr int LL_NSLOT = LL_NSLOT_N;             // ring slots of one 4352-byte 
 constexpr int LL_PLANES = 4;                     // producer lanes issuing TMA copies
 constexpr int LL_MAXK = 6144;                    // largest contraction length (talker intermediate size)
 constexpr int LL_MAXH = 2048;                    // largest hidden size (one float4 per consumer thread)
-constexpr int LL_MAXT = 64;                      // max tiles of one matrix per CTA
+constexpr int LL_MAXT = 48;                      // max tiles of one matrix per CTA
 constexpr int LL_MAXSPLIT = 16;                  // attention splits per kv head
 constexpr int LL_REC = 130;                      // attention record: 128 acc + m + l
 constexpr int LL_SPIN_LIMIT = 1 << 22;           // watchdog: a poll that spins this long (~1 s) aborts the launch
@@ -211,12 +211,14 @@ struct LLSmem {
     LayerD* lay;            // [LL_MAXLAYERS]  talker layers first, then code-predictor layers
     MatD* hd;               // [LL_MAXHEADS]   0 = cp_proj, 1 = codec head (or the stack-mode head), 2.. = cp heads
     uint8_t* ring;          // [LL_NSLOT][4352]
-    uint4* xfrag;           // [LL_MAXK/64][32] digit planes in mma B-fragment order (lanes 16..31 stay zero); sampler scratch
-    float* xsum;            // [LL_MAXK/64]
-    float* xscl;            // [LL_MAXK/64]
-    float* resid;           // [LL_MAXH]
-    float* tile_out;        // [LL_MAXT][16]
-    float* att;             // attention scratch: q [2][128], new k/v [2][128], partials [16][2][130]
+    uint4* dig;             // [LL_CWARPS][4 groups][16] warp-private digit planes of one 256-wide k-chunk (mma B-fragment order)
+    float* xsum;            // [LL_CWARPS][4]
+    float* xscl;            // [LL_CWARPS][4]
+    unsigned char* stage;   // [32 KB] attention K/V staging (cp.async.bulk target); parked split records; sampler scratch
+    float* resid;           // [2][LL_MAXH] residual stream, double buffered (see gemv_phase)
+    float* tile_out;        // [2][LL_MAXT][16], double buffered by phase parity
+    float* ssq;             // [2][32] per-k-chunk sums of squares of the phase input (RMSNorm), by phase parity
+    float* att;             // attention scratch: q [2][128], scores [2][64], new k/v, partials
     float* red;             // [2][32] block reductions, double buffered
     float* cs;              // [64] cos(pos * inv_freq)
     float* sn;              // [64]
@@ -226,16 +228,19 @@ struct LLSmem {
     uint64_t* empty;        // [LL_NSLOT]
     uint64_t* kvbar;        // attention K/V staging (cp.async.bulk completion)
 };
-constexpr size_t LL_ATT_FLOATS = 4 * 128 + 16 * 2 * LL_REC;
+constexpr size_t LL_STAGE_BYTES = 32768;
+constexpr size_t LL_ATT_FLOATS = 4 * 128 + 8 * 128 + 32;
 constexpr size_t LL_OFF_LAY = 1024;                                      // the first KB holds a copy of LLParams
 constexpr size_t LL_OFF_HD = LL_OFF_LAY + LL_MAXLAYERS * sizeof(LayerD);
 constexpr size_t LL_OFF_RING = (LL_OFF_HD + LL_MAXHEADS * sizeof(MatD) + 127) / 128 * 128;
-constexpr size_t LL_OFF_XFRAG = LL_OFF_RING + (size_t)LL_NSLOT * Q3T_TILE_BYTES;
-constexpr size_t LL_OFF_XSUM = LL_OFF_XFRAG + (size_t)(LL_MAXK / 64) * 512;
-constexpr size_t LL_OFF_XSCL = LL_OFF_XSUM + (LL_MAXK / 64) * 4;
-constexpr size_t LL_OFF_RESID = LL_OFF_XSCL + (LL_MAXK / 64) * 4;
-constexpr size_t LL_OFF_TILE = LL_OFF_RESID + LL_MAXH * 4;
-constexpr size_t LL_OFF_ATT = LL_OFF_TILE + LL_MAXT * 16 * 4;
+constexpr size_t LL_OFF_DIG = LL_OFF_RING + (size_t)LL_NSLOT * Q3T_TILE_BYTES;
+constexpr size_t LL_OFF_XSUM = LL_OFF_DIG + (size_t)LL_CWARPS * 4 * 16 * 16;
+constexpr size_t LL_OFF_XSCL = LL_OFF_XSUM + LL_CWARPS * 4 * 4;
+constexpr size_t LL_OFF_STAGE = LL_OFF_XSCL + LL_CWARPS * 4 * 4;
+constexpr size_t LL_OFF_RESID = LL_OFF_STAGE + LL_STAGE_BYTES;
+constexpr size_t LL_OFF_TILE = LL_OFF_RESID + 2 * LL_MAXH * 4;
+constexpr size_t LL_OFF_SSQ = LL_OFF_TILE + 2 * LL_MAXT * 16 * 4;
+constexpr size_t LL_OFF_ATT = LL_OFF_SSQ + 2 * 32 * 4;
 constexpr size_t LL_OFF_RED = LL_OFF_ATT + LL_ATT_FLOATS * 4;
 constexpr size_t LL_OFF_CS = LL_OFF_RED + 64 * 4;
 constexpr size_t LL_OFF_SN = LL_OFF_CS + 64 * 4;
@@ -246,6 +251,7 @@ constexpr size_t LL_OFF_EMPTY = LL_OFF_FULL + LL_NSLOT * 8;
 constexpr size_t LL_OFF_KVBAR = LL_OFF_EMPTY + LL_NSLOT * 8;
 constexpr size_t LL_SMEM_BYTES = LL_OFF_KVBAR + 8;
 static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
+static_assert(LL_OFF_STAGE % 128 == 0 && LL_OFF_DIG % 16 == 0, "frame_ll: staging / digit alignment");
 
 __device__ __forceinline__ const LLParams& ll_params() { return *reinterpret_cast<const LLParams*>(ll_smem_raw); }
 __device__ __forceinline__ LLSmem ll_smem() {
@@ -254,11 +260,13 @@ __device__ __forceinline__ LLSmem ll_smem() {
     s.lay = reinterpret_cast<LayerD*>(b + LL_OFF_LAY);
     s.hd = reinterpret_cast<MatD*>(b + LL_OFF_HD);
     s.ring = b + LL_OFF_RING;
-    s.xfrag = reinterpret_cast<uint4*>(b + LL_OFF_XFRAG);
+    s.dig = reinterpret_cast<uint4*>(b + LL_OFF_DIG);
     s.xsum = reinterpret_cast<float*>(b + LL_OFF_XSUM);
     s.xscl = reinterpret_cast<float*>(b + LL_OFF_XSCL);
+    s.stage = b + LL_OFF_STAGE;
     s.resid = reinterpret_cast<float*>(b + LL_OFF_RESID);
     s.tile_out = reinterpret_cast<float*>(b + LL_OFF_TILE);
+    s.ssq = reinterpret_cast<float*>(b + LL_OFF_SSQ);
     s.att = reinterpret_cast<float*>(b + LL_OFF_ATT);
     s.red = reinterpret_cast<float*>(b + LL_OFF_RED);
     s.cs = reinterpret_cast<float*>(b + LL_OFF_CS);
@@ -279,6 +287,8 @@ struct CState {
     int chunk;
     int red_par;            // parity of the double-buffered block-reduction scratch
     uint32_t kv_par;        // phase parity of the K/V staging barrier
+    int res_par;            // which half of the residual double buffer is current
+    int pp;                 // phase parity of tile_out / ssq
 };
 
 // Profiling stamps (thread 0 of every CTA): {id : 20 bits | clock64 cycles of this SM : 44 bits}.  ids < 32 mark phase ends
@@ -308,7 +318,8 @@ __device__ __forceinline__ float cblock_sum(float v, float* red, int parity) {
 
 // v = 4 consecutive inputs starting at k = 4*k4 -> signed base-256 digit planes + per-group sum/scale.
 // Whole warps call this together (16 lanes share a 64-wide quantisation group).
-__device__ __forceinline__ void emit_digits(const LLSmem& s, float4 v, int k4, int lane) {
+// k4 = index of the float4 inside the warp's 256-wide k-chunk (0..63); dig / xsum / xscl are the warp's private areas.
+__device__ __forceinline__ void emit_digits(uint4* dig, float* xsum, float* xscl, float4 v, int k4, int lane) {
     float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
@@ -325,17 +336,18 @@ __device__ __forceinline__ void emit_digits(const LLSmem& s, float4 v, int k4, i
     wd[2] = __byte_perm(t2, t3, 0x5410); wd[3] = __byte_perm(t2, t3, 0x7632);
     const int k = k4 << 2, G = k >> 6, kk = k & 63;
     const int r = ((kk >> 5) << 1) | ((kk >> 4) & 1), t = (kk >> 2) & 3;
-    uint32_t* base = reinterpret_cast<uint32_t*>(s.xfrag + G * 32);
+    uint32_t* base = reinterpret_cast<uint32_t*>(dig + G * 16);
 #pragma unroll
     for (int d = 0; d < 4; ++d) base[(d * 4 + t) * 4 + r] = wd[d];
     float gs = ((float)e0 + (float)e1) + ((float)e2 + (float)e3);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) gs += __shfl_xor_sync(0xffffffffu, gs, o);
-    if ((lane & 15) == 0) { s.xsum[G] = gs * xscale; s.xscl[G] = xscale; }
+    if ((lane & 15) == 0) { xsum[G] = gs * xscale; xscl[G] = xscale; }
 }
 
 // One 4352-byte tile out of the ring against the digit planes: 16 output rows (partial over this tile's 256 inputs).
-__device__ __forceinline__ void tile_dot(const LLSmem& s, const uint8_t* tile, int kc, int lane, float& out_lo, float& out_hi) {
+// Lanes 16..31 carry the four unused columns of the 8-wide B operand: zeros from registers.
+__device__ __forceinline__ void tile_dot(const uint4* dig, const float* xsum, const float* xscl, const uint8_t* tile, int lane, float& out_lo, float& out_hi) {
     const int g = lane >> 2, t = lane & 3;
     const uint4 mlo = *reinterpret_cast<const uint4*>(tile + 4096 + g * 16);
     const uint4 mhi = *reinterpret_cast<const uint4*>(tile + 4096 + (g + 8) * 16);
@@ -343,14 +355,14 @@ __device__ __forceinline__ void tile_dot(const LLSmem& s, const uint8_t* tile, i
     float f[4] = {0.f, 0.f, 0.f, 0.f}, bacc_lo = 0.f, bacc_hi = 0.f;
 #pragma unroll
     for (int j4 = 0; j4 < 4; ++j4) {
-        const int G = kc * 4 + j4;
+        const int G = j4;
         const uint4 a0 = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + 0) * 512 + lane * 16);
         const uint4 a1 = *reinterpret_cast<const uint4*>(tile + (j4 * 2 + 1) * 512 + lane * 16);
-        const uint4 b = s.xfrag[G * 32 + lane];
+        const uint4 b = lane < 16 ? dig[G * 16 + lane] : make_uint4(0u, 0u, 0u, 0u);
         int acc[4] = {0, 0, 0, 0};
         imma_16832_ll(acc, a0, b.x, b.y);
         imma_16832_ll(acc, a1, b.z, b.w);
-        const float xg = s.xscl[G], xs = s.xsum[G];
+        const float xg = xscl[G], xs = xsum[G];
         const uint32_t sw_lo = slo_w[j4 >> 1], sw_hi = shi_w[j4 >> 1], bw_lo = blo_w[j4 >> 1], bw_hi = bhi_w[j4 >> 1];
         const float slo = ((j4 & 1) ? bf16hi(sw_lo) : bf16lo(sw_lo)) * xg;
         const float shi = ((j4 & 1) ? bf16hi(sw_hi) : bf16lo(sw_hi)) * xg;
@@ -369,29 +381,129 @@ __device__ __forceinline__ void tile_dot(const LLSmem& s, const uint8_t* tile, i
     out_hi = v_hi + bacc_hi;
 }
 
-// ---- GEMV phase (consumers): this CTA's row tiles out of the ring -> epilogue -> LL words (+ optional plain copy) --------
-__device__ LL_FN void gemv_phase(CState& st, const MatD& W, int epi, u64* ll_out, float* plain_out, uint32_t tag) {
+// ---- GEMV phase (consumers): per-WARP data flow ---------------------------------------------------------------------------
+// A warp needs only the 256 inputs of its own k-chunk: it polls those words (two float4 per lane), applies the input
+// transform, writes the digit planes of that chunk into its PRIVATE 1 KB area and starts its tile - no block-wide prologue,
+// no barrier before the tiles, and a chunk whose producers are late delays one warp instead of the CTA.  RMSNorm: the
+// digits are taken from norm_w * x (block fixed point is scale-invariant per group) and 1/rms multiplies the row sums in
+// the epilogue; the per-chunk sums of squares meet in shared memory at the one barrier a phase keeps (tiles -> row sums).
+// Residual stream: x = resid + delta is written by the warp of tile j < nkc into the OTHER half of a double buffer (several
+// warps may convert the same chunk - 16 warps, 4 or 8 chunks - and all of them read the old half).  tile_out / ssq are
+// double buffered by phase parity: a fast warp may be in the tiles of phase p+1 while a slow one is in the epilogue of p.
+enum { IN_NORM = 0, IN_LL = 1, IN_PLAIN = 2 };
+struct PhaseIn {
+    int kind;
+    const u64* words; uint32_t tag;      // IN_NORM: residual delta (or nullptr); IN_LL: the input vector
+    const float* norm_w; float inv_h, eps;   // IN_NORM
+    const float* plain;                  // IN_PLAIN: fp32 vector in global memory (table row / written by an earlier launch)
+    float* hidden_out;                   // IN_NORM: CTA 0 stores the normalised input here (final norm), or nullptr
+};
+__device__ __forceinline__ PhaseIn in_norm(const u64* add, uint32_t tag, const float* w, int H, float eps, float* hidden_out = nullptr) {
+    PhaseIn in; in.kind = IN_NORM; in.words = add; in.tag = tag; in.norm_w = w; in.inv_h = 1.f / (float)H; in.eps = eps;
+    in.plain = nullptr; in.hidden_out = hidden_out; return in;
+}
+__device__ __forceinline__ PhaseIn in_ll(const u64* words, uint32_t tag) {
+    PhaseIn in; in.kind = IN_LL; in.words = words; in.tag = tag; in.norm_w = nullptr; in.inv_h = 0.f; in.eps = 0.f;
+    in.plain = nullptr; in.hidden_out = nullptr; return in;
+}
+__device__ __forceinline__ PhaseIn in_plain(const float* x) {
+    PhaseIn in; in.kind = IN_PLAIN; in.words = nullptr; in.tag = 0u; in.norm_w = nullptr; in.inv_h = 0.f; in.eps = 0.f;
+    in.plain = x; in.hidden_out = nullptr; return in;
+}
+
+__device__ LL_FN void gemv_phase(CState& st, const MatD& W, const PhaseIn& in, int epi, u64* ll_out, float* plain_out, uint32_t tag) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nkc = W.nkc, rb = W.rb, nloc = W.re - W.rb;
     const int nt = nloc * nkc;
-    int kc = warp % nkc;                     // tile j covers k-chunk j % nkc (j = warp, warp + 16, ...)
+    const bool norm = in.kind == IN_NORM, add = norm && in.words != nullptr;
+    float* tout = s.tile_out + st.pp * (LL_MAXT * 16);
+    float* ssq = s.ssq + st.pp * 32;
+    const float* res_old = s.resid + st.res_par * LL_MAXH;
+    float* res_new = s.resid + (add ? (st.res_par ^ 1) : st.res_par) * LL_MAXH;
+    uint4* dig = s.dig + warp * 64;
+    float* xsum = s.xsum + warp * 4;
+    float* xscl = s.xscl + warp * 4;
+    // a norm phase walks every chunk even where this CTA has no tile: the residual stream must stay complete
+    const int jmax = norm ? (nt > nkc ? nt : nkc) : nt;
+    int kc = warp % nkc, cur = -1;           // tile j covers k-chunk j % nkc (j = warp, warp + 16, ...)
     const int kstep = LL_CWARPS % nkc;
-    for (int j = warp; j < nt; j += LL_CWARPS) {
-        const uint32_t i = st.seq + j, slot = i % LL_NSLOT, par = (i / LL_NSLOT) & 1;
-        mbar_wait(smem_u32(&s.full[slot]), par, p.state, 0x200u);
-        float lo, hi;
-        tile_dot(s, s.ring + (size_t)slot * Q3T_TILE_BYTES, kc, lane, lo, hi);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.empty[slot]));
-        if ((lane & 3) == 0) { s.tile_out[j * 16 + (lane >> 2)] = lo; s.tile_out[j * 16 + (lane >> 2) + 8] = hi; }
+    for (int j = warp; j < jmax; j += LL_CWARPS) {
+        if (kc != cur) {
+            const int k4a = kc * 64 + lane, k4b = k4a + 32;
+            float4 va, vb;
+            if (in.kind == IN_PLAIN) {
+                va = __ldcg(reinterpret_cast<const float4*>(in.plain) + k4a);
+                vb = __ldcg(reinterpret_cast<const float4*>(in.plain) + k4b);
+            } else {
+                float4 na = make_float4(1.f, 1.f, 1.f, 1.f), nb = na;
+                if (norm) {                      // in flight while the words are polled
+                    na = __ldg(reinterpret_cast<const float4*>(in.norm_w) + k4a);
+                    nb = __ldg(reinterpret_cast<const float4*>(in.norm_w) + k4b);
+                }
+                va = make_float4(0.f, 0.f, 0.f, 0.f); vb = va;
+                if (in.words) {
+                    const u64* const pp[2] = {in.words + 4 * (size_t)k4a, in.words + 4 * (size_t)k4b};
+                    const bool on[2] = {true, true};
+                    float4 o[2];
+                    ll_ld4n<2>(pp, on, in.tag, o, p.state);
+                    va = o[0]; vb = o[1];
+                }
+                if (norm) {
+                    const float4 ra = reinterpret_cast<const float4*>(res_old)[k4a], rb4 = reinterpret_cast<const float4*>(res_old)[k4b];
+                    va.x += ra.x; va.y += ra.y; va.z += ra.z; va.w += ra.w;
+                    vb.x += rb4.x; vb.y += rb4.y; vb.z += rb4.z; vb.w += rb4.w;
+                    if (add && j < nkc) {        // the one writer of this chunk's new residual
+                        reinterpret_cast<float4*>(res_new)[k4a] = va;
+                        reinterpret_cast<float4*>(res_new)[k4b] = vb;
+                    }
+                    float ss = (va.x * va.x + va.y * va.y) + (va.z * va.z + va.w * va.w) + (vb.x * vb.x + vb.y * vb.y) + (vb.z * vb.z + vb.w * vb.w);
+                    ss = warp_sum(ss);
+                    if (j < nkc && lane == 0) ssq[kc] = ss;
+                    va.x *= na.x; va.y *= na.y; va.z *= na.z; va.w *= na.w;
+                    vb.x *= nb.x; vb.y *= nb.y; vb.z *= nb.z; vb.w *= nb.w;
+                }
+            }
+            if (j < nt) {
+                __syncwarp();                    // the previous tile's reads of the private area are done
+                emit_digits(dig, xsum, xscl, va, lane, lane);
+                emit_digits(dig, xsum, xscl, vb, lane + 32, lane);
+                __syncwarp();
+            }
+            cur = kc;
+        }
+        if (j < nt) {
+            const uint32_t i = st.seq + j, slot = i % LL_NSLOT, par = (i / LL_NSLOT) & 1;
+            mbar_wait(smem_u32(&s.full[slot]), par, p.state, 0x200u);
+            float lo, hi;
+            tile_dot(dig, xsum, xscl, s.ring + (size_t)slot * Q3T_TILE_BYTES, lane, lo, hi);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&s.empty[slot]));
+            if ((lane & 3) == 0) { tout[j * 16 + (lane >> 2)] = lo; tout[j * 16 + (lane >> 2) + 8] = hi; }
+        }
         kc += kstep; if (kc >= nkc) kc -= nkc;
     }
     st.seq += nt;
+    st.pp ^= 1;
+    if (add) st.res_par ^= 1;
     LL_STAMP(ST_F_TILES);
     cbar();
     LL_STAMP(ST_F_GBAR);
+    float rstd = 1.f;
+    if (norm) {
+        float t = 0.f;
+        for (int k = 0; k < nkc; ++k) t += ssq[k];
+        rstd = rsqrtf(t * in.inv_h + in.eps);
+        if (in.hidden_out && blockIdx.x == 0) {
+            const int H4 = nkc * 64;
+            for (int k4 = tid; k4 < H4; k4 += LL_CTHREADS) {
+                const float4 x = reinterpret_cast<const float4*>(res_new)[k4];
+                const float4 nw = __ldg(reinterpret_cast<const float4*>(in.norm_w) + k4);
+                reinterpret_cast<float4*>(in.hidden_out)[k4] = make_float4(nw.x * (x.x * rstd), nw.y * (x.y * rstd), nw.z * (x.z * rstd), nw.w * (x.w * rstd));
+            }
+        }
+    }
     // rows: four lanes per output row add every fourth k-chunk, two shuffles finish the sum (fixed order); a warp
     // covers 8 rows per iteration.  SwiGLU tiles hold gate rows 0..7 and the matching up rows 8..15 (weights interleaved
     // at load): slots 0..3 of a warp take gate rows, slots 4..7 the matching up rows, paired with one more shuffle.
@@ -402,9 +514,10 @@ __device__ LL_FN void gemv_phase(CState& st, const MatD& W, int epi, u64* ll_out
         if (epi == EPI_SWIGLU) { const int blk = i0 >> 3; rtl = blk >> 1; r = ((blk & 1) << 2) + (sl & 3) + ((sl >> 2) << 3); }
         else { const int i = i0 + sl; rtl = i >> 4; r = i & 15; }
         float v = 0.f;
-        for (int k = q; k < nkc; k += 4) v += s.tile_out[(rtl * nkc + k) * 16 + r];
+        for (int k = q; k < nkc; k += 4) v += tout[(rtl * nkc + k) * 16 + r];
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v *= rstd;
         if (epi == EPI_SWIGLU) {
             const float u = __shfl_xor_sync(0xffffffffu, v, 16);
             if (sl < 4 && q == 0) ll_st(ll_out + (size_t)(rb + rtl) * 8 + (r & 7), silu_f(v) * u, tag);
@@ -417,60 +530,27 @@ __device__ LL_FN void gemv_phase(CState& st, const MatD& W, int epi, u64* ll_out
     }
 }
 
-// ---- prologues: phase input -> digit planes in shared memory ---------------------------------------------------------------
-// resid (+= LL words of the previous projection) -> RMSNorm -> digits
-__device__ LL_FN void pro_norm(CState& st, const u64* ll_add, uint32_t tag_add, const float* norm_w, float* hidden_out, int H,
-                               float eps) {
+// final RMSNorm without a following contraction (stack mode, hidden state only): block-wide, once per launch at most
+__device__ LL_FN void final_norm_only(CState& st, const u64* ll_add, uint32_t tag_add, const float* norm_w, float* hidden_out, int H,
+                                      float eps) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
-    const int tid = threadIdx.x, lane = tid & 31, H4 = H >> 2;
+    const int tid = threadIdx.x, H4 = H >> 2;
     const bool on = tid < H4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f), nw = make_float4(0.f, 0.f, 0.f, 0.f);
     if (on) {
-        nw = __ldg(reinterpret_cast<const float4*>(norm_w) + tid);      // in flight while the words are polled
-        v = reinterpret_cast<float4*>(s.resid)[tid];
+        nw = __ldg(reinterpret_cast<const float4*>(norm_w) + tid);
+        v = reinterpret_cast<const float4*>(s.resid + st.res_par * LL_MAXH)[tid];
         if (ll_add) {
             const float4 a = ll_ld4(ll_add + 4 * tid, tag_add, p.state);
             v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-            reinterpret_cast<float4*>(s.resid)[tid] = v;
         }
     }
-    LL_STAMP(ST_F_POLL);
     const float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     st.red_par ^= 1;
     const float rstd = rsqrtf(cblock_sum(ss, s.red, st.red_par) / (float)H + eps);
-    if (on) {
-        v.x = nw.x * (v.x * rstd); v.y = nw.y * (v.y * rstd); v.z = nw.z * (v.z * rstd); v.w = nw.w * (v.w * rstd);
-        if (hidden_out && blockIdx.x == 0) reinterpret_cast<float4*>(hidden_out)[tid] = v;
-        emit_digits(s, v, tid, lane);
-    }
-    cbar();
-}
-
-// LL words (already activated values) -> digits; K <= LL_MAXK
-__device__ LL_FN void pro_ll(CState& st, const u64* ll, uint32_t tag, int K) {
-    const LLParams& p = ll_params();
-    const LLSmem s = ll_smem();
-    const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
-    constexpr int NV = LL_MAXK / 4 / LL_CTHREADS;   // 3
-    const u64* pp[NV]; bool on[NV]; float4 v[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { const int k4 = tid + i * LL_CTHREADS; on[i] = k4 < K4; pp[i] = ll + 4 * (size_t)k4; }
-    ll_ld4n<NV>(pp, on, tag, v, p.state);
-    LL_STAMP(ST_F_POLL);
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-        if (on[i]) emit_digits(s, v[i], tid + i * LL_CTHREADS, lane);
-    LL_STAMP(ST_F_DIG);
-    cbar();
-}
-
-// plain fp32 vector in global memory (constant table row or a vector written by an earlier launch) -> digits
-__device__ LL_FN void pro_plain(const float* x, int K) {
-    const LLSmem s = ll_smem();
-    const int tid = threadIdx.x, lane = tid & 31, K4 = K >> 2;
-    for (int k4 = tid; k4 < K4; k4 += LL_CTHREADS) emit_digits(s, __ldcg(reinterpret_cast<const float4*>(x) + k4), k4, lane);
-    cbar();
+    if (on && hidden_out && blockIdx.x == 0)
+        reinterpret_cast<float4*>(hidden_out)[tid] = make_float4(nw.x * (v.x * rstd), nw.y * (v.y * rstd), nw.z * (v.z * rstd), nw.w * (v.w * rstd));
 }
 
 // ---- attention geometry (uniform over the grid) -----------------------------------------------------------------------------
@@ -488,13 +568,15 @@ __device__ __forceinline__ void attn_geometry(int ctx, int n_kv, int grid, int c
 
 // ---- attention phase: q/k RMSNorm + RoPE + KV-page write + split-KV GQA decode attention -> LL records ----------------------
 // K/V staging: the rows of this CTA's (kv head, chunk) are whole 4 KB blocks of the paged cache ([page][k|v][head][16][128]
-// bf16), so 64 tokens are eight cp.async.bulk copies issued by ONE thread right after the QKV prologue - they land in digit
-// groups 32..95 (idle until the down projection) while the QKV contraction runs, and nobody computes an address per row.
-constexpr int LL_KV_GROUP0 = 32;                 // first digit group of the staging area (needs q_dim, hidden <= 2048)
+// bf16), so 64 tokens are eight cp.async.bulk copies issued as ONE warp instruction; the staging buffer is dedicated, so
+// the copies of layer l+1 are issued right after the O projection of layer l and nobody computes an address per row.
 constexpr int LL_KV_ROUND = 64;                  // tokens staged per round (4 pages)
-static_assert((LL_MAXK / 64 - LL_KV_GROUP0) * 512 >= LL_KV_ROUND * 512, "attention K/V staging must fit the idle digit groups");
+static_assert(LL_KV_ROUND * 512 <= LL_STAGE_BYTES, "attention K/V staging buffer");
+static_assert((LL_MAXSPLIT - 1) * 2 * LL_REC * 4 <= LL_STAGE_BYTES, "parked split records must fit the staging buffer");
+constexpr int LL_SAMPLE_MAXV = 3072;             // largest vocabulary the in-kernel sampler holds in the staging buffer
+static_assert(LL_SAMPLE_MAXV * (4 + 4 + 2) + 1024 <= LL_STAGE_BYTES && LL_SAMPLE_MAXV <= SAMPLE_MAXV, "sampler scratch must fit the staging buffer");
 
-__device__ __forceinline__ unsigned char* kv_stage(const LLSmem& s) { return reinterpret_cast<unsigned char*>(s.xfrag + LL_KV_GROUP0 * 32); }
+__device__ __forceinline__ unsigned char* kv_stage(const LLSmem& s) { return s.stage; }
 
 // lanes 0..2*npg-1 of ONE warp (all 32 lanes call): pages [pg0, pg0 + npg) of this CTA's chunk -> staging area, one 4 KB
 // block per lane, completion on s.kvbar.  One warp instruction issues all copies; the warp loses ~0.1 us.
@@ -505,13 +587,13 @@ __device__ __forceinline__ void kv_issue(const LLSmem& s, const LLStack& S, int 
     const __nv_bfloat16* src = S.kv_pool + (size_t)layer * S.kv_layer_stride + (size_t)s.pages[pg0 + pg] * page_elems +
                                (size_t)(is_v * S.n_kv + kvh) * Q3T_KV_PAGE * 128;
     const uint32_t bar = smem_u32(s.kvbar), dst = smem_u32(kv_stage(s)) + pg * 8192 + is_v * 4096;
-    // generic-proxy writes to the staging area (digits, zeroing) were ordered before this thread by a block barrier
+    // generic-proxy accesses to the staging area (parked records, sampler scratch) were ordered before this thread by a block barrier
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (lane == 0) mbar_expect_tx(bar, (uint32_t)npg * 8192u);   // a copy that lands first only drives the tx count negative
     tma_load_1d(dst, src, 4096, bar);
 }
 
-// called by every consumer thread after the QKV prologue of a layer (round 0 of the attention chunk)
+// called by every consumer thread once all reads of the staging buffer are behind a block barrier (round 0 of the chunk)
 __device__ __forceinline__ void attn_prefetch(const CState& st, const LLStack& S, int layer, int pos) {
     const int cta = blockIdx.x;
     if (cta >= S.n_kv * st.nsplit || (threadIdx.x >> 5) != LL_CWARPS - 1) return;
@@ -668,10 +750,6 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
     LL_STAMP(ST_F_ATT_F);   // F: partial outputs stored
     cbar();
     LL_STAMP(ST_F_ATT_G);   // G: barrier
-    // every thread has read its staged rows (barrier above).  The staging area is part of the digit-plane buffer: lanes
-    // 16..31 of every group must read as zero again (the lower halves are rewritten by the next prologue before anything
-    // reads them; the barrier of that prologue orders these stores before the next tile loop)
-    for (int i = tid; i < LL_KV_ROUND * 16; i += LL_CTHREADS) s.xfrag[(LL_KV_GROUP0 + (i >> 4)) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
     // 3. this CTA's partial for (head r, dim d): the token groups summed out of shared memory (all share one max)
     const bool mine = tid < REP * D;
     const int r = tid / D, d = tid % D;
@@ -695,14 +773,12 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
         return;
     }
     // 6. merger: the records of the other splits are requested by all 512 threads at once (one 16-byte load per thread
-    //    covers four splits of two heads -> one L2 round trip at ctx <= 320), parked in the lower halves of the digit
-    //    groups (rewritten by the next prologue before anything reads them; the K/V staging above is dead), merged with
-    //    this CTA's own partial and published as plain normalised words: every consumer of the O projection then needs
-    //    ONE poll of its own float4 instead of nsplit dependent record reads of lines that 148 CTAs hammer at once.
-    //    The groups the O-projection prologue rewrites (q_dim / 64 of them) are skipped: a fast thread of this CTA may
-    //    already be writing its digits while a slow one still reads the parked records.
-    float* tmp = reinterpret_cast<float*>(s.xfrag + (S.n_heads * D / 64) * 32);
-    auto tmp_at = [&](int f) -> float& { return tmp[((f >> 6) << 7) + (f & 63)]; };
+    //    covers four splits of two heads -> one L2 round trip at ctx <= 320), parked in the staging buffer (its K/V rows are
+    //    dead), merged with this CTA's own partial and published as plain normalised words: every consumer of the O
+    //    projection then needs ONE poll of its own words instead of nsplit dependent record reads of lines that 148 CTAs
+    //    hammer at once.
+    float* tmp = reinterpret_cast<float*>(s.stage);
+    auto tmp_at = [&](int f) -> float& { return tmp[f]; };
     const int n_items = (nsplit - 1) * REP * 64;
     for (int it0 = 0; it0 < n_items; it0 += LL_CTHREADS) {
         const int it = it0 + tid;
@@ -746,18 +822,15 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
 }
 
 // ---- one token through a dense stack (consumers) ------------------------------------------------------------------------------
-// resid must hold the stack input (or zeros when first_add carries it as LL words).  On return, if want_final, the digit
-// planes hold the final-norm output (and hidden_out is written by CTA 0).
-struct StackIO {
-    const u64* first_add; uint32_t first_tag;
-    bool want_final; float* hidden_out;
-};
+// The current half of the residual buffer must hold the stack input (or zeros when first_add carries it as LL words).
+// Returns the words the caller's final norm still has to add (the last down projection).
+struct StackOut { const u64* add; uint32_t tag; };
 
-__device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const StackIO& io) {
+__device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const u64* first_add, uint32_t first_tag) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
-    const int q_dim = S.n_heads * S.head_dim, rep = S.n_heads / S.n_kv;
+    const int rep = S.n_heads / S.n_kv;
     // RoPE table of this position (rotate_half convention, fp32 cos/sin as the oracle)
     if (tid < S.head_dim / 2) {
         float sn, cs;
@@ -767,21 +840,20 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
     attn_geometry(pos + 1, S.n_kv, gridDim.x, p.att_chunk, p.att_maxsplit, st.chunk, st.nsplit);
     if ((int)blockIdx.x < S.n_kv * st.nsplit) {
         // page ids of this CTA's attention chunk: constant during the pass, so no attention phase starts with a
-        // dependent block-table load in front of its K/V loads
+        // dependent block-table load in front of its K/V copies
         const int split = blockIdx.x / S.n_kv, p0 = (split * st.chunk) / Q3T_KV_PAGE;
         const int np = min(st.chunk / Q3T_KV_PAGE, (pos / Q3T_KV_PAGE) - p0 + 1);
         if (tid < np && tid < 64) s.pages[tid] = S.block_tbl[p0 + tid];
     }
-    const u64* add = io.first_add;
-    uint32_t add_tag = io.first_tag;
+    cbar();                                       // page ids, RoPE table and the caller's residual are visible to every warp
+    attn_prefetch(st, S, 0, pos);
+    const u64* add = first_add;
+    uint32_t add_tag = first_tag;
     for (int l = 0; l < S.n_layers; ++l) {
         const LayerD& L = lay[l];
         // ---- QKV
-        pro_norm(st, add, add_tag, L.input_norm, nullptr, S.hidden, S.eps);
-        attn_prefetch(st, S, l, pos);             // this layer's K/V rows stream in under the QKV contraction
-        LL_STAMP(ST_QKV_PRO);
         const uint32_t t_qkv = ++st.gen;
-        gemv_phase(st, L.qkv, EPI_RAW, p.x_qkv, nullptr, t_qkv);
+        gemv_phase(st, L.qkv, in_norm(add, add_tag, L.input_norm, S.hidden, S.eps), EPI_RAW, p.x_qkv, nullptr, t_qkv);
         LL_STAMP(ST_QKV);
         // ---- attention (first n_kv*nsplit CTAs)
         const uint32_t t_att = ++st.gen;
@@ -789,26 +861,24 @@ __device__ LL_FN void stack_consume(CState& st, const LLStack& S, const LayerD* 
         else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att);
         LL_STAMP(ST_ATTN);
         // ---- O projection
-        pro_ll(st, p.x_attnf, t_att, q_dim);
-        LL_STAMP(ST_O_PRO);
         const uint32_t t_o = ++st.gen;
-        gemv_phase(st, L.o, EPI_RAW, p.x_o, nullptr, t_o);
+        gemv_phase(st, L.o, in_ll(p.x_attnf, t_att), EPI_RAW, p.x_o, nullptr, t_o);
         LL_STAMP(ST_O);
+        // every read of the staging buffer (K/V rows, parked records) is behind the barrier of the O projection: the next
+        // layer's rows stream in under gate/up, down and QKV
+        if (l + 1 < S.n_layers) attn_prefetch(st, S, l + 1, pos);
         // ---- gate/up (+ SwiGLU in the epilogue)
-        pro_norm(st, p.x_o, t_o, L.post_norm, nullptr, S.hidden, S.eps);
-        LL_STAMP(ST_GU_PRO);
         const uint32_t t_act = ++st.gen;
-        gemv_phase(st, L.gu, EPI_SWIGLU, p.x_act, nullptr, t_act);
+        gemv_phase(st, L.gu, in_norm(p.x_o, t_o, L.post_norm, S.hidden, S.eps), EPI_SWIGLU, p.x_act, nullptr, t_act);
         LL_STAMP(ST_GU);
         // ---- down
-        pro_ll(st, p.x_act, t_act, S.inter);
-        LL_STAMP(ST_DOWN_PRO);
         const uint32_t t_down = ++st.gen;
-        gemv_phase(st, L.down, EPI_RAW, p.x_down, nullptr, t_down);
+        gemv_phase(st, L.down, in_ll(p.x_act, t_act), EPI_RAW, p.x_down, nullptr, t_down);
         LL_STAMP(ST_DOWN);
         add = p.x_down; add_tag = t_down;
     }
-    if (io.want_final) pro_norm(st, add, add_tag, S.final_norm, io.hidden_out, S.hidden, S.eps);
+    StackOut o; o.add = add; o.tag = add_tag;
+    return o;
 }
 
 // ---- producer side: the same program, streaming instead of computing ---------------------------------------------------------
@@ -855,12 +925,12 @@ __device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint3
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
-    float* sc = reinterpret_cast<float*>(s.xfrag);            // [V]  (aliases the digit planes: re-zeroed below)
-    float* pe = sc + SAMPLE_MAXV;                              // [V]
-    unsigned short* cand = reinterpret_cast<unsigned short*>(pe + SAMPLE_MAXV);   // [V]
+    float* sc = reinterpret_cast<float*>(s.stage);            // [V]  (the attention staging buffer is idle between passes)
+    float* pe = sc + LL_SAMPLE_MAXV;                           // [V]
+    unsigned short* cand = reinterpret_cast<unsigned short*>(pe + LL_SAMPLE_MAXV);   // [V]
     SampleScratch scr;
     scr.sc = sc; scr.pe = pe; scr.cand = cand;
-    scr.hist = reinterpret_cast<unsigned int*>(cand + SAMPLE_MAXV);                  // [256]
+    scr.hist = reinterpret_cast<unsigned int*>(cand + LL_SAMPLE_MAXV);               // [256]
     scr.redf = s.red; scr.redi = s.ibuf; scr.sh_i = s.ibuf + 32;
     const int V4 = V >> 2;
     for (int k4 = tid; k4 < V4; k4 += LL_CTHREADS) {
@@ -876,9 +946,7 @@ __device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint3
     cbar();
     const float u = sp.do_sample ? hash_uniform(sp.seed, step, g, 0) : 0.f;
     const int choice = sample_core<LL_CTHREADS>(scr, V, sp, u, tid, [] { cbar(); });
-    // the scratch lived in the digit planes: lanes 16..31 of every group must read as zero again
-    for (int i = tid; i < (LL_MAXK / 64) * 16; i += LL_CTHREADS) s.xfrag[(i >> 4) * 32 + 16 + (i & 15)] = make_uint4(0, 0, 0, 0);
-    cbar();
+    cbar();                                    // scratch reads done before the next pass stages K/V rows there
     return choice;
 }
 
@@ -887,16 +955,15 @@ __device__ __noinline__ int cp_pass(CState& st, const float* src, int pos, int g
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, Hc = p.cp.hidden, G = p.n_groups;
-    pro_plain(src, p.emb_dim);
     const uint32_t t_proj = ++st.gen;
-    gemv_phase(st, s.hd[0], EPI_RAW, p.x_proj, nullptr, t_proj);
-    for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS) reinterpret_cast<float4*>(s.resid)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
-    StackIO io{p.x_proj, t_proj, g_head >= 0, nullptr};
-    stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, io);
+    gemv_phase(st, s.hd[0], in_plain(src), EPI_RAW, p.x_proj, nullptr, t_proj);
+    for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
+        reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, p.x_proj, t_proj);
     if (g_head < 0) return 0;
     const uint32_t t_head = ++st.gen;
     float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
-    gemv_phase(st, s.hd[2 + g_head], EPI_RAW, p.x_head, lg, t_head);
+    gemv_phase(st, s.hd[2 + g_head], in_norm(so.add, so.tag, p.cp.final_norm, Hc, p.cp.eps), EPI_RAW, p.x_head, lg, t_head);
     int c = sample_here(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g_head + 1);
     const long long fo = (long long)step * G + g_head + 1;
     const bool rec = (blockIdx.x == 0 && tid == 0);
@@ -946,7 +1013,6 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         mbar_init(smem_u32(s.kvbar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < (LL_MAXK / 64) * 32; i += LL_THREADS) s.xfrag[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) s.ibuf[63] = 0;
     __syncthreads();
 
@@ -968,18 +1034,20 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
 
     // =============================== consumers ================================================================
     CState st;
-    st.seq = 0; st.nstamp = 0; st.red_par = 0; st.kv_par = 0; st.nsplit = 1; st.chunk = 128;
+    st.seq = 0; st.nstamp = 0; st.red_par = 0; st.kv_par = 0; st.res_par = 0; st.pp = 0; st.nsplit = 1; st.chunk = 128;
     st.gen = *reinterpret_cast<volatile unsigned int*>(p.state);
     LL_STAMP(ST_START);
     if (p.mode == LL_MODE_STACK) {
         const int pos = __ldcg(p.pos);
         for (int k4 = tid; k4 < (p.talker.hidden >> 2); k4 += LL_CTHREADS)
-            reinterpret_cast<float4*>(s.resid)[k4] = __ldcg(reinterpret_cast<const float4*>(p.x_in) + k4);
-        StackIO io{nullptr, 0u, p.hidden_out != nullptr || p.head.w != nullptr, p.hidden_out};
-        stack_consume(st, p.talker, s.lay, pos, io);
+            reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = __ldcg(reinterpret_cast<const float4*>(p.x_in) + k4);
+        const StackOut so = stack_consume(st, p.talker, s.lay, pos, nullptr, 0u);
         if (p.head.w) {
             const uint32_t t_head = ++st.gen;
-            gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits_out, t_head);
+            gemv_phase(st, s.hd[1], in_norm(so.add, so.tag, p.talker.final_norm, p.talker.hidden, p.talker.eps, p.hidden_out), EPI_RAW,
+                       p.x_head, p.logits_out, t_head);
+        } else if (p.hidden_out) {
+            final_norm_only(st, so.add, so.tag, p.talker.final_norm, p.hidden_out, p.talker.hidden, p.talker.eps);
         }
         LL_STAMP(ST_END);
     } else {
@@ -1022,15 +1090,14 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 const float4 b = __ldg(reinterpret_cast<const float4*>(last) + tid);
                 const float4 c = __ldcg(reinterpret_cast<const float4*>(tr) + tid);
                 xn.x = (xn.x + b.x) + c.x; xn.y = (xn.y + b.y) + c.y; xn.z = (xn.z + b.z) + c.z; xn.w = (xn.w + b.w) + c.w;
-                reinterpret_cast<float4*>(s.resid)[tid] = xn;
+                reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[tid] = xn;
                 if (cta == 0) reinterpret_cast<float4*>(p.x)[tid] = xn;
             }
         }
         // ---- talker decode step
-        StackIO io{nullptr, 0u, true, p.hidden};
-        stack_consume(st, p.talker, s.lay, pos_t, io);
+        const StackOut so = stack_consume(st, p.talker, s.lay, pos_t, nullptr, 0u);
         const uint32_t t_head = ++st.gen;
-        gemv_phase(st, s.hd[1], EPI_RAW, p.x_head, p.logits, t_head);
+        gemv_phase(st, s.hd[1], in_norm(so.add, so.tag, p.talker.final_norm, H, p.talker.eps, p.hidden), EPI_RAW, p.x_head, p.logits, t_head);
         LL_STAMP(ST_END);
         // state other CTAs read at the start of the launch is only updated here, after the last all-to-all exchange
         if (rec) {
@@ -1069,15 +1136,8 @@ static int check_stack(const q3t_stack& st, int grid) {
     Q3T_REQUIRE(st.head_dim == 128, "frame_ll: head_dim must be 128");
     Q3T_REQUIRE(st.n_heads == st.n_kv_heads || st.n_heads == 2 * st.n_kv_heads, "frame_ll: H/Hkv must be 1 or 2");
     Q3T_REQUIRE(st.hidden % 256 == 0 && st.inter % 256 == 0, "frame_ll: dims % 256");
-    Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_KV_GROUP0 * 64, "frame_ll: dims too large");
+    Q3T_REQUIRE(st.hidden <= LL_MAXH && st.inter <= LL_MAXK && st.n_heads * st.head_dim <= LL_MAXK, "frame_ll: dims too large");
     Q3T_REQUIRE(st.n_kv_heads <= grid, "frame_ll: more kv heads than CTAs");
-    {   // parked attention records of the merger CTA must fit the digit groups the O-projection prologue leaves alone
-        const int ms = grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit;
-        Q3T_REQUIRE((LL_MAXK / 64 - st.n_heads * st.head_dim / 64) * 64 >= (ms - 1) * (st.n_heads / st.n_kv_heads) * LL_REC,
-                    "frame_ll: attention merge scratch too small for this many splits");
-    }
-    Q3T_REQUIRE(st.max_pages <= 64 * (grid / st.n_kv_heads < ll_tune().msplit ? grid / st.n_kv_heads : ll_tune().msplit),
-                "frame_ll: context too long for the per-CTA page-id table");
     const int qkv_n = (st.n_heads + 2 * st.n_kv_heads) * st.head_dim;
     const int n_max = 2 * st.inter > qkv_n ? 2 * st.inter : qkv_n;
     const long long t1 = ((long long)(n_max / 16) + grid - 1) / grid * (st.hidden / 256);
@@ -1166,7 +1226,7 @@ int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream) {
     Q3T_REQUIRE(f->talker.n_layers + f->cp.n_layers <= LL_MAXLAYERS && f->talker.n_layers <= 64 && f->n_groups + 1 <= LL_MAXHEADS,
                 "frame_ll: too many layers / code groups");
     Q3T_REQUIRE(f->ll_work && f->ll_state && f->cp_heads_dev && f->cp_embeddings_dev, "frame_ll: workspace / device tables missing");
-    Q3T_REQUIRE(f->talker_vocab <= SAMPLE_MAXV && f->cp_vocab <= SAMPLE_MAXV && f->talker_vocab % 16 == 0 && f->cp_vocab % 16 == 0,
+    Q3T_REQUIRE(f->talker_vocab <= LL_SAMPLE_MAXV && f->cp_vocab <= LL_SAMPLE_MAXV && f->talker_vocab % 16 == 0 && f->cp_vocab % 16 == 0,
                 "frame_ll: vocabulary size");
     Q3T_REQUIRE(f->cp_proj.K == f->talker.hidden && f->cp_proj.N == f->cp.hidden,
                 "frame_ll: cp_proj shape (embedding width must equal the talker hidden size)");
