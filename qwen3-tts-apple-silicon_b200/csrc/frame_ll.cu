@@ -162,6 +162,9 @@ __device__ __forceinline__ void ll_ld4n(const u64* const (&p)[NV], const bool (&
         }
         if (all) break;
         if (++spins > LL_SPIN_LIMIT) ll_fail(state, 0x100u | (tag & 0xffu));
+#if LL_POLL_SLEEP > 0
+        __nanosleep(LL_POLL_SLEEP);
+#endif
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             if (!ok[i]) { ll_ld2(p[i], w[i][0], w[i][1]); ll_ld2(p[i] + 2, w[i][2], w[i][3]); }
@@ -192,6 +195,9 @@ extern __shared__ __align__(128) unsigned char ll_smem_raw[];
 
 #ifndef LL_FN
 #define LL_FN __forceinline__
+#endif
+#ifndef LL_POLL_SLEEP
+#define LL_POLL_SLEEP 0                          // ns between poll rounds of the LL words (experiments: 0 is fastest)
 #endif
 
 // per-CTA view of one W8 matrix / one layer, built once per launch in shared memory: no phase starts with a dependent
@@ -425,11 +431,23 @@ __device__ LL_FN void gemv_phase(CState& st, const MatD& W, const PhaseIn& in, i
     uint4* dig = s.dig + warp * 64;
     float* xsum = s.xsum + warp * 4;
     float* xscl = s.xscl + warp * 4;
+    // 16 warps, nkc chunks: when nkc divides 16 a warp keeps ONE chunk for the whole phase and warps kc, kc + nkc, ... share
+    // it - warp kc polls and converts (into its own area), the others wait on named barrier 2 + kc and read that area.
+    const bool share = (LL_CWARPS % nkc) == 0 && nkc < LL_CWARPS;
     // a norm phase walks every chunk even where this CTA has no tile: the residual stream must stay complete
     const int jmax = norm ? (nt > nkc ? nt : nkc) : nt;
     int kc = warp % nkc, cur = -1;           // tile j covers k-chunk j % nkc (j = warp, warp + 16, ...)
     const int kstep = LL_CWARPS % nkc;
     for (int j = warp; j < jmax; j += LL_CWARPS) {
+        const bool mine = !share || warp < nkc;          // this warp polls and converts chunk kc itself
+        if (kc != cur && !mine) {
+            if (j < nt) {
+                const int users = ((nt < LL_CWARPS ? nt : LL_CWARPS) - kc + nkc - 1) / nkc;
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + kc), "r"(32 * users) : "memory");
+                dig = s.dig + kc * 64; xsum = s.xsum + kc * 4; xscl = s.xscl + kc * 4;
+            }
+            cur = kc;
+        }
         if (kc != cur) {
             const int k4a = kc * 64 + lane, k4b = k4a + 32;
             float4 va, vb;
@@ -470,6 +488,10 @@ __device__ LL_FN void gemv_phase(CState& st, const MatD& W, const PhaseIn& in, i
                 emit_digits(dig, xsum, xscl, va, lane, lane);
                 emit_digits(dig, xsum, xscl, vb, lane + 32, lane);
                 __syncwarp();
+                if (share) {
+                    const int users = ((nt < LL_CWARPS ? nt : LL_CWARPS) - kc + nkc - 1) / nkc;
+                    if (users > 1) asm volatile("bar.arrive %0, %1;" ::"r"(2 + kc), "r"(32 * users) : "memory");
+                }
             }
             cur = kc;
         }
@@ -734,13 +756,12 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             const unsigned char* vcol = kv_s + 4096 + dh * 128 + lane * 4;
 #pragma unroll
             for (int j = 0; j < TPG; ++j) {
+                // unconditional load (the 16 of them pipeline); a stale slot may hold anything, its weight is exactly zero
                 const int t = tg * TPG + j;
-                if (t < nr) {
-                    const float pv = __shfl_sync(0xffffffffu, pj, j);
-                    const uint32_t vv = *reinterpret_cast<const uint32_t*>(vcol + (t >> 4) * 8192 + (t & 15) * 256);
-                    acc0 = fmaf(pv, bf16lo(vv), acc0);
-                    acc1 = fmaf(pv, bf16hi(vv), acc1);
-                }
+                const float pv = __shfl_sync(0xffffffffu, pj, j);
+                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vcol + (t >> 4) * 8192 + (t & 15) * 256);
+                acc0 = fmaf(pv, t < nr ? bf16lo(vv) : 0.f, acc0);
+                acc1 = fmaf(pv, t < nr ? bf16hi(vv) : 0.f, acc1);
             }
         }
         if (rd + 1 < n_rounds) cbar();                                   // staged rows and scores are read
