@@ -754,6 +754,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             acc0 *= corr; acc1 *= corr;
             m_run = mn;
             const unsigned char* vcol = kv_s + 4096 + dh * 128 + lane * 4;
+            if (tg * TPG < nr) {                                         // (a code-predictor pass never has more than 17 tokens)
 #pragma unroll
             for (int j = 0; j < TPG; ++j) {
                 // unconditional load (the 16 of them pipeline); a stale slot may hold anything, its weight is exactly zero
@@ -762,6 +763,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
                 const uint32_t vv = *reinterpret_cast<const uint32_t*>(vcol + (t >> 4) * 8192 + (t & 15) * 256);
                 acc0 = fmaf(pv, t < nr ? bf16lo(vv) : 0.f, acc0);
                 acc1 = fmaf(pv, t < nr ? bf16hi(vv) : 0.f, acc1);
+            }
             }
         }
         if (rd + 1 < n_rounds) cbar();                                   // staged rows and scores are read

@@ -166,8 +166,19 @@ def main():
         d = [(cp[i + 1] - cp[i]) / 1e3 for i in range(len(cp) - 1)]
         print("cp pass us:", " ".join(f"{v:.1f}" for v in d))
     if os.environ.get("Q3T_LL_FINE"):
-        # code-predictor layers (first 5*17 layers of the launch): per-layer breakdown over the CP part
-        report(ids, ns, (0, 1, 73), "frame (CP passes + talker step mixed, per 'layer' average)", skip_first=0)
+        # code-predictor passes only: the stamps between the first and the last cp_pass mark of a CTA, averaged per pass
+        import numpy as np
+        ids2, ns2 = np.zeros_like(ids), np.zeros_like(ns)
+        for c in (0, 1, 73, G - 1):
+            n_c = int((ns[c] > 0).sum())
+            marks = [i for i in range(n_c) if ids[c, i] == 12]
+            if len(marks) >= 2:
+                a, b = marks[0], marks[-1] + 1
+                ids2[c, :b - a] = ids[c, a:b]; ns2[c, :b - a] = ns[c, a:b]
+                rows = {}
+                report(ids2, ns2, (c,), "", skip_first=0, quiet=rows)
+                npass = len(marks) - 1
+                print(f"cp-only cta {c:3d} ({npass} passes, us per pass): " + "  ".join(f"{k}={float(v) / npass:.2f}" for k, v in rows[c].items()))
     e.fa.ll_timing = 0
     s.record()
     for _ in range(20):
