@@ -217,14 +217,22 @@ class CodecDecoder:
         L.check(self.lib.q3t_clamp_pcm16(wav.data_ptr(), wav.numel(), out.data_ptr(), 0, L.stream_ptr()), "clamp")
         return out
 
-    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+    def decode_interval(self, codes: torch.Tensor, start: int, end: int) -> torch.Tensor:
+        """Samples of frames [start, end) of codes [B,16,T'] (T' >= end): one vocoder call over the interval plus
+        `left_context` frames of history, the history's samples dropped (one step of the chunked decode below; the
+        streaming path of BASELINE config 3 calls it once per interval as the frames arrive)."""
+        k = self.k
+        ctx = k.left_context if start - k.left_context > 0 else start
+        wav = self.forward(codes[..., start - ctx:end])
+        return wav[:, ctx * k.hop:]
+
+    def decode(self, codes: torch.Tensor, chunk_size: Optional[int] = None) -> torch.Tensor:
         """Chunked decode (300-frame chunks, 25 frames of left context; cousin :3780-3790). codes [B,16,T] -> [B, n]."""
         k = self.k
+        chunk = chunk_size or k.chunk_size
         wavs, start, T = [], 0, codes.shape[-1]
         while start < T:
-            end = min(start + k.chunk_size, T)
-            ctx = k.left_context if start - k.left_context > 0 else start
-            wav = self.forward(codes[..., start - ctx:end])
-            wavs.append(wav[:, ctx * k.hop:])
+            end = min(start + chunk, T)
+            wavs.append(self.decode_interval(codes, start, end))
             start = end
         return torch.cat(wavs, -1)

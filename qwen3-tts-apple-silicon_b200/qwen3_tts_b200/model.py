@@ -145,6 +145,32 @@ class Model:
             codes = codes[: int(eos[0, 0])]
         return codes
 
+    def stream_codes(self, prefill: torch.Tensor, trailing: torch.Tensor, max_frames: int, interval: int = 25):
+        """Streaming generation (BASELINE config 3): frames are produced one persistent launch at a time and every
+        `interval` frames the codec decodes the new ones with its left context.  Yields (codes [n, 16], wav [n * hop])
+        per interval; the concatenated pieces are bit-identical to generate_codes() followed by
+        CodecDecoder.decode(chunk_size=interval).  One host synchronisation per interval (the EOS check)."""
+        e = self.engine
+        assert max_frames <= e.max_frames and interval >= 1
+        e.prefill(prefill[None], None, trailing[None])
+        eos_id = self.cfg.talker.codec_eos_id
+        start = 0
+        while start < max_frames:
+            end = min(start + interval, max_frames)
+            for _ in range(end - start):
+                e._run("frame")
+            new = e.codes[0, start:end]
+            eos = (new[:, 0] == eos_id).nonzero()
+            stop = eos.numel() > 0
+            if stop:
+                end = start + int(eos[0, 0])
+            if end > start:
+                wav = self.codec.decode_interval(e.codes[0, :end].t()[None].contiguous(), start, end)[0]
+                yield e.codes[0, start:end], wav
+            if stop:
+                return
+            start = end
+
     def decode(self, codes: torch.Tensor) -> torch.Tensor:
         """codes [T, 16] -> wav [n] on device."""
         if codes.shape[0] == 0:
@@ -156,8 +182,9 @@ class Model:
                  lang_code: str = "auto", ref_audio: Optional[str] = None, ref_text: Optional[str] = None,
                  temperature: Optional[float] = None, top_k: int = 50, top_p: float = 1.0,
                  repetition_penalty: float = 1.05, max_tokens: int = 1200, seed: int = 0, verbose: bool = False,
-                 **kwargs) -> Iterator[GenerationResult]:
-        """One utterance -> one result (the reference consumes only audio_000.wav, io.py:156).
+                 stream: bool = False, streaming_interval: float = 2.0, **kwargs) -> Iterator[GenerationResult]:
+        """One utterance -> one result (the reference consumes only audio_000.wav, io.py:156); with `stream=True` one
+        result per `streaming_interval` seconds of audio as it is generated (segment_idx counts the pieces).
         `speed` is accepted and ignored exactly like an unknown library kwarg; `temperature=0`
         or `None` with greedy=True selects the greedy parity path."""
         t0 = time.perf_counter()
@@ -178,6 +205,17 @@ class Model:
         ids = self.chat_ids(text)
         prefill, trailing = self.build_prefill(ids, ins, speaker, language, speaker_vec, streaming)
         max_frames = min(max_tokens, self.engine.max_frames)
+        if stream:
+            interval = max(1, int(round(streaming_interval * self.sample_rate / self.cfg.codec.hop)))
+            for i, (c, w) in enumerate(self.stream_codes(prefill, trailing, max_frames, interval)):
+                audio = w.float().cpu().numpy()
+                dt = time.perf_counter() - t0
+                dur = audio.shape[0] / self.sample_rate
+                yield GenerationResult(audio=audio, sample_rate=self.sample_rate, samples=int(audio.shape[0]), segment_idx=i,
+                                       token_count=int(c.shape[0]), audio_duration=dur, processing_time_seconds=dt,
+                                       real_time_factor=(dur / dt if dt > 0 else 0.0), codes=c.cpu().numpy())
+                t0 = time.perf_counter()
+            return
         codes = self.generate_codes(prefill, trailing, max_frames)
         wav = self.decode(codes)
         audio = wav.float().cpu().numpy()

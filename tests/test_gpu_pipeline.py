@@ -340,3 +340,27 @@ def test_bf16_chaining_between_batched_kernels_is_bit_identical(cuda, monkeypatc
         outs.append((e.logits.clone(), codes, e.launches_per_frame))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert outs[0][2] < outs[1][2], "the chained path must need fewer launches per frame"
+
+
+def test_streaming_generation_equals_offline_chunked_decode(small_setup):
+    """BASELINE config 3 (streaming, frame by frame): the pieces yielded every `interval` frames - codes and audio -
+    concatenate to exactly what the offline path gives (same greedy codes; codec chunked with chunk_size = interval and
+    the usual left context), for an interval that divides the frame count and one that does not."""
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 13, 31)
+    pre, tr = oracle.build_prefill(ids, streaming=True, speaker_vec=torch.randn(cfg.talker.hidden_size, generator=torch.Generator().manual_seed(5)) * 0.02)
+    model.engine.set_sampling(do_sample=False)
+    n = 40
+    codes_off = model.generate_codes(pre.cuda(), tr.cuda(), n)
+    for interval in (8, 25, 27):
+        pieces = list(model.stream_codes(pre.cuda(), tr.cuda(), n, interval))
+        assert all(0 < c.shape[0] <= interval for c, _ in pieces)
+        codes_s = torch.cat([c for c, _ in pieces], 0)
+        wav_s = torch.cat([w for _, w in pieces], 0)
+        assert torch.equal(codes_s, codes_off)
+        wav_off = model.codec.decode(codes_off.t()[None].contiguous(), chunk_size=interval)[0]
+        assert torch.equal(wav_s, wav_off)
+        assert bool(torch.isfinite(wav_s).all())
+    # the reference-facing generator with stream=True yields one result per interval
+    res = list(model.generate("hello there", voice="ryan", greedy=True, stream=True, streaming_interval=1.0, max_tokens=30))
+    assert len(res) >= 2 and sum(r.token_count for r in res) <= 30 and all(r.samples > 0 for r in res)
