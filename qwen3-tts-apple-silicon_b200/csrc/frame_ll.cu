@@ -734,12 +734,14 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
     const int chunk = st.chunk, nsplit = st.nsplit;
     const int cta = blockIdx.x;
     if (cta >= S.n_kv * nsplit) return;
+#ifndef LL_NO_TINY
     if (nsplit == 1 && pos < 32) {
         const uint32_t par = st.kv_par;
         st.kv_par ^= 1;                           // every thread keeps the parity; only the working warps wait
         if ((threadIdx.x >> 5) < REP + 2) attn_tiny<REP>(S, LD, layer, pos, ll_qkv, tag_qkv, ll_attnf, tag_out, par);
         return;
     }
+#endif
     const int split = cta / S.n_kv, kvh = cta - split * S.n_kv;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ctx = pos + 1, s0 = split * chunk, s1 = min(ctx, s0 + chunk), n = s1 - s0;
