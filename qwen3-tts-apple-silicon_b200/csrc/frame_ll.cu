@@ -36,7 +36,8 @@ typedef unsigned long long u64;
 
 constexpr int LL_CWARPS = 16;
 constexpr int LL_CTHREADS = LL_CWARPS * 32;      // 512 consumers
-constexpr int LL_THREADS = LL_CTHREADS + 32;     // + producer warp
+constexpr int LL_THREADS = LL_CTHREADS + 64;     // + producer warp + L2 prefetch warp (18 warps cost no registers: the cap
+                                                 // of 96 comes from five warps on one scheduler partition either way)
 #ifndef LL_NSLOT_N
 #define LL_NSLOT_N 32
 #endif
@@ -1016,7 +1017,9 @@ __device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const Laye
 // ---- producer side: the same program, streaming instead of computing ---------------------------------------------------------
 struct Producer {
     unsigned int* state; int lane; uint32_t seq; int pf_dist;
-    // lanes 0..LL_PLANES-1: TMA copies into the ring; lane LL_PLANES: L2 prefetch of the same tiles, pf_dist tiles ahead
+    // lane ids 0..LL_PLANES-1 (producer warp): TMA copies into the ring; id LL_PLANES (lane 0 of the prefetch warp, its own
+    // warp so that its spin does not time-slice with the TMA lanes): L2 prefetch of the same tiles, matrix by matrix, as long
+    // as the matrix starts no more than pf_dist tiles ahead of the TMA cursor - HBM keeps streaming while the ring is full
     __device__ LL_FN void stream(const MatD& W) {
         const LLSmem s = ll_smem();
         const uint8_t* src = W.w + (size_t)W.rb * W.nkc * Q3T_TILE_BYTES;
@@ -1148,10 +1151,11 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
     if (tid == 0) s.ibuf[63] = 0;
     __syncthreads();
 
-    if (warp == LL_CWARPS) {
-        // =========================== producer ================================================================
-        if (lane < LL_PLANES + (p.pf_dist > 0 ? 1 : 0)) {
-            Producer pr{p.state, lane, 0u, p.pf_dist};
+    if (warp >= LL_CWARPS) {
+        // =========================== producer / L2 prefetcher ================================================
+        const int role = warp == LL_CWARPS ? (lane < LL_PLANES ? lane : -1) : (lane == 0 && p.pf_dist > 0 ? LL_PLANES : -1);
+        if (role >= 0) {
+            Producer pr{p.state, role, 0u, p.pf_dist};
             if (p.mode == LL_MODE_STACK) {
                 pr.stack(s.lay, nA);
                 if (p.head.w) pr.stream(s.hd[1]);
