@@ -1,0 +1,31 @@
+"""The persistent kernel's attention geometry is chosen from the context length: at the default setting (64-token chunks,
+up to 16 splits per kv head) the small parity cases never reach a chunk of several 64-token ROUNDS (needs ctx > 1024) or a
+merger that collects 15 split records.  The geometry is read once per process from the environment (profiling aid,
+csrc/frame_ll.cu:ll_tune), so these cases re-run the parity tests of test_gpu_pipeline.py in a child process:
+
+  Q3T_LL_MAXSPLIT=1   one split per kv head: every context > 64 tokens is walked in rounds (online rescale between rounds)
+  Q3T_LL_MAXSPLIT=2   two splits, each several rounds long, merged by split 0
+  Q3T_LL_CHUNK=16     16-token chunks: up to 16 splits per kv head, the merger polls the records in several rounds
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = "teacher_forced_logits_and_argmax or free_running_greedy or persistent_kernel_and_multikernel or streaming_trailing_text"
+
+
+@pytest.mark.parametrize("env", [{"Q3T_LL_MAXSPLIT": "1"}, {"Q3T_LL_MAXSPLIT": "2"}, {"Q3T_LL_CHUNK": "16"}],
+                         ids=["one-split-rounds", "two-splits-rounds", "sixteen-splits"])
+def test_parity_cases_under_other_attention_geometries(cuda, env):
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_pipeline.py"), "-m", "gpu", "-x", "-q",
+                        "-k", CASES, "-p", "no:cacheprovider"], cwd=ROOT, env=e, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-2000:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "failed" not in r.stdout, tail
