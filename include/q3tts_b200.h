@@ -274,6 +274,11 @@ typedef struct {
     void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
     unsigned long long* ll_timing;  /* optional profiling stamps (profiling build only), or NULL */
     void* gemm_xb2;        /* optional second bf16 scratch [B, max K]: attention output and SwiGLU activations stay bf16 */
+    /* optional (persistent-kernel path): DEVICE array [G-1] of device tables; table g = cp_proj applied to every row of the
+     * embedding table that feeds code-predictor pass g (g = 0: codec_embedding [V, Hc]; g >= 1: cp_embeddings[g-1] [Vc, Hc]),
+     * fp32.  The input of a pass is a table row - a function of one sampled code - so its projection is a lookup; with the
+     * tables the kernel skips one contraction phase per pass.  NULL = project in the kernel. */
+    const float* const* cp_proj_rows_dev;
 } q3t_frame_args;
 
 /* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).

@@ -79,6 +79,7 @@ struct LLParams {
     // ---- frame mode
     q3t_w8 codec_head, cp_proj; const q3t_w8* cp_heads;          // DEVICE array [G-1]
     const float* codec_embedding; const float* const* cp_embeddings;   // DEVICE array [G-1]
+    const float* const* cp_proj_rows;            // optional DEVICE array [G-1]: projected embedding tables (see q3t_frame_args)
     int emb_dim, talker_vocab, cp_vocab, n_groups;
     q3t_sampling talker_sp, cp_sp;
     float* x; float* hidden; float* logits; float* cp_logits; int keep_cp_logits;
@@ -234,6 +235,7 @@ struct LLSmem {
     uint64_t* full;         // [LL_NSLOT]
     uint64_t* empty;        // [LL_NSLOT]
     uint64_t* kvbar;        // attention K/V staging (cp.async.bulk completion)
+    const float** prows;    // [LL_MAXHEADS] projected embedding tables of the code-predictor passes (optional)
 };
 constexpr size_t LL_STAGE_BYTES = 32768;
 constexpr size_t LL_ATT_FLOATS = 4 * 128 + 8 * 128 + 32;
@@ -256,7 +258,8 @@ constexpr size_t LL_OFF_PAGES = LL_OFF_IBUF + 64 * 4;
 constexpr size_t LL_OFF_FULL = LL_OFF_PAGES + 64 * 4;
 constexpr size_t LL_OFF_EMPTY = LL_OFF_FULL + LL_NSLOT * 8;
 constexpr size_t LL_OFF_KVBAR = LL_OFF_EMPTY + LL_NSLOT * 8;
-constexpr size_t LL_SMEM_BYTES = LL_OFF_KVBAR + 8;
+constexpr size_t LL_OFF_PROWS = LL_OFF_KVBAR + 8;
+constexpr size_t LL_SMEM_BYTES = LL_OFF_PROWS + LL_MAXHEADS * 8;
 static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
 static_assert(LL_OFF_STAGE % 128 == 0 && LL_OFF_DIG % 16 == 0, "frame_ll: staging / digit alignment");
 
@@ -283,6 +286,7 @@ __device__ __forceinline__ LLSmem ll_smem() {
     s.full = reinterpret_cast<uint64_t*>(b + LL_OFF_FULL);
     s.empty = reinterpret_cast<uint64_t*>(b + LL_OFF_EMPTY);
     s.kvbar = reinterpret_cast<uint64_t*>(b + LL_OFF_KVBAR);
+    s.prows = reinterpret_cast<const float**>(b + LL_OFF_PROWS);
     return s;
 }
 
@@ -1086,15 +1090,24 @@ __device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint3
 }
 
 // one code-predictor pass: projected input -> 5 layers (-> head -> sampled code)
-__device__ __noinline__ int cp_pass(CState& st, const float* src, int pos, int g_head, int step) {
+// prow != nullptr: the projected input row is a table lookup (no projection phase in this pass)
+__device__ __noinline__ int cp_pass(CState& st, const float* src, const float* prow, int pos, int g_head, int step) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, Hc = p.cp.hidden, G = p.n_groups;
-    const uint32_t t_proj = ++st.gen;
-    gemv_phase(st, s.hd[0], in_plain(src), EPI_RAW, p.x_proj, nullptr, t_proj);
-    for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
-        reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, p.x_proj, t_proj);
+    const u64* first_add = nullptr;
+    uint32_t t_proj = 0u;
+    if (prow) {
+        for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
+            reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = __ldcg(reinterpret_cast<const float4*>(prow) + k4);
+    } else {
+        t_proj = ++st.gen;
+        gemv_phase(st, s.hd[0], in_plain(src), EPI_RAW, p.x_proj, nullptr, t_proj);
+        for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
+            reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        first_add = p.x_proj;
+    }
+    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, first_add, t_proj);
     if (g_head < 0) return 0;
     const uint32_t t_head = ++st.gen;
     float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
@@ -1142,6 +1155,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         if (tid == 64) build_mat(s.hd[0], p_in.cp_proj, cta, gridDim.x);
         if (tid == 65) build_mat(s.hd[1], p_in.codec_head, cta, gridDim.x);
         if (tid >= 66 && tid < 66 + G - 1) build_mat(s.hd[2 + tid - 66], p_in.cp_heads[tid - 66], cta, gridDim.x);
+        if (p_in.cp_proj_rows && tid >= 96 && tid < 96 + G - 1) s.prows[tid - 96] = p_in.cp_proj_rows[tid - 96];
     } else if (tid == 65 && p_in.head.w) build_mat(s.hd[1], p_in.head, cta, gridDim.x);
     if (tid == 0) {
         for (int i = 0; i < LL_NSLOT; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
@@ -1161,7 +1175,10 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 if (p.head.w) pr.stream(s.hd[1]);
             } else {
                 pr.stream(s.hd[0]); pr.stack(s.lay + nA, nB);
-                for (int g = 0; g < G - 1; ++g) { pr.stream(s.hd[0]); pr.stack(s.lay + nA, nB); pr.stream(s.hd[2 + g]); }
+                for (int g = 0; g < G - 1; ++g) {
+                    if (!p.cp_proj_rows) pr.stream(s.hd[0]);
+                    pr.stack(s.lay + nA, nB); pr.stream(s.hd[2 + g]);
+                }
                 pr.stack(s.lay, nA); pr.stream(s.hd[1]);
             }
         }
@@ -1205,7 +1222,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         LL_STAMP(ST_SAMPLE);
         // ---- code predictor: position 0 = projected talker hidden, then one pass per residual codebook.
         // The next talker input is accumulated on the way, in registers: emb0[c0] + emb1[c1] + ... in order
-        cp_pass(st, p.hidden, 0, -1, step);
+        cp_pass(st, p.hidden, nullptr, 0, -1, step);
         LL_STAMP(ST_CP_PASS);
         float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int g = 0; g < G - 1; ++g) {
@@ -1214,7 +1231,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(row) + tid);
                 if (g == 0) xn = r4; else { xn.x += r4.x; xn.y += r4.y; xn.z += r4.z; xn.w += r4.w; }
             }
-            code = cp_pass(st, row, g + 1, g, step);
+            code = cp_pass(st, row, p.cp_proj_rows ? s.prows[g] + (size_t)code * p.cp.hidden : nullptr, g + 1, g, step);
             LL_STAMP(ST_CP_PASS);
         }
         // ---- next talker input: running sum + last code's row, then the trailing text row
@@ -1375,7 +1392,7 @@ int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream) {
     carve(p, f->ll_work, &f->talker, &f->cp);
     p.state = f->ll_state; p.timing = f->ll_timing;
     p.codec_head = f->codec_head; p.cp_proj = f->cp_proj; p.cp_heads = f->cp_heads_dev;
-    p.codec_embedding = f->codec_embedding; p.cp_embeddings = f->cp_embeddings_dev;
+    p.codec_embedding = f->codec_embedding; p.cp_embeddings = f->cp_embeddings_dev; p.cp_proj_rows = f->cp_proj_rows_dev;
     p.emb_dim = f->talker.hidden; p.talker_vocab = f->talker_vocab; p.cp_vocab = f->cp_vocab; p.n_groups = f->n_groups;
     p.talker_sp = f->talker_sp; p.cp_sp = f->cp_sp;
     p.x = f->x; p.hidden = f->hidden; p.logits = f->logits; p.cp_logits = f->cp_logits; p.keep_cp_logits = f->keep_cp_logits;

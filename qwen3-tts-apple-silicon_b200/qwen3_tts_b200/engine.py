@@ -133,6 +133,7 @@ class TalkerEngine:
         self._cp_heads_dev = torch.frombuffer(bytearray(bytes(memoryview(self._cp_heads).cast("B"))), dtype=torch.uint8).to(dev)
         fa.cp_heads_dev = self.keep(self._cp_heads_dev)
         fa.cp_vocab, fa.n_groups = c.vocab_size, self.G
+        self._cp_proj_tabs = None               # built lazily (batch 1, persistent kernel): see _ensure_cp_proj_rows
         # text side (prefill only)
         self.text_embedding = fp("talker.text_embedding")
         self.tp_fc1 = w8(["talker.text_projection.fc1"], "talker.text_projection.fc1.bias")
@@ -237,6 +238,23 @@ class TalkerEngine:
             self.fa.forced_codes = self.forced.data_ptr()
         self._graphs = {}
 
+    def _ensure_cp_proj_rows(self):
+        """Projected embedding tables for the persistent kernel (q3t_frame_args.cp_proj_rows_dev): the input of
+        code-predictor pass g is cp_proj(table_g[code]), a function of one sampled code, so the projection of every table
+        row is computed once here with the same W8 GEMV the kernel would run (33.8 k rows, 0.14 GB at full size) and each
+        pass starts from a lookup instead of a contraction phase.  Q3T_CP_PROJ_TABLES=0 keeps the in-kernel projection."""
+        if self._cp_proj_tabs is not None or self.B != 1 or os.environ.get("Q3T_CP_PROJ_TABLES", "1") == "0":
+            return
+        tabs = [self.codec_embedding] + self.cp_embeddings[: self.G - 2]
+        self._cp_proj_tabs = []
+        for tab in tabs:
+            y = torch.empty(tab.shape[0], self.cfg.cp.hidden_size, device=self.dev, dtype=torch.float32)
+            self._gemv_rows(self.fa.cp_proj, tab, y)
+            self._cp_proj_tabs.append(y)
+        self._cp_proj_dev = torch.tensor([t.data_ptr() for t in self._cp_proj_tabs], device=self.dev, dtype=torch.int64)
+        torch.cuda.synchronize()
+        self.fa.cp_proj_rows_dev = self._cp_proj_dev.data_ptr()
+
     # ---- embeddings for the prefill (W8 GEMVs, two rows per launch) ------------------------------------
     def text_embed(self, ids: torch.Tensor) -> torch.Tensor:
         """P(ids) = fc2(silu(fc1(text_embedding[ids]))) -> [n, H] on device."""
@@ -314,6 +332,8 @@ class TalkerEngine:
         embeds = embeds.to(self.dev, torch.float32)
         lengths = list(lengths) if lengths is not None else [Lmax] * B
         assert max(lengths) == Lmax and Lmax + self.max_frames <= self.max_ctx
+        if self.fa.use_mega:
+            self._ensure_cp_proj_rows()
         self._ensure_graphs()
         self.reset()
         if trailing is None:

@@ -84,6 +84,7 @@ def main():
     ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False, parts=("talker", "cp"))
     e = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=1024)
     del ws
+    e._ensure_cp_proj_rows()                # projected embedding tables of the code-predictor passes (Q3T_CP_PROJ_TABLES=0: off)
     NST = 2048
     G = torch.cuda.get_device_properties(0).multi_processor_count
     timing = torch.zeros(G * NST, dtype=torch.int64, device="cuda")
