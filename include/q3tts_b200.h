@@ -279,6 +279,10 @@ typedef struct {
      * fp32.  The input of a pass is a table row - a function of one sampled code - so its projection is a lookup; with the
      * tables the kernel skips one contraction phase per pass.  NULL = project in the kernel. */
     const float* const* cp_proj_rows_dev;
+    /* optional, needs cp_proj_rows_dev: DEVICE array [G-1] of tables [V_g, (H+2Hkv)*D] fp32 = the first code-predictor layer's
+     * fused q|k|v projection of RMSNorm(projected row) - equally a function of one code.  With it the first layer of those
+     * passes starts at the attention (one more contraction phase less per pass).  NULL = compute in the kernel. */
+    const float* const* cp_qkv0_rows_dev;
 } q3t_frame_args;
 
 /* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).

@@ -80,6 +80,7 @@ struct LLParams {
     q3t_w8 codec_head, cp_proj; const q3t_w8* cp_heads;          // DEVICE array [G-1]
     const float* codec_embedding; const float* const* cp_embeddings;   // DEVICE array [G-1]
     const float* const* cp_proj_rows;            // optional DEVICE array [G-1]: projected embedding tables (see q3t_frame_args)
+    const float* const* cp_qkv0_rows;            // optional: first-layer q|k|v tables of the same rows
     int emb_dim, talker_vocab, cp_vocab, n_groups;
     q3t_sampling talker_sp, cp_sp;
     float* x; float* hidden; float* logits; float* cp_logits; int keep_cp_logits;
@@ -236,6 +237,7 @@ struct LLSmem {
     uint64_t* empty;        // [LL_NSLOT]
     uint64_t* kvbar;        // attention K/V staging (cp.async.bulk completion)
     const float** prows;    // [LL_MAXHEADS] projected embedding tables of the code-predictor passes (optional)
+    const float** qrows;    // [LL_MAXHEADS] first-layer q|k|v tables (optional)
 };
 constexpr size_t LL_STAGE_BYTES = 32768;
 constexpr size_t LL_ATT_FLOATS = 4 * 128 + 8 * 128 + 32;
@@ -259,7 +261,8 @@ constexpr size_t LL_OFF_FULL = LL_OFF_PAGES + 64 * 4;
 constexpr size_t LL_OFF_EMPTY = LL_OFF_FULL + LL_NSLOT * 8;
 constexpr size_t LL_OFF_KVBAR = LL_OFF_EMPTY + LL_NSLOT * 8;
 constexpr size_t LL_OFF_PROWS = LL_OFF_KVBAR + 8;
-constexpr size_t LL_SMEM_BYTES = LL_OFF_PROWS + LL_MAXHEADS * 8;
+constexpr size_t LL_OFF_QROWS = LL_OFF_PROWS + LL_MAXHEADS * 8;
+constexpr size_t LL_SMEM_BYTES = LL_OFF_QROWS + LL_MAXHEADS * 8;
 static_assert(LL_SMEM_BYTES <= 227 * 1024, "frame_ll: shared memory budget exceeded");
 static_assert(LL_OFF_STAGE % 128 == 0 && LL_OFF_DIG % 16 == 0, "frame_ll: staging / digit alignment");
 
@@ -287,6 +290,7 @@ __device__ __forceinline__ LLSmem ll_smem() {
     s.empty = reinterpret_cast<uint64_t*>(b + LL_OFF_EMPTY);
     s.kvbar = reinterpret_cast<uint64_t*>(b + LL_OFF_KVBAR);
     s.prows = reinterpret_cast<const float**>(b + LL_OFF_PROWS);
+    s.qrows = reinterpret_cast<const float**>(b + LL_OFF_QROWS);
     return s;
 }
 
@@ -640,7 +644,7 @@ __device__ __forceinline__ void attn_prefetch(const CState& st, const LLStack& S
 // (measured: +9 % per talker step, which never takes this path); the call is made by the four working warps only.
 template <int REP>
 __device__ __noinline__ void attn_tiny(const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
-                                       uint32_t tag_qkv, u64* ll_attnf, uint32_t tag_out, uint32_t par) {
+                                       uint32_t tag_qkv, u64* ll_attnf, uint32_t tag_out, uint32_t par, const float* plain_qkv) {
     constexpr int D = 128;
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
@@ -652,7 +656,7 @@ __device__ __noinline__ void attn_tiny(const LLStack& S, const LayerD& LD, int l
     float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
     if (is_q || is_k) nw4 = __ldg(reinterpret_cast<const float4*>(is_q ? LD.q_norm : LD.k_norm) + lane);
     const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
-    const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
+    const float4 xv = plain_qkv ? __ldcg(reinterpret_cast<const float4*>(plain_qkv + n0)) : ll_ld4(ll_qkv + n0, tag_qkv, p.state);
     float x[4] = {xv.x, xv.y, xv.z, xv.w};
     if (is_q || is_k) {
         const float nw[4] = {nw4.x, nw4.y, nw4.z, nw4.w};
@@ -731,7 +735,7 @@ __device__ __noinline__ void attn_tiny(const LLStack& S, const LayerD& LD, int l
 
 template <int REP>
 __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD, int layer, int pos, const u64* ll_qkv,
-                                 uint32_t tag_qkv, u64* ll_attn, u64* ll_attnf, uint32_t tag_out) {
+                                 uint32_t tag_qkv, u64* ll_attn, u64* ll_attnf, uint32_t tag_out, const float* plain_qkv) {
     constexpr int D = 128;
     constexpr int TG = LL_CWARPS / (2 * REP), TPG = LL_KV_ROUND / TG;   // token groups per round / tokens per group
     const LLParams& p = ll_params();
@@ -743,7 +747,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
     if (nsplit == 1 && pos < 32) {
         const uint32_t par = st.kv_par;
         st.kv_par ^= 1;                           // every thread keeps the parity; only the working warps wait
-        if ((threadIdx.x >> 5) < REP + 2) attn_tiny<REP>(S, LD, layer, pos, ll_qkv, tag_qkv, ll_attnf, tag_out, par);
+        if ((threadIdx.x >> 5) < REP + 2) attn_tiny<REP>(S, LD, layer, pos, ll_qkv, tag_qkv, ll_attnf, tag_out, par, plain_qkv);
         return;
     }
 #endif
@@ -769,7 +773,7 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
             float4 nw4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (is_q || is_k) nw4 = __ldg(reinterpret_cast<const float4*>(is_q ? LD.q_norm : LD.k_norm) + lane);
             const int n0 = (is_q ? (kvh * REP + warp) : (is_k ? (S.n_heads + kvh) : (S.n_heads + S.n_kv + kvh))) * D + lane * 4;
-            const float4 xv = ll_ld4(ll_qkv + n0, tag_qkv, p.state);
+            const float4 xv = plain_qkv ? __ldcg(reinterpret_cast<const float4*>(plain_qkv + n0)) : ll_ld4(ll_qkv + n0, tag_qkv, p.state);
             LL_STAMP(ST_F_ATT_B);   // B: q words arrived
             float x[4] = {xv.x, xv.y, xv.z, xv.w};
             if (is_q || is_k) {
@@ -963,7 +967,9 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
 // Returns the words the caller's final norm still has to add (the last down projection).
 struct StackOut { const u64* add; uint32_t tag; };
 
-__device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const u64* first_add, uint32_t first_tag) {
+// qkv0 != nullptr: q|k|v of the first layer come from a table row (plain fp32), its QKV phase is skipped
+__device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const u64* first_add, uint32_t first_tag,
+                                        const float* qkv0 = nullptr) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
@@ -989,13 +995,17 @@ __device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const Laye
     for (int l = 0; l < S.n_layers; ++l) {
         const LayerD& L = lay[l];
         // ---- QKV
-        const uint32_t t_qkv = ++st.gen;
-        gemv_phase(st, L.qkv, in_norm(add, add_tag, L.input_norm, S.hidden, S.eps), EPI_RAW, p.x_qkv, nullptr, t_qkv);
+        const float* plain_qkv = l == 0 ? qkv0 : nullptr;
+        uint32_t t_qkv = 0u;
+        if (!plain_qkv) {
+            t_qkv = ++st.gen;
+            gemv_phase(st, L.qkv, in_norm(add, add_tag, L.input_norm, S.hidden, S.eps), EPI_RAW, p.x_qkv, nullptr, t_qkv);
+        }
         LL_STAMP(ST_QKV);
         // ---- attention (first n_kv*nsplit CTAs)
         const uint32_t t_att = ++st.gen;
-        if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att);
-        else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att);
+        if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att, plain_qkv);
+        else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att, plain_qkv);
         LL_STAMP(ST_ATTN);
         // ---- O projection
         const uint32_t t_o = ++st.gen;
@@ -1052,8 +1062,11 @@ struct Producer {
             if (lane == 0) *issued = (int)seq;
         }
     }
-    __device__ __forceinline__ void stack(const LayerD* lay, int n_layers) {
-        for (int l = 0; l < n_layers; ++l) { stream(lay[l].qkv); stream(lay[l].o); stream(lay[l].gu); stream(lay[l].down); }
+    __device__ __forceinline__ void stack(const LayerD* lay, int n_layers, bool skip_qkv0 = false) {
+        for (int l = 0; l < n_layers; ++l) {
+            if (!(skip_qkv0 && l == 0)) stream(lay[l].qkv);
+            stream(lay[l].o); stream(lay[l].gu); stream(lay[l].down);
+        }
     }
 };
 
@@ -1091,7 +1104,7 @@ __device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint3
 
 // one code-predictor pass: projected input -> 5 layers (-> head -> sampled code)
 // prow != nullptr: the projected input row is a table lookup (no projection phase in this pass)
-__device__ __noinline__ int cp_pass(CState& st, const float* src, const float* prow, int pos, int g_head, int step) {
+__device__ __noinline__ int cp_pass(CState& st, const float* src, const float* prow, const float* qrow, int pos, int g_head, int step) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x, Hc = p.cp.hidden, G = p.n_groups;
@@ -1107,7 +1120,7 @@ __device__ __noinline__ int cp_pass(CState& st, const float* src, const float* p
             reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
         first_add = p.x_proj;
     }
-    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, first_add, t_proj);
+    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, first_add, t_proj, prow ? qrow : nullptr);
     if (g_head < 0) return 0;
     const uint32_t t_head = ++st.gen;
     float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
@@ -1156,6 +1169,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         if (tid == 65) build_mat(s.hd[1], p_in.codec_head, cta, gridDim.x);
         if (tid >= 66 && tid < 66 + G - 1) build_mat(s.hd[2 + tid - 66], p_in.cp_heads[tid - 66], cta, gridDim.x);
         if (p_in.cp_proj_rows && tid >= 96 && tid < 96 + G - 1) s.prows[tid - 96] = p_in.cp_proj_rows[tid - 96];
+        if (p_in.cp_qkv0_rows && tid >= 128 && tid < 128 + G - 1) s.qrows[tid - 128] = p_in.cp_qkv0_rows[tid - 128];
     } else if (tid == 65 && p_in.head.w) build_mat(s.hd[1], p_in.head, cta, gridDim.x);
     if (tid == 0) {
         for (int i = 0; i < LL_NSLOT; ++i) { mbar_init(smem_u32(&s.full[i]), 1); mbar_init(smem_u32(&s.empty[i]), 1); }
@@ -1177,7 +1191,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 pr.stream(s.hd[0]); pr.stack(s.lay + nA, nB);
                 for (int g = 0; g < G - 1; ++g) {
                     if (!p.cp_proj_rows) pr.stream(s.hd[0]);
-                    pr.stack(s.lay + nA, nB); pr.stream(s.hd[2 + g]);
+                    pr.stack(s.lay + nA, nB, p.cp_proj_rows && p.cp_qkv0_rows); pr.stream(s.hd[2 + g]);
                 }
                 pr.stack(s.lay, nA); pr.stream(s.hd[1]);
             }
@@ -1222,7 +1236,7 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         LL_STAMP(ST_SAMPLE);
         // ---- code predictor: position 0 = projected talker hidden, then one pass per residual codebook.
         // The next talker input is accumulated on the way, in registers: emb0[c0] + emb1[c1] + ... in order
-        cp_pass(st, p.hidden, nullptr, 0, -1, step);
+        cp_pass(st, p.hidden, nullptr, nullptr, 0, -1, step);
         LL_STAMP(ST_CP_PASS);
         float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int g = 0; g < G - 1; ++g) {
@@ -1231,7 +1245,8 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(row) + tid);
                 if (g == 0) xn = r4; else { xn.x += r4.x; xn.y += r4.y; xn.z += r4.z; xn.w += r4.w; }
             }
-            code = cp_pass(st, row, p.cp_proj_rows ? s.prows[g] + (size_t)code * p.cp.hidden : nullptr, g + 1, g, step);
+            code = cp_pass(st, row, p.cp_proj_rows ? s.prows[g] + (size_t)code * p.cp.hidden : nullptr,
+                           p.cp_qkv0_rows ? s.qrows[g] + (size_t)code * ((p.cp.n_heads + 2 * p.cp.n_kv) * p.cp.head_dim) : nullptr, g + 1, g, step);
             LL_STAMP(ST_CP_PASS);
         }
         // ---- next talker input: running sum + last code's row, then the trailing text row
@@ -1393,6 +1408,7 @@ int launch_frame_ll(const q3t_frame_args* f, cudaStream_t stream) {
     p.state = f->ll_state; p.timing = f->ll_timing;
     p.codec_head = f->codec_head; p.cp_proj = f->cp_proj; p.cp_heads = f->cp_heads_dev;
     p.codec_embedding = f->codec_embedding; p.cp_embeddings = f->cp_embeddings_dev; p.cp_proj_rows = f->cp_proj_rows_dev;
+    p.cp_qkv0_rows = f->cp_proj_rows_dev ? f->cp_qkv0_rows_dev : nullptr;
     p.emb_dim = f->talker.hidden; p.talker_vocab = f->talker_vocab; p.cp_vocab = f->cp_vocab; p.n_groups = f->n_groups;
     p.talker_sp = f->talker_sp; p.cp_sp = f->cp_sp;
     p.x = f->x; p.hidden = f->hidden; p.logits = f->logits; p.cp_logits = f->cp_logits; p.keep_cp_logits = f->keep_cp_logits;

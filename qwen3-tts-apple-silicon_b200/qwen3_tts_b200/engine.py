@@ -241,8 +241,8 @@ class TalkerEngine:
     def _ensure_cp_proj_rows(self):
         """Projected embedding tables for the persistent kernel (q3t_frame_args.cp_proj_rows_dev): the input of
         code-predictor pass g is cp_proj(table_g[code]), a function of one sampled code, so the projection of every table
-        row is computed once here with the same W8 GEMV the kernel would run (33.8 k rows, 0.14 GB at full size) and each
-        pass starts from a lookup instead of a contraction phase.  Q3T_CP_PROJ_TABLES=0 keeps the in-kernel projection."""
+        row is computed once here with the same W8 GEMV the kernel would run (31.7 k rows; 0.13 GB + 0.52 GB for the q|k|v
+        tables at full size) and each pass starts from lookups instead of two contraction phases.  Q3T_CP_PROJ_TABLES=0 keeps the in-kernel projection."""
         if self._cp_proj_tabs is not None or self.B != 1 or os.environ.get("Q3T_CP_PROJ_TABLES", "1") == "0":
             return
         tabs = [self.codec_embedding] + self.cp_embeddings[: self.G - 2]
@@ -252,8 +252,18 @@ class TalkerEngine:
             self._gemv_rows(self.fa.cp_proj, tab, y)
             self._cp_proj_tabs.append(y)
         self._cp_proj_dev = torch.tensor([t.data_ptr() for t in self._cp_proj_tabs], device=self.dev, dtype=torch.int64)
+        # ... and the first layer's q|k|v of RMSNorm(projected row): the first layer of those passes starts at the attention
+        self._cp_qkv0_tabs = []
+        ly0 = self._cl[0]
+        for tab in self._cp_proj_tabs:
+            y = torch.empty(tab.shape[0], ly0.qkv.N, device=self.dev, dtype=torch.float32)
+            self._gemv_rows(ly0.qkv, tab, y, prologue=L.PRO_RMSNORM, norm_w=int(ly0.input_norm), eps=self.cp_stack.eps)
+            self._cp_qkv0_tabs.append(y)
+        self._cp_qkv0_dev = torch.tensor([t.data_ptr() for t in self._cp_qkv0_tabs], device=self.dev, dtype=torch.int64)
         torch.cuda.synchronize()
         self.fa.cp_proj_rows_dev = self._cp_proj_dev.data_ptr()
+        if os.environ.get("Q3T_CP_QKV0_TABLES", "1") != "0":
+            self.fa.cp_qkv0_rows_dev = self._cp_qkv0_dev.data_ptr()
 
     # ---- embeddings for the prefill (W8 GEMVs, two rows per launch) ------------------------------------
     def text_embed(self, ids: torch.Tensor) -> torch.Tensor:
@@ -275,7 +285,7 @@ class TalkerEngine:
             a = L.GemvArgs()
             a.w, a.M, a.prologue = w, min(2, n - r), prologue
             a.x, a.x_stride = x[r:].data_ptr(), x.stride(0)
-            a.norm_w, a.eps = L.ptr(norm_w), eps
+            a.norm_w, a.eps = (norm_w if isinstance(norm_w, int) else L.ptr(norm_w)), eps
             a.act = act
             if resid is not None:
                 a.resid, a.resid_stride = resid[r:].data_ptr(), resid.stride(0)
