@@ -6,6 +6,8 @@ csrc/frame_ll.cu:ll_tune), so these cases re-run the parity tests of test_gpu_pi
   Q3T_LL_MAXSPLIT=1   one split per kv head: every context > 64 tokens is walked in rounds (online rescale between rounds)
   Q3T_LL_MAXSPLIT=2   two splits, each several rounds long, merged by split 0
   Q3T_LL_CHUNK=16     16-token chunks: up to 16 splits per kv head, the merger polls the records in several rounds
+                      (+ Q3T_CP_PROJ_TABLES=0: the code-predictor passes project their input and run the first layer's QKV
+                      contraction in the kernel instead of reading the precomputed table rows the default path uses)
 """
 import os
 import subprocess
@@ -19,8 +21,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = "teacher_forced_logits_and_argmax or free_running_greedy or persistent_kernel_and_multikernel or streaming_trailing_text"
 
 
-@pytest.mark.parametrize("env", [{"Q3T_LL_MAXSPLIT": "1"}, {"Q3T_LL_MAXSPLIT": "2"}, {"Q3T_LL_CHUNK": "16"}],
-                         ids=["one-split-rounds", "two-splits-rounds", "sixteen-splits"])
+@pytest.mark.parametrize("env", [{"Q3T_LL_MAXSPLIT": "1"}, {"Q3T_LL_MAXSPLIT": "2"}, {"Q3T_LL_CHUNK": "16", "Q3T_CP_PROJ_TABLES": "0"}],
+                         ids=["one-split-rounds", "two-splits-rounds", "sixteen-splits-no-tables"])
 def test_parity_cases_under_other_attention_geometries(cuda, env):
     e = dict(os.environ)
     e.update(env)
