@@ -60,6 +60,24 @@ __global__ void __launch_bounds__(256) next_input_kernel(const float* __restrict
     if (threadIdx.x < G && step < max_frames) codes[((size_t)b * max_frames + step) * G + threadIdx.x] = cc[threadIdx.x];
 }
 
+// input of code-predictor pass g for every sequence of a lock-step batch: row cur_codes[b][g] of the projected embedding
+// table (and of the first layer's q|k|v table) - q3t_frame_args.cp_proj_rows_dev / cp_qkv0_rows_dev - instead of two GEMMs
+__global__ void __launch_bounds__(256) cp_rows_gather_kernel(const float* const* __restrict__ proj_tabs,
+                                                             const float* const* __restrict__ qkv_tabs, int g,
+                                                             const int* cur_codes, int G, int Hc, int qkvd, float* xc, float* qkv) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int b = blockIdx.x, code = cur_codes[(size_t)b * G + g];
+    const float4* pr = reinterpret_cast<const float4*>(proj_tabs[g] + (size_t)code * Hc);
+    float4* xo = reinterpret_cast<float4*>(xc + (size_t)b * Hc);
+    for (int i = threadIdx.x; i < Hc / 4; i += blockDim.x) xo[i] = pr[i];
+    if (qkv_tabs) {
+        const float4* qr = reinterpret_cast<const float4*>(qkv_tabs[g] + (size_t)code * qkvd);
+        float4* qo = reinterpret_cast<float4*>(qkv + (size_t)b * qkvd);
+        for (int i = threadIdx.x; i < qkvd / 4; i += blockDim.x) qo[i] = qr[i];
+    }
+}
+
 int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float eps, cudaStream_t s) {
     launch_pdl(rmsnorm_kernel, dim3(M), dim3(256), 0, s, x, w, y, H, eps);
     Q3T_CHECK_LAUNCH("rmsnorm");
@@ -111,13 +129,15 @@ static int gemm_bf16(const q3t_w8& w, int M, const void* x_bf16, int prologue, c
 }
 
 // one token through a dense Qwen3 stack; x [B, hidden] is updated in place (residual stream)
-static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x, const int* pos, cudaStream_t s) {
+// skip_qkv0: f->qkv already holds the first layer's q|k|v rows (table lookup, see cp_rows_gather_kernel)
+static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x, const int* pos, cudaStream_t s, bool skip_qkv0 = false) {
     const int B = f->B, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim;
     const int qkvd = qd + 2 * kvd;
     for (int l = 0; l < st.n_layers; ++l) {
         const q3t_layer& L = st.layers_host[l];
-        Q3T_TRY(gemv_rows(L.qkv, B, Q3T_PRO_RMSNORM, x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->qkv,
-                          qkvd, s));
+        if (!(skip_qkv0 && l == 0))
+            Q3T_TRY(gemv_rows(L.qkv, B, Q3T_PRO_RMSNORM, x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->qkv,
+                              qkvd, s));
         q3t_attn_args a;
         memset(&a, 0, sizeof(a));
         a.qkv = f->qkv; a.q_norm_w = L.q_norm; a.k_norm_w = L.k_norm; a.eps = st.eps; a.inv_freq = st.inv_freq;
@@ -202,10 +222,17 @@ static int frame(const q3t_frame_args* f, cudaStream_t s) {
     Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos, s));
     for (int g = 0; g < G - 1; ++g) {
         const float* table = g == 0 ? f->codec_embedding : f->cp_embeddings_host[g - 1];
-        Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, table, 0, nullptr, 0.f, f->cur_codes + g, G, H, 0, nullptr, 0, f->xc,
-                          Hc, s));
+        const bool tabs = f->cp_proj_rows_dev != nullptr, qtabs = tabs && f->cp_qkv0_rows_dev != nullptr;
+        if (tabs) {
+            launch_pdl(cp_rows_gather_kernel, dim3(B), dim3(256), 0, s, f->cp_proj_rows_dev, qtabs ? f->cp_qkv0_rows_dev : nullptr, g,
+                       (const int*)f->cur_codes, G, Hc, (c.n_heads + 2 * c.n_kv_heads) * c.head_dim, f->xc, f->qkv);
+            Q3T_CHECK_LAUNCH("cp_rows_gather");
+        } else {
+            Q3T_TRY(gemv_rows(f->cp_proj, B, Q3T_PRO_RAW, table, 0, nullptr, 0.f, f->cur_codes + g, G, H, 0, nullptr, 0, f->xc,
+                              Hc, s));
+        }
         float* lg = f->keep_cp_logits ? f->cp_logits + (size_t)g * B * f->cp_vocab : f->cp_logits;
-        Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s));
+        Q3T_TRY(stack_forward(f, c, f->xc, f->cp_pos + (size_t)(g + 1) * B, s, qtabs));
         Q3T_TRY(gemv_rows(f->cp_heads_host[g], B, Q3T_PRO_RMSNORM, f->xc, Hc, c.final_norm, c.eps, nullptr, 0, 0, 0,
                           nullptr, 0, lg, f->cp_vocab, s));
         Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));

@@ -239,11 +239,11 @@ class TalkerEngine:
         self._graphs = {}
 
     def _ensure_cp_proj_rows(self):
-        """Projected embedding tables for the persistent kernel (q3t_frame_args.cp_proj_rows_dev): the input of
+        """Projected embedding tables (q3t_frame_args.cp_proj_rows_dev; persistent kernel and batched frame alike): the input of
         code-predictor pass g is cp_proj(table_g[code]), a function of one sampled code, so the projection of every table
         row is computed once here with the same W8 GEMV the kernel would run (31.7 k rows; 0.13 GB + 0.52 GB for the q|k|v
         tables at full size) and each pass starts from lookups instead of two contraction phases.  Q3T_CP_PROJ_TABLES=0 keeps the in-kernel projection."""
-        if self._cp_proj_tabs is not None or self.B != 1 or os.environ.get("Q3T_CP_PROJ_TABLES", "1") == "0":
+        if self._cp_proj_tabs is not None or os.environ.get("Q3T_CP_PROJ_TABLES", "1") == "0":
             return
         tabs = [self.codec_embedding] + self.cp_embeddings[: self.G - 2]
         self._cp_proj_tabs = []
@@ -342,8 +342,7 @@ class TalkerEngine:
         embeds = embeds.to(self.dev, torch.float32)
         lengths = list(lengths) if lengths is not None else [Lmax] * B
         assert max(lengths) == Lmax and Lmax + self.max_frames <= self.max_ctx
-        if self.fa.use_mega:
-            self._ensure_cp_proj_rows()
+        self._ensure_cp_proj_rows()
         self._ensure_graphs()
         self.reset()
         if trailing is None:
