@@ -17,14 +17,20 @@
 //     full/empty pairs (four issuing lanes: one lane tops out at ~186 cycles per 4352-byte tile);
 //   * 16 consumer warps run the IMMA dequant-dot (uint8 codes x signed base-256 digits of the block-fixed-point
 //     activation, exact int32 sums per quantisation group - see w8_gemv.cu) out of the ring;
+//   * per-WARP data flow inside a CTA: a warp polls only the 256 inputs of its own tile's k-chunk, converts them into a
+//     warp-private digit area and starts its tile - no block-wide prologue, no barrier in front of the tiles; 1/rms of the
+//     RMSNorm is applied in the epilogue, the residual stream is a per-CTA double buffer (see gemv_phase);
 //   * row tiles (16 output rows x all of K) are dealt to CTAs whole, so every output element has exactly one producer and
 //     epilogues (bias, SwiGLU) run before the value is published; the residual stream is replicated per CTA in shared
 //     memory, so residual adds never touch global memory;
 //   * attention: (kv head, 64-token split) units on the first n_kv*nsplit CTAs.  The chunk's K/V pages are whole 4 KB
-//     blocks of the paged cache: eight cp.async.bulk copies (one warp instruction) stage them under the QKV contraction;
+//     blocks of the paged cache: eight cp.async.bulk copies (one warp instruction) stage them a whole layer ahead;
 //     scores by 8 threads per token, then per warp (head, dim half, token group) softmax + P.V out of shared memory.
 //     Split 0 of every kv head merges the other splits' (m, l, acc) records (one poll round) and publishes normalised
 //     head outputs, so every consumer of the O projection polls ONE float4 instead of nsplit records of hot lines.
+//     Contexts of at most 32 tokens (every code-predictor pass) take a barrier-free path, one warp per q head (attn_tiny);
+//   * the input of a code-predictor pass and its first layer's q|k|v are functions of ONE sampled code: table rows computed
+//     at load (q3t_frame_args.cp_proj_rows_dev / cp_qkv0_rows_dev), two contraction phases less in 15 of the 16 passes.
 // Re-use of an exchange buffer is safe without extra synchronisation because every phase is an all-to-all dependency:
 // a CTA can only be one phase ahead of the slowest CTA, and each buffer is rewritten five or more phases later.
 #include <stdlib.h>

@@ -82,7 +82,7 @@ def main():
     cfg = getattr(Cfg, size)()
     ctx = int(sys.argv[2]) if len(sys.argv) > 2 else (300 if size == "full" else 40)
     ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False, parts=("talker", "cp"))
-    e = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=1024)
+    e = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=int(os.environ.get("Q3T_MAX_CTX", "1024")))
     del ws
     e._ensure_cp_proj_rows()                # projected embedding tables of the code-predictor passes (Q3T_CP_PROJ_TABLES=0: off)
     NST = 2048
