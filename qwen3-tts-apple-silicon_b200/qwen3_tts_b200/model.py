@@ -24,6 +24,7 @@ from . import config as cfgmod
 from .codec import CodecDecoder
 from .config import ModelConfig
 from .engine import TalkerEngine
+from .text import segment_text
 from .weights import WeightStore, make_weights
 
 
@@ -182,9 +183,12 @@ class Model:
                  lang_code: str = "auto", ref_audio: Optional[str] = None, ref_text: Optional[str] = None,
                  temperature: Optional[float] = None, top_k: int = 50, top_p: float = 1.0,
                  repetition_penalty: float = 1.05, max_tokens: int = 1200, seed: int = 0, verbose: bool = False,
-                 stream: bool = False, streaming_interval: float = 2.0, **kwargs) -> Iterator[GenerationResult]:
+                 stream: bool = False, streaming_interval: float = 2.0, max_segment_chars: int = 600,
+                 **kwargs) -> Iterator[GenerationResult]:
         """One utterance -> one result (the reference consumes only audio_000.wav, io.py:156); with `stream=True` one
-        result per `streaming_interval` seconds of audio as it is generated (segment_idx counts the pieces).
+        result per `streaming_interval` seconds of audio as it is generated (segment_idx counts the pieces).  A text
+        longer than `max_segment_chars` is cut at sentence boundaries (text.segment_text) and generated segment by
+        segment, one result each (the shim joins them); 0 disables the segmentation.
         `speed` is accepted and ignored exactly like an unknown library kwarg; `temperature=0`
         or `None` with greedy=True selects the greedy parity path."""
         t0 = time.perf_counter()
@@ -202,6 +206,19 @@ class Model:
         elif mode == "base" and ref_audio is not None:
             ref_codes, speaker_vec = self._reference_prompt(ref_audio)
             streaming = True
+        segments = segment_text(text, max_segment_chars)
+        if len(segments) > 1:
+            kw = dict(voice=voice, instruct=instruct, speed=speed, lang_code=lang_code, ref_audio=ref_audio, ref_text=ref_text,
+                      temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty,
+                      max_tokens=max_tokens, seed=seed, verbose=verbose, stream=stream, streaming_interval=streaming_interval,
+                      max_segment_chars=0, greedy=greedy, **kwargs)
+            idx = 0
+            for seg in segments:
+                for r in self.generate(seg, **kw):
+                    r.segment_idx = idx
+                    idx += 1
+                    yield r
+            return
         ids = self.chat_ids(text)
         prefill, trailing = self.build_prefill(ids, ins, speaker, language, speaker_vec, streaming)
         max_frames = min(max_tokens, self.engine.max_frames)

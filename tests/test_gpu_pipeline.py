@@ -364,3 +364,22 @@ def test_streaming_generation_equals_offline_chunked_decode(small_setup):
     # the reference-facing generator with stream=True yields one result per interval
     res = list(model.generate("hello there", voice="ryan", greedy=True, stream=True, streaming_interval=1.0, max_tokens=30))
     assert len(res) >= 2 and sum(r.token_count for r in res) <= 30 and all(r.samples > 0 for r in res)
+
+
+def test_long_text_is_generated_segment_by_segment(small_setup, tmp_path):
+    """A text beyond the per-utterance budget comes back as one result per segment (and as ONE joined audio_000.wav
+    through the reference-facing generate_audio)."""
+    from qwen3_tts_b200.text import segment_text
+    cfg, ws, model, oracle = small_setup
+    text = "First sentence here. Second sentence follows! A third one? And the fourth sentence ends it."
+    segs = segment_text(text, 32)
+    assert len(segs) >= 3
+    res = list(model.generate(text, voice="ryan", greedy=True, max_tokens=5, max_segment_chars=32))
+    assert [r.segment_idx for r in res] == list(range(len(segs))) and all(r.samples > 0 for r in res)
+    one = list(model.generate(segs[1], voice="ryan", greedy=True, max_tokens=5))
+    assert len(one) == 1 and (one[0].codes == res[1].codes).all()
+    from mlx_audio.tts.generate import generate_audio
+    path = generate_audio(text=text, model=model, voice="ryan", output_path=str(tmp_path), greedy=True, max_tokens=5, max_segment_chars=32)
+    import wave
+    with wave.open(path) as w:
+        assert w.getframerate() == 24000 and w.getnframes() == sum(r.samples for r in res)

@@ -184,3 +184,22 @@ def test_write_wav_is_pcm16_mono_24k(tmp_path):
     with wave.open(p) as w:
         assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 24000, 4)
         assert np.frombuffer(w.readframes(4), dtype="<i2").tolist() == [0, 16384, -32767, 32767]
+
+
+def test_long_text_segmentation():
+    """SURVEY 8f-4 / BASELINE config 5 ("2-min texts chunked"): whole sentences packed into segments of bounded length, in
+    order, nothing dropped; over-long sentences cut at commas / spaces, unspaced runs at the limit."""
+    from qwen3_tts_b200.text import segment_text, split_sentences
+    t = ("Hello there. How are you today? I am fine! 你好。今天天气不错！Line one\nLine two; and more, with commas, and so on "
+         "and so forth without any end in sight whatsoever")
+    assert split_sentences(t)[:5] == ["Hello there.", "How are you today?", "I am fine!", "你好。", "今天天气不错！"]
+    squash = lambda x: "".join(x.split())
+    for m in (30, 60, 200):
+        segs = segment_text(t, m)
+        assert all(0 < len(x) <= m for x in segs)
+        assert squash("".join(segs)) == squash(t)
+    assert segment_text(t, 1000) == [t] and segment_text(t, 0) == [t] and segment_text("   ", 10) == []
+    assert segment_text("a" * 95, 30) == ["a" * 30, "a" * 30, "a" * 30, "a" * 5]
+    two_minutes = " ".join(f"This is sentence number {i} of a long narration." for i in range(60))
+    segs = segment_text(two_minutes, 400)
+    assert len(segs) >= 6 and all(s.endswith(".") for s in segs)
