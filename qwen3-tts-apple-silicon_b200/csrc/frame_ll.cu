@@ -48,7 +48,10 @@ constexpr int LL_THREADS = LL_CTHREADS + 64;     // + producer warp + L2 prefetc
 #define LL_NSLOT_N 32
 #endif
 constexpr int LL_NSLOT = LL_NSLOT_N;             // ring slots of one 4352-byte tile
-constexpr int LL_PLANES = 4;                     // producer lanes issuing TMA copies
+#ifndef LL_PLANES_N
+#define LL_PLANES_N 4
+#endif
+constexpr int LL_PLANES = LL_PLANES_N;           // producer lanes issuing TMA copies (one lane needs ~95 ns per tile)
 constexpr int LL_MAXK = 6144;                    // largest contraction length (talker intermediate size)
 constexpr int LL_MAXH = 2048;                    // largest hidden size (one float4 per consumer thread)
 constexpr int LL_MAXT = 48;                      // max tiles of one matrix per CTA
