@@ -16,6 +16,7 @@ ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False, parts=("talker", "c
 e = TalkerEngine(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=1024)
 del ws
 e.set_sampling(do_sample=False)
+e._ensure_cp_proj_rows()      # code-predictor table rows, as prefill() builds them in production
 e.use_graphs = False
 e.x.normal_(0, 0.02)
 e.pos.fill_(300)
