@@ -71,6 +71,9 @@ typedef struct {
 } q3t_gemv_args;
 
 int q3t_w8_gemv(const q3t_gemv_args* a, void* stream);
+/* The same contraction over n_rows rows (a->M is ignored): two rows per launch, enqueued from C.  Used to project whole
+ * embedding tables at load (q3t_frame_args.cp_proj_rows_dev) without a host round trip per pair of rows. */
+int q3t_w8_gemv_rows(const q3t_gemv_args* a, int n_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * W8 GEMM on the tcgen05 tensor cores (replaces mx.quantized_matmul, qmm path: batched decode, prefill)

@@ -320,3 +320,16 @@ int launch_w8_gemv(const q3t_gemv_args* a, cudaStream_t stream) {
 extern "C" int q3t_w8_gemv(const q3t_gemv_args* a, void* stream) {
     return q3t::launch_w8_gemv(a, (cudaStream_t)stream);
 }
+
+extern "C" int q3t_w8_gemv_rows(const q3t_gemv_args* a0, int n_rows, void* stream) {
+    for (int r = 0; r < n_rows; r += 2) {
+        q3t_gemv_args a = *a0;
+        a.M = n_rows - r >= 2 ? 2 : 1;
+        if (a0->gather_idx) a.gather_idx = a0->gather_idx + (long long)r * a0->gather_idx_stride;
+        else a.x = a0->x + (long long)r * a0->x_stride;
+        a.y = a0->y + (long long)r * a0->y_stride;
+        if (a0->resid) a.resid = a0->resid + (long long)r * a0->resid_stride;
+        if (const int rc = q3t_w8_gemv(&a, stream)) return rc;
+    }
+    return 0;
+}

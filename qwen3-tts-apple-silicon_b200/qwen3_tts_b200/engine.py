@@ -280,17 +280,15 @@ class TalkerEngine:
     def _gemv_rows(self, w: L.W8, x: torch.Tensor, y: torch.Tensor, act: int = 0, prologue: int = 0,
                    norm_w: Optional[torch.Tensor] = None, eps: float = 0.0, resid: Optional[torch.Tensor] = None):
         n = x.shape[0]
-        s = L.stream_ptr()
-        for r in range(0, n, 2):
-            a = L.GemvArgs()
-            a.w, a.M, a.prologue = w, min(2, n - r), prologue
-            a.x, a.x_stride = x[r:].data_ptr(), x.stride(0)
-            a.norm_w, a.eps = (norm_w if isinstance(norm_w, int) else L.ptr(norm_w)), eps
-            a.act = act
-            if resid is not None:
-                a.resid, a.resid_stride = resid[r:].data_ptr(), resid.stride(0)
-            a.y, a.y_stride = y[r:].data_ptr(), y.stride(0)
-            L.check(self.lib.q3t_w8_gemv(C.byref(a), s), "w8_gemv")
+        a = L.GemvArgs()
+        a.w, a.M, a.prologue = w, min(2, n), prologue
+        a.x, a.x_stride = x.data_ptr(), x.stride(0)
+        a.norm_w, a.eps = (norm_w if isinstance(norm_w, int) else L.ptr(norm_w)), eps
+        a.act = act
+        if resid is not None:
+            a.resid, a.resid_stride = resid.data_ptr(), resid.stride(0)
+        a.y, a.y_stride = y.data_ptr(), y.stride(0)
+        L.check(self.lib.q3t_w8_gemv_rows(C.byref(a), n, L.stream_ptr()), "w8_gemv_rows")   # two rows per launch, looped in C
 
     # ---- generation --------------------------------------------------------------------------------
     def reset(self):

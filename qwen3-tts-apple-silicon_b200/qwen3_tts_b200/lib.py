@@ -101,7 +101,7 @@ class TapGemmArgs(C.Structure):
 
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
-SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
+SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemv_rows", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
            "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_clamp_pcm16"]
 
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     lib.q3t_last_error.restype = C.c_char_p
     lib.q3t_launch_count.restype = u64
     lib.q3t_w8_gemv.argtypes = [C.POINTER(GemvArgs), vp]
+    lib.q3t_w8_gemv_rows.argtypes = [C.POINTER(GemvArgs), i32, vp]
     lib.q3t_w8_gemm.argtypes = [C.POINTER(GemmArgs), vp]
     lib.q3t_rmsnorm.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     lib.q3t_attn_decode.argtypes = [C.POINTER(AttnArgs), vp]
