@@ -61,7 +61,7 @@ def report(ids, ns, ctas, title, skip_first=9, quiet=None):
             a = acc.setdefault(key, [0, 0])
             a[0] += d
             a[1] += 1
-        n_layers = max(1, max((v[1] for k, v in acc.items() if k[1] == 1), default=1))
+        n_layers = max(1, max((v[1] for k, v in acc.items() if k[1] == 2), default=1))   # QKV phase-end stamps = layers
         parts = []
         tot = 0.0
         for (ph, sid), (d, c) in acc.items():
@@ -179,7 +179,7 @@ def main():
                 rows = {}
                 report(ids2, ns2, (c,), "", skip_first=0, quiet=rows)
                 npass = len(marks) - 1
-                print(f"cp-only cta {c:3d} ({npass} passes, us per pass): " + "  ".join(f"{k}={float(v) / npass:.2f}" for k, v in rows[c].items()))
+                print(f"cp-only cta {c:3d} ({npass} passes, us per layer): " + "  ".join(f"{k}={float(v):.2f}" for k, v in rows[c].items()))
     e.fa.ll_timing = 0
     s.record()
     for _ in range(20):
