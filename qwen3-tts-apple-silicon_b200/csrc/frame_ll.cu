@@ -1079,6 +1079,46 @@ struct Producer {
     }
 };
 
+// ---- greedy fast path: argmax straight out of the polled words - no score array, ONE block barrier -------------------------
+// Same choice as sample_core's greedy branch (largest score, lowest index on ties; 0 when every score is -inf or NaN).
+// The two-level reduction scratch is double buffered by `par` (the caller flips it), so no barrier is needed after the read.
+__device__ __noinline__ int sample_greedy(const float* plain, const u64* ll, uint32_t tag, int V, const q3t_sampling& sp,
+                                          const unsigned int* seen, int step, int par) {
+    const LLParams& p = ll_params();
+    const LLSmem s = ll_smem();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int k4 = tid; k4 < (V >> 2); k4 += LL_CTHREADS) {
+        const float4 v = plain ? __ldcg(reinterpret_cast<const float4*>(plain) + k4) : ll_ld4(ll + 4 * (size_t)k4, tag, p.state);
+        const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = (k4 << 2) + e;
+            const float sc = sample_score(x[e], i, sp, seen, step);
+            if (sc > bv || (sc == bv && i < bi)) { bv = sc; bi = i; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    float* rf = s.red + par * 32;
+    int* ri = s.ibuf + par * 16;
+    if (lane == 0) { rf[warp] = bv; ri[warp] = bi; }
+    cbar();
+    bv = lane < LL_CWARPS ? rf[lane] : -INFINITY;
+    bi = lane < LL_CWARPS ? ri[lane] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    return bi == 0x7fffffff ? 0 : bi;
+}
+
 // ---- in-kernel sampler (every CTA computes the same choice; CTA 0 records it) ------------------------------------------------
 // scores come from plain logits (previous launch) or from LL words of the head GEMV of this launch
 __device__ __noinline__ int sample_here(const float* plain, const u64* ll, uint32_t tag, int V, const q3t_sampling& sp,
@@ -1134,7 +1174,9 @@ __device__ __noinline__ int cp_pass(CState& st, const float* src, const float* p
     const uint32_t t_head = ++st.gen;
     float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
     gemv_phase(st, s.hd[2 + g_head], in_norm(so.add, so.tag, p.cp.final_norm, Hc, p.cp.eps), EPI_RAW, p.x_head, lg, t_head);
-    int c = sample_here(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g_head + 1);
+    int c;
+    if (!p.cp_sp.do_sample) { st.red_par ^= 1; c = sample_greedy(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, st.red_par); }
+    else c = sample_here(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g_head + 1);
     const long long fo = (long long)step * G + g_head + 1;
     const bool rec = (blockIdx.x == 0 && tid == 0);
     if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo] = c;
@@ -1233,7 +1275,9 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
         const bool rec = (cta == 0 && tid == 0);
         const bool xon = tid < (H >> 2);
         // ---- code 0 from the talker logits of the previous launch
-        int code = sample_here(p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, 0);
+        int code;
+        if (!p.talker_sp.do_sample) { st.red_par ^= 1; code = sample_greedy(p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, st.red_par); }
+        else code = sample_here(p.logits, nullptr, 0u, p.talker_vocab, p.talker_sp, p.seen, step, 0);
         if (rec && p.own_codes && step < p.max_frames) p.own_codes[fo] = code;
         if (p.forced) code = p.forced[fo];
         if (rec) {
