@@ -93,12 +93,14 @@ typedef struct {
     int act;  int swiglu_out;
     const float* resid;  long long resid_stride;
     float* y;  long long y_stride;
-    void* xb;
+    void* xb;                                  /* scratch for the prepared activations: split bf16 rows [M, 2K] (4*M*K bytes) */
     /* optional split-K workspace (decode-sized M): partial sums [splits][M][N] fp32 + zero-initialised counters [1024] */
     float* splitk_ws;  long long splitk_ws_floats;  int* splitk_counters;
-    /* optional bf16 chaining between kernels (saves the fp32 round trip and the prologue launch):
-     *   x_bf16: the input rows are ALREADY bf16 [M, K] contiguous (prologue must be Q3T_PRO_RAW, x is ignored);
-     *   y_bf16: the epilogue writes bf16 rows [M, N] (or [M, N/2] with swiglu_out) contiguous INSTEAD of fp32 y. */
+    /* optional bf16 chaining between kernels (saves the fp32 round trip and the prologue launch).  Every operand of the
+     * tensor-core GEMM is carried as hi + lo, both bf16 (hi = rn(v), lo = rn(v - hi)); a "split row" of width K is
+     * [hi(K) | lo(K)] = 2K bf16, contiguous:
+     *   x_bf16: the input rows are ALREADY split rows [M, 2K] (prologue must be Q3T_PRO_RAW, x is ignored);
+     *   y_bf16: the epilogue writes split rows [M, 2N] (or [M, 2(N/2)] with swiglu_out) INSTEAD of fp32 y. */
     const void* x_bf16;  void* y_bf16;
 } q3t_gemm_args;
 
@@ -130,7 +132,7 @@ typedef struct {
     int mode;                 /* 0 = fused decode step; 1 = only write K/V of every row (prefill pass 1, use nsplit = 1);
                                  2 = attention only, K/V of the row itself already in the cache (prefill pass 2) */
     const int* seq_of_row;    /* optional [B]: block-table row of launch row b (prefill rows of one sequence share pages) */
-    void* out_bf16;           /* optional [B, H*D] bf16: written INSTEAD of `out` (feeds q3t_w8_gemm.x_bf16 directly) */
+    void* out_bf16;           /* optional split bf16 rows [B, 2*H*D] (hi | lo): written INSTEAD of `out` (feeds q3t_w8_gemm.x_bf16 directly) */
 } q3t_attn_args;
 
 int q3t_attn_decode(const q3t_attn_args* a, void* stream);
@@ -140,7 +142,8 @@ int q3t_attn_decode(const q3t_attn_args* a, void* stream);
  * mx.fast.scaled_dot_product_attention over the prompt).  K/V of every row are already in the paged cache
  * (q3t_attn_decode mode 1).  Rows are ragged: row m is position pos[m] of sequence seq_of_row[m]; `blocks` [n_blocks, 2]
  * = (first row, row count <= 32) lists runs of consecutive rows of ONE sequence (one CTA per block and kv head).
- * Built for D = 128 and H = 2 * Hkv.  Writes out [M, H*D] fp32, or out_bf16 [M, H*D] when given.
+ * Built for D = 128 and H = 2 * Hkv.  Writes out [M, H*D] fp32, or out_bf16 as split rows
+ * [M, 2*H*D] = hi(H*D) | lo(H*D) (see q3t_gemm_args.x_bf16) when given.
  * k_norm_w != NULL (with M = number of rows): pass 1 runs first in the same call - K (RMSNorm + RoPE) and V of every row
  * are written to the cache, bit-identical to q3t_attn_decode mode 1.
  * ------------------------------------------------------------------------------------------- */
@@ -269,14 +272,14 @@ typedef struct {
     const float* trailing; /* [B, n_trailing, H]; row min(step, n_trailing-1) is added (last row = tts_pad) */
     int n_trailing;
     const int* forced_codes;  /* optional [B, max_frames, G]: teacher forcing (parity tests) */
-    void* gemm_xb;         /* bf16 scratch [B, max K] for the tcgen05 GEMM (used when B > 2), or NULL */
+    void* gemm_xb;         /* bf16 scratch of split rows [B, 2 * max K] for the tcgen05 GEMM (used when B > 2), or NULL */
     float* gemm_ws; long long gemm_ws_floats; int* gemm_counters;   /* split-K workspace of the GEMM (optional) */
     /* persistent-kernel path (used when use_mega != 0 and B == 1): the whole frame is ONE launch (csrc/frame_ll.cu) */
     int use_mega;
     const q3t_w8* cp_heads_dev;     /* cp_heads_host in DEVICE memory */
     void* ll_work; long long ll_work_bytes; unsigned int* ll_state;
     unsigned long long* ll_timing;  /* optional profiling stamps (profiling build only), or NULL */
-    void* gemm_xb2;        /* optional second bf16 scratch [B, max K]: attention output and SwiGLU activations stay bf16 */
+    void* gemm_xb2;        /* optional second bf16 scratch [B, 2 * max K]: attention output and SwiGLU activations stay (split) bf16 */
     /* optional (persistent-kernel path): DEVICE array [G-1] of device tables; table g = cp_proj applied to every row of the
      * embedding table that feeds code-predictor pass g (g = 0: codec_embedding [V, Hc]; g >= 1: cp_embeddings[g-1] [Vc, Hc]),
      * fp32.  The input of a pass is a table row - a function of one sampled code - so its projection is a lookup; with the
@@ -299,7 +302,7 @@ typedef struct {
     float* qkv; float* attn; float* gu; void* xb;
     float* attn_work; int* attn_counters;    /* >= M*Hkv*(H/Hkv)*(D+2) floats, M*Hkv ints (zeroed) */
     const int* blocks; int n_blocks;         /* optional row blocks for q3t_attn_prefill (see there); 0 = per-row decode kernel */
-    void* xb2;                               /* optional second bf16 scratch [M, max(H*D, inter)]: attention output and SwiGLU
+    void* xb2;                               /* optional second bf16 scratch of split rows [M, 2*max(H*D, inter)]: attention output and SwiGLU
                                                 activations stay bf16 between kernels (needs `blocks`) */
 } q3t_prefill_args;
 int q3t_talker_prefill(const q3t_prefill_args* a, void* stream);
@@ -342,6 +345,10 @@ typedef struct {
 } q3t_tapgemm_args;
 
 int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream);
+/* which kernel served the q3t_tapgemm calls so far: out3[0] tcgen05 TF32 tap-GEMM, out3[1] FP32-pipe kernel although
+ * Cin % 32 == 0 (fewer than 64 GEMM rows, N not a multiple of 16), out3[2] FP32-pipe kernel because Cin % 32 != 0.
+ * reset != 0 zeroes the counters after reading.  (Test / evidence aid: parity at the BASELINE shapes asserts out3[1] == 0.) */
+void q3t_tapgemm_stats(unsigned long long* out3, int reset);
 
 /* depthwise causal conv k (weights [C, k]) + LayerNorm over C (ConvNeXt front half) */
 int q3t_dwconv_ln(const float* x, const float* dw_w, const float* dw_b, const float* ln_w, const float* ln_b,

@@ -291,9 +291,11 @@ class OracleModel:
     # ---- full frame loop ----------------------------------------------------------------
     def generate(self, prefill: torch.Tensor, trailing: torch.Tensor, max_frames: int,
                  talker_sp: Optional[SamplingParams] = None, cp_sp: Optional[SamplingParams] = None,
-                 forced_codes: Optional[torch.Tensor] = None, record: bool = False):
+                 forced_codes: Optional[torch.Tensor] = None, record: bool = False, uniforms=None):
         """Returns codes [T, 16] (int64).  `forced_codes` [T,16] teacher-forces every sampled code while
-        still recording what the oracle itself would have picked (used for teacher-forced parity)."""
+        still recording what the oracle itself would have picked (used for teacher-forced parity).
+        `uniforms(step, group) -> float in [0,1)` supplies the random number of every stochastic draw (RNG streams
+        cannot match across frameworks: stochastic parity feeds both sides the same numbers)."""
         self.talker.reset()
         tsp = self.talker_sampling(talker_sp)
         h, logits = self.talker_forward(prefill)
@@ -302,19 +304,24 @@ class OracleModel:
         hist: List[int] = []
         for step in range(max_frames):
             s = process_logits(logits, tsp, hist, step)
-            own0 = draw(s, tsp)
+            own0 = draw(s, tsp, None if uniforms is None else uniforms(step, 0))
             code0 = own0 if forced_codes is None else int(forced_codes[step, 0])
             if code0 == tsp.eos_id:
                 break
             hist.append(code0)
             forced = None if forced_codes is None else [int(v) for v in forced_codes[step, 1:]]
-            rest, acc, cpl = self.cp_frame(h, code0, cp_sp, None, forced, True)
             csp = cp_sp or SamplingParams()
-            own_rest = [draw(process_logits(cpl[g], csp, (), g), csp) for g in range(cpl.shape[0])] \
-                if not csp.do_sample else list(rest)
+            us = None if uniforms is None else [uniforms(step, g + 1) for g in range(self.cfg.cp.num_code_groups - 1)]
+            rest, acc, cpl = self.cp_frame(h, code0, cp_sp, us, forced, True)
+            if not csp.do_sample or us is not None:      # what the oracle itself picks from these logits (forced or not)
+                own_rest = [draw(process_logits(cpl[g], csp, (), g), csp, None if us is None else us[g])
+                            for g in range(cpl.shape[0])]
+            else:
+                own_rest = list(rest)
             out.append([code0] + list(rest))
             if record:
                 top2 = torch.topk(s, 2).values
+                rec.setdefault("talker_scores", []).append(s.clone())
                 rec["talker_logits"].append(logits.clone())
                 rec["cp_logits"].append(cpl)
                 rec["own_codes"].append([own0] + list(own_rest))

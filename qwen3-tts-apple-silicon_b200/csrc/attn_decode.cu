@@ -217,8 +217,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
             A = fmaf(__ldcg(rec + d), w, A);
         }
         const size_t oi = (size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d;
-        if (p.out_bf16) p.out_bf16[oi] = __float2bfloat16_rn(A / L);   // feeds the O-projection GEMM without an fp32 round trip
-        else p.out[oi] = A / L;
+        if (p.out_bf16) {          // feeds the O-projection GEMM without an fp32 round trip: split row [hi(H*D) | lo(H*D)]
+            const float v = A / L;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const size_t si = oi + (size_t)b * p.H * D;
+            p.out_bf16[si] = hi;
+            p.out_bf16[si + (size_t)p.H * D] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        } else p.out[oi] = A / L;
     }
     if (tid == 0) p.counters[b * p.Hkv + kvh] = 0;   // re-arm for the next launch / graph replay
 }

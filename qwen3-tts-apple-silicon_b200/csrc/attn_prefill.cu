@@ -49,6 +49,12 @@ __device__ __forceinline__ uint32_t pf_pack(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// two adjacent outputs into a split bf16 row [hi(width) | lo(width)] (what the tcgen05 W8 GEMM reads, w8_gemm_tc.cu)
+__device__ __forceinline__ void pf_store_split(__nv_bfloat16* dst, size_t width, float a, float b) {
+    const uint32_t hi = pf_pack(a, b);
+    *reinterpret_cast<uint32_t*>(dst) = hi;
+    *reinterpret_cast<uint32_t*>(dst + width) = pf_pack(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
 
 __global__ void __launch_bounds__(PF_THREADS) attn_prefill_kernel(const PrefillAttnParams p) {
     extern __shared__ __align__(16) unsigned char pf_raw[];
@@ -214,12 +220,12 @@ __global__ void __launch_bounds__(PF_THREADS) attn_prefill_kernel(const PrefillA
         const int d = n * 8 + 2 * t4;
         if (ra_ < nrows) {
             const size_t oi = (size_t)(row0 + ra_) * ostride + hoff + d;
-            if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + oi) = pf_pack(o[n][0] * ia, o[n][1] * ia);
+            if (p.out_bf16) pf_store_split(p.out_bf16 + oi + (size_t)(row0 + ra_) * ostride, ostride, o[n][0] * ia, o[n][1] * ia);
             else *reinterpret_cast<float2*>(p.out + oi) = make_float2(o[n][0] * ia, o[n][1] * ia);
         }
         if (rb_ < nrows) {
             const size_t oi = (size_t)(row0 + rb_) * ostride + hoff + d;
-            if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + oi) = pf_pack(o[n][2] * ib, o[n][3] * ib);
+            if (p.out_bf16) pf_store_split(p.out_bf16 + oi + (size_t)(row0 + rb_) * ostride, ostride, o[n][2] * ib, o[n][3] * ib);
             else *reinterpret_cast<float2*>(p.out + oi) = make_float2(o[n][2] * ib, o[n][3] * ib);
         }
     }

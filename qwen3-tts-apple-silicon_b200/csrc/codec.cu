@@ -279,7 +279,16 @@ extern "C" int q3t_rvq_gather_sum(const int* codes, const float* const* tables_h
     return 0;
 }
 
-namespace q3t { int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream); }
+namespace q3t {
+int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream);
+// which kernel served q3t_tapgemm: [0] tcgen05 tap-GEMM, [1] FP32-pipe kernel although Cin % 32 == 0 (too few rows / odd N /
+// Q3T_CODEC_TC=0), [2] FP32-pipe kernel because Cin % 32 != 0.  Tests assert [1] == 0 at the BASELINE shapes.
+static unsigned long long g_tap_stats[3] = {0, 0, 0};
+}
+
+extern "C" void q3t_tapgemm_stats(unsigned long long* out3, int reset) {
+    for (int i = 0; i < 3; ++i) { if (out3) out3[i] = q3t::g_tap_stats[i]; if (reset) q3t::g_tap_stats[i] = 0; }
+}
 
 extern "C" int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream) {
     Q3T_REQUIRE(a->taps >= 1 && a->taps <= 8, "tapgemm: taps in [1,8]");
@@ -290,9 +299,10 @@ extern "C" int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream) {
         if (use_tc < 0) { const char* e = getenv("Q3T_CODEC_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
         if (use_tc && (long long)a->B * a->T_out_rows > 0) {
             const int rc = q3t::launch_tapgemm_tc(a, (cudaStream_t)stream);
-            if (rc >= 0) return rc;
+            if (rc >= 0) { q3t::g_tap_stats[0]++; return rc; }
         }
     }
+    q3t::g_tap_stats[(a->Cin % 32 == 0) ? 1 : 2]++;
     TapGemmParams p;
     p.A = a->A; p.B = a->B; p.T_in = a->T_in; p.Cin = a->Cin; p.W = a->W; p.bias = a->bias; p.taps = a->taps;
     for (int i = 0; i < 8; ++i) p.shift[i] = a->shift[i];

@@ -16,8 +16,13 @@
 //                 act_prep_kernel) is a 2-D TMA tensor-map load with hardware SWIZZLE_128B issued by a second producer lane;
 //                 (c) warps 2..5 run the epilogue: tcgen05.ld (32 lanes x 32
 //                 columns) -> bias / SiLU / SwiGLU pair / residual -> coalesced fp32 stores.
-// Numerics: bf16 operands, fp32 accumulation (BASELINE.json: "logits within 1e-2 relative (bf16)"); the batch-1/2 GEMV
-// (w8_gemv.cu, frame_ll.cu) stays exact-integer.
+// Numerics: SPLIT-bf16 operands, fp32 accumulation.  A 28-layer random-init stack amplifies a single bf16 rounding of the
+// operands (2^-9) to 1.4e-2 of max|logit| (measured against the fp32 CPU oracle at the 1.7B shapes; weights alone 1.7e-2,
+// TF32 operands 6e-3) - outside the 1e-2 BASELINE.json allows.  So every operand is carried as hi + lo, both bf16
+// (hi = rn(v), lo = rn(v - hi): 16 mantissa bits), and a K block costs three MMAs: W_hi.x_hi + W_lo.x_hi + W_hi.x_lo (the
+// lo.lo term is 2^-18 relative).  The tensor pipe is idle at decode sizes anyway (HBM / latency bound); prompt GEMMs pay
+// 3x MMA issue.  Activation rows therefore travel between kernels as "split rows" [hi(K) | lo(K)] of 2K bf16 (the same
+// bytes as the fp32 row).  The batch-1/2 GEMV (w8_gemv.cu, frame_ll.cu) stays exact-integer.
 #include <cuda.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
@@ -27,28 +32,31 @@ namespace q3t {
 constexpr int TC_DQ_WARPS = 16;                 // two warps per 16-row weight tile (one 32-wide K half each)
 constexpr int TC_THREADS = 64 + TC_DQ_WARPS * 32;   // 18 warps
 constexpr int TC_BM = 128;                      // features per CTA (MMA M)
-constexpr int TC_BN_MAX = 256;                  // tokens per CTA (MMA N)
+constexpr int TC_BN_MAX = 128;                  // tokens per CTA (MMA N)
 constexpr int TC_BK = 64;                       // K per operand stage (= one quantisation group = one 128-byte swizzle row)
-constexpr int TC_STAGES = 3;
+constexpr int TC_STAGES = 3;                    // at most; 2 when the token block is wider than 64 (see GemmParams.nst)
 constexpr int TC_RAW_STAGES = 2;
 constexpr int TC_RAW_BYTES = 8 * Q3T_TILE_BYTES;            // 34 816
-constexpr int TC_A_BYTES = TC_BM * 128;                      // 16 384
-constexpr int TC_B_BYTES = TC_BN_MAX * 128;                  // 32 768
+constexpr int TC_A_HALF = TC_BM * 128;                       // 16 384: one bf16 plane (hi or lo) of the weight block
+constexpr int TC_A_BYTES = 2 * TC_A_HALF;                    // hi plane, then lo plane
 constexpr int TC_OFF_A = 0;
-constexpr int TC_OFF_B = TC_OFF_A + TC_STAGES * TC_A_BYTES;  // 49 152
-constexpr int TC_OFF_RAW = TC_OFF_B + TC_STAGES * TC_B_BYTES;   // 147 456
+// operand ring: nst stages of {A hi | A lo} (32 KB each) followed by nst stages of {B hi | B lo} (2 * bn * 128 bytes each):
+// 128 tokens -> 2 stages (64 + 64 KB), <= 64 tokens (decode) -> 3 stages (96 + <= 48 KB)
+constexpr int TC_AB_BUDGET = 147456;
+constexpr int TC_OFF_RAW = TC_AB_BUDGET;
 constexpr int TC_OFF_BAR = TC_OFF_RAW + TC_RAW_STAGES * TC_RAW_BYTES;   // 217 088
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 256 + 1024;      // + barriers + slack for the 1024-byte alignment of the base
 
 struct GemmParams {
     const uint8_t* w; int N, K;                 // W8 tiles [N/16][K/256]
-    const __nv_bfloat16* xb; long long xb_stride;   // activations [M, K] bf16
+    const __nv_bfloat16* xb; long long xb_stride;   // activations, split rows [M, 2K] bf16: hi(K) | lo(K)
     int M;
     const float* lin_bias; int act; int swiglu;     // epilogue
     const float* resid; long long resid_stride;
     float* y; long long y_stride;
-    __nv_bfloat16* yb;                          // optional: bf16 rows [M, N] ([M, N/2] with swiglu) instead of y
-    int bn;                                     // tokens per CTA (multiple of 16, <= 256)
+    __nv_bfloat16* yb;                          // optional: split bf16 rows [M, 2N] ([M, 2(N/2)] with swiglu) instead of y
+    int bn;                                     // tokens per CTA (multiple of 16, <= 128)
+    int nst;                                    // operand stages (2 or 3, see TC_AB_BUDGET)
     int splits;                                 // split-K factor (gridDim.z); > 1 needs ws + counters
     float* ws; int* counters;                   // [splits][M][N] partial sums, one arrival counter per (n block, m block)
 };
@@ -101,6 +109,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+// four fp32 values -> hi plane (rn to bf16) and lo plane (rn of what the hi plane dropped)
+__device__ __forceinline__ void split_bf16x4(const float4 v, uint2& hi, uint2& lo) {
+    hi.x = pack_bf16x2(v.x, v.y); hi.y = pack_bf16x2(v.z, v.w);
+    lo.x = pack_bf16x2(v.x - __uint_as_float(hi.x << 16), v.y - __uint_as_float(hi.x & 0xffff0000u));
+    lo.y = pack_bf16x2(v.z - __uint_as_float(hi.y << 16), v.w - __uint_as_float(hi.y & 0xffff0000u));
+}
 
 #ifdef TC_TIMING
 #define TC_STAMP(i) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); reinterpret_cast<unsigned long long*>(p.ws)[i] = t_; } } while (0)
@@ -123,7 +137,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) TC_STAMP(0);
     const int nb = blockIdx.x, m0 = blockIdx.y * p.bn;
-    const int bn = p.bn;
+    const int bn = p.bn, nst = p.nst;
+    const int b_half = bn * 128, b_bytes = 2 * b_half, off_b = nst * TC_A_BYTES;
     // split-K: this CTA contracts the 256-wide chunks [kc_lo, kc_hi)
     const int nkc_all = p.K >> 8;
     const int kc_lo = (nkc_all * (int)blockIdx.z) / p.splits, kc_hi = (nkc_all * ((int)blockIdx.z + 1)) / p.splits;
@@ -164,13 +179,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
             pdl_wait();                           // the bf16 activations come from the previous kernel
             TC_STAMP(2);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+                const int st = kb % nst, par = (kb / nst) & 1;
                 tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
                 const uint32_t fb = tc_smem_u32(&full_ab[st]);
-                tc_mbar_expect_tx(fb, (uint32_t)bn * 128u);
+                tc_mbar_expect_tx(fb, (uint32_t)bn * 256u);
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                             ::"r"(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
+                             ::"r"(tc_smem_u32(smem + off_b + st * b_bytes)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
                                "r"((kc_lo * 4 + kb) * TC_BK), "r"(m0), "r"(fb) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(tc_smem_u32(smem + off_b + st * b_bytes + b_half)), "l"(reinterpret_cast<uint64_t>(&tmap_x)),
+                               "r"(p.K + (kc_lo * 4 + kb) * TC_BK), "r"(m0), "r"(fb) : "memory");   // lo plane: columns K.. of the split row
             }
         }
     } else if (warp == 1) {
@@ -178,15 +196,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             for (int kb = 0; kb < nkb; ++kb) {
-                const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+                const int st = kb % nst, par = (kb / nst) & 1;
                 tc_mbar_wait(tc_smem_u32(&full_ab[st]), par);
                 if (kb == 0) TC_STAMP(3);
                 tc_fence_after();
-                const uint64_t a_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_A + st * TC_A_BYTES));
-                const uint64_t b_desc = tc_smem_desc(tc_smem_u32(smem + TC_OFF_B + st * TC_B_BYTES));
+                const uint64_t a_hi = tc_smem_desc(tc_smem_u32(smem + TC_OFF_A + st * TC_A_BYTES));
+                const uint64_t a_lo = tc_smem_desc(tc_smem_u32(smem + TC_OFF_A + st * TC_A_BYTES + TC_A_HALF));
+                const uint64_t b_hi = tc_smem_desc(tc_smem_u32(smem + off_b + st * b_bytes));
+                const uint64_t b_lo = tc_smem_desc(tc_smem_u32(smem + off_b + st * b_bytes + b_half));
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)      // 16 bf16 = 32 bytes = 2 descriptor units along K
-                    tc_mma_bf16(tmem_d, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                for (int k = 0; k < TC_BK / 16; ++k) {    // 16 bf16 = 32 bytes = 2 descriptor units along K
+                    tc_mma_bf16(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);     // small terms first
+                    tc_mma_bf16(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    tc_mma_bf16(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                }
                 tc_commit(tc_smem_u32(&empty_ab[st]));     // frees the stage once these MMAs have read it
             }
             tc_commit(tc_smem_u32(tmem_full));              // accumulator complete
@@ -199,7 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
         const int g = lane >> 2, t = lane & 3;
         pdl_wait();                               // activations come from the previous kernel
         for (int kb = 0; kb < nkb; ++kb) {
-            const int st = kb % TC_STAGES, par = (kb / TC_STAGES) & 1;
+            const int st = kb % nst, par = (kb / nst) & 1;
             const int kc = kb >> 2, j4 = kb & 3, rs = kc % TC_RAW_STAGES, rpar = (kc / TC_RAW_STAGES) & 1;
             tc_mbar_wait(tc_smem_u32(&empty_ab[st]), par ^ 1);
             // ---- A operand: dequantise group j4 of this warp's raw tile
@@ -228,9 +251,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                         }
                         const int row8 = g;                       // row inside its 8-row atom
                         const int chunk = 4 * j + 2 * (i >> 1) + (t >> 1);
-                        uint2 o;
+                        uint2 o, ol;
                         o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
-                        *reinterpret_cast<uint2*>(adst + (i & 1) * 1024 + row8 * 128 + ((chunk ^ row8) << 4) + (t & 1) * 8) = o;
+                        // lo plane: what the bf16 rounding of the hi plane dropped (exact in fp32, then rounded once)
+                        ol.x = pack_bf16x2(f[0] - __uint_as_float(o.x << 16), f[1] - __uint_as_float(o.x & 0xffff0000u));
+                        ol.y = pack_bf16x2(f[2] - __uint_as_float(o.y << 16), f[3] - __uint_as_float(o.y & 0xffff0000u));
+                        unsigned char* dsta = adst + (i & 1) * 1024 + row8 * 128 + ((chunk ^ row8) << 4) + (t & 1) * 8;
+                        *reinterpret_cast<uint2*>(dsta) = o;
+                        *reinterpret_cast<uint2*>(dsta + TC_A_HALF) = ol;
                     }
                 }
             }
@@ -317,8 +345,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                         }
                         const float4 o = make_float4(silu_f(g.x) * u.x, silu_f(g.y) * u.y, silu_f(g.z) * u.z, silu_f(g.w) * u.w);
                         if (p.yb) {
-                            uint2 ob; ob.x = pack_bf16x2(o.x, o.y); ob.y = pack_bf16x2(o.z, o.w);
-                            *reinterpret_cast<uint2*>(p.yb + (size_t)m * (p.N >> 1) + (n0 >> 1) + 8 * j + 4 * h) = ob;
+                            uint2 ob, ol; split_bf16x4(o, ob, ol);
+                            __nv_bfloat16* yr = p.yb + (size_t)m * p.N + (n0 >> 1) + 8 * j + 4 * h;      // split row: 2 * (N/2) wide
+                            *reinterpret_cast<uint2*>(yr) = ob;
+                            *reinterpret_cast<uint2*>(yr + (p.N >> 1)) = ol;
                         } else {
                             *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + (n0 >> 1) + 8 * j + 4 * h) = o;
                         }
@@ -348,8 +378,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                             x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
                         }
                         if (p.yb) {
-                            uint2 ob; ob.x = pack_bf16x2(x.x, x.y); ob.y = pack_bf16x2(x.z, x.w);
-                            *reinterpret_cast<uint2*>(p.yb + (size_t)m * p.N + n0 + 4 * q4) = ob;
+                            uint2 ob, ol; split_bf16x4(x, ob, ol);
+                            __nv_bfloat16* yr = p.yb + (size_t)m * 2 * p.N + n0 + 4 * q4;
+                            *reinterpret_cast<uint2*>(yr) = ob;
+                            *reinterpret_cast<uint2*>(yr + p.N) = ol;
                         } else {
                             *reinterpret_cast<float4*>(p.y + (size_t)m * p.y_stride + n0 + 4 * q4) = x;
                         }
@@ -400,7 +432,9 @@ __global__ void __launch_bounds__(256) act_prep_kernel(const PrepParams p) {
         } else {
             v = xr[k];
         }
-        o[k] = __float2bfloat16_rn(v);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        o[k] = hi;
+        o[p.K + k] = __float2bfloat16_rn(v - __bfloat162float(hi));      // lo plane of the split row
     }
 }
 
@@ -415,7 +449,7 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     memset(&pp, 0, sizeof(pp));
     pp.x = a->x; pp.x_stride = a->x_stride; pp.M = a->M; pp.K = K; pp.prologue = a->prologue; pp.norm_w = a->norm_w; pp.eps = a->eps;
     pp.gather_idx = a->gather_idx; pp.gather_idx_stride = a->gather_idx_stride; pp.gather_row_stride = a->gather_row_stride;
-    pp.out = (__nv_bfloat16*)a->xb; pp.out_stride = K;
+    pp.out = (__nv_bfloat16*)a->xb; pp.out_stride = 2 * K;
     if (!a->x_bf16) {
         launch_pdl(act_prep_kernel, dim3(a->M), dim3(256), 0, stream, pp);
         Q3T_CHECK_LAUNCH("act_prep");
@@ -423,13 +457,14 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
     // 2. the GEMM
     GemmParams p;
     memset(&p, 0, sizeof(p));
-    p.w = (const uint8_t*)a->w.w; p.N = a->w.N; p.K = K; p.xb = (const __nv_bfloat16*)(a->x_bf16 ? a->x_bf16 : a->xb); p.xb_stride = K; p.M = a->M;
+    p.w = (const uint8_t*)a->w.w; p.N = a->w.N; p.K = K; p.xb = (const __nv_bfloat16*)(a->x_bf16 ? a->x_bf16 : a->xb); p.xb_stride = 2 * K; p.M = a->M;
     p.lin_bias = a->w.lin_bias; p.act = a->act; p.swiglu = a->swiglu_out; p.resid = a->resid; p.resid_stride = a->resid_stride;
     p.y = a->y; p.y_stride = a->y_stride; p.yb = (__nv_bfloat16*)a->y_bf16;
     int bn = (a->M + 15) / 16 * 16;
     if (bn > TC_BN_MAX) bn = TC_BN_MAX;
     if (bn < 16) bn = 16;
     p.bn = bn;
+    p.nst = (3 * (TC_A_BYTES + 2 * bn * 128) <= TC_AB_BUDGET) ? 3 : 2;
     // split-K for decode-sized problems: fill the machine when N/128 CTAs would leave most SMs idle
     p.splits = 1; p.ws = (float*)a->splitk_ws; p.counters = a->splitk_counters;
     {
@@ -447,7 +482,7 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
         attr_set = true;
     }
     static_assert(TC_SMEM_BYTES <= 227 * 1024, "w8_gemm: shared memory budget exceeded");
-    // 2-D tensor map of the bf16 activations [M, K]: box = 64 K-elements (128 bytes) x bn tokens, SWIZZLE_128B, zero fill
+    // 2-D tensor map of the split bf16 activations [M, 2K]: box = 64 K-elements (128 bytes) x bn tokens, SWIZZLE_128B, zero fill
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -462,8 +497,8 @@ int launch_w8_gemm(const q3t_gemm_args* a, cudaStream_t stream) {
         encode = (EncodeFn)fn;
     }
     CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)a->M};
-    const cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
+    const cuuint64_t gdim[2] = {(cuuint64_t)2 * K, (cuuint64_t)a->M};          // split rows: hi(K) | lo(K)
+    const cuuint64_t gstride[1] = {(cuuint64_t)K * 4};
     const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)p.xb, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,

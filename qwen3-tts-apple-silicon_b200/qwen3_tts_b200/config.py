@@ -155,6 +155,87 @@ class ModelConfig:
         return cls(talker=t, cp=c, codec=CodecConfig(**k), **d)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# the checkpoint's own config.json (what mlx_audio.tts.utils.load_model reads; reference io.py:111-112, folders of
+# config.py:17,26,35).  Layout per SURVEY Appendix A: top-level token ids + `talker_config` (with a nested
+# `code_predictor_config`, `spk_id`, `codec_language_id`, codec control ids) + `quantization`, and
+# `speech_tokenizer/config.json` with a `decoder_config`.  Every [U] constant of the survey is read from the file; the
+# dataclass defaults above only fill keys a checkpoint does not carry.  Several spellings are accepted per key because the
+# exact upstream names cannot be checked offline.
+# ---------------------------------------------------------------------------------------------------------------------
+def _pick(d: dict, names, default):
+    for n in names:
+        if n in d and d[n] is not None:
+            return d[n]
+    return default
+
+
+def _rope_theta(d: dict, default: float) -> float:
+    rp = d.get("rope_parameters") or {}
+    return float(_pick(d, ("rope_theta",), rp.get("rope_theta", default)))
+
+
+def from_hf_config(meta: dict, speech_meta: dict = None) -> ModelConfig:
+    """`config.json` (+ `speech_tokenizer/config.json`) of a Qwen3-TTS folder -> ModelConfig."""
+    cfg = ModelConfig()
+    cfg.tts_model_type = meta.get("tts_model_type", cfg.tts_model_type)
+    for ours, theirs in (("tts_pad_token_id", ("tts_pad_token_id",)), ("tts_bos_token_id", ("tts_bos_token_id",)),
+                         ("tts_eos_token_id", ("tts_eos_token_id",)), ("im_start_id", ("im_start_token_id", "im_start_id")),
+                         ("im_end_id", ("im_end_token_id", "im_end_id")), ("assistant_id", ("assistant_token_id", "assistant_id"))):
+        setattr(cfg, ours, int(_pick(meta, theirs, getattr(cfg, ours))))
+    q = meta.get("quantization") or meta.get("quantization_config") or {}
+    cfg.quant_group, cfg.quant_bits = int(q.get("group_size", cfg.quant_group)), int(q.get("bits", cfg.quant_bits))
+    if cfg.quant_bits != 8 or cfg.quant_group != 64:
+        raise ValueError(f"unsupported quantization {q}: this build streams affine 8-bit, group 64 (the *-8bit checkpoints)")
+    tc = meta.get("talker_config") or {}
+    t = cfg.talker
+    for ours, theirs in (("hidden_size", ("hidden_size",)), ("num_layers", ("num_hidden_layers",)), ("num_heads", ("num_attention_heads",)),
+                         ("num_kv_heads", ("num_key_value_heads",)), ("intermediate_size", ("intermediate_size",)),
+                         ("vocab_size", ("vocab_size",)), ("text_vocab_size", ("text_vocab_size",)), ("text_hidden_size", ("text_hidden_size",)),
+                         ("codec_pad_id", ("codec_pad_id", "codec_pad_token_id")), ("codec_bos_id", ("codec_bos_id", "codec_bos_token_id")),
+                         ("codec_eos_id", ("codec_eos_token_id", "codec_eos_id")), ("codec_think_id", ("codec_think_id",)),
+                         ("codec_nothink_id", ("codec_nothink_id",)), ("codec_think_bos_id", ("codec_think_bos_id",)),
+                         ("codec_think_eos_id", ("codec_think_eos_id",))):
+        setattr(t, ours, int(_pick(tc, theirs, getattr(t, ours))))
+    t.head_dim = int(_pick(tc, ("head_dim",), t.hidden_size // t.num_heads if "hidden_size" in tc and "head_dim" not in tc else t.head_dim))
+    t.rms_norm_eps = float(_pick(tc, ("rms_norm_eps",), t.rms_norm_eps))
+    t.rope_theta = _rope_theta(tc, t.rope_theta)
+    if tc.get("codec_language_id"):
+        t.codec_language_id = {str(k).lower(): int(v) for k, v in tc["codec_language_id"].items()}
+    if tc.get("spk_id"):
+        # values may be plain ids or one-element lists (the speaker slot of the prefill takes one codec id)
+        t.spk_id = {str(k).lower(): int(v[0] if isinstance(v, (list, tuple)) else v) for k, v in tc["spk_id"].items()}
+    pc = tc.get("code_predictor_config") or meta.get("code_predictor_config") or {}
+    c = cfg.cp
+    for ours, theirs in (("hidden_size", ("hidden_size",)), ("num_layers", ("num_hidden_layers",)), ("num_heads", ("num_attention_heads",)),
+                         ("num_kv_heads", ("num_key_value_heads",)), ("intermediate_size", ("intermediate_size",)),
+                         ("vocab_size", ("vocab_size",)), ("num_code_groups", ("num_code_groups",))):
+        setattr(c, ours, int(_pick(pc, theirs, getattr(c, ours))))
+    c.num_code_groups = int(_pick(tc, ("num_code_groups",), c.num_code_groups)) if "num_code_groups" not in pc else c.num_code_groups
+    c.head_dim = int(_pick(pc, ("head_dim",), c.head_dim))
+    c.rms_norm_eps = float(_pick(pc, ("rms_norm_eps",), c.rms_norm_eps))
+    c.rope_theta = _rope_theta(pc, c.rope_theta)
+    c.embed_dim = int(_pick(pc, ("codec_embedding_dim", "embed_dim"), t.hidden_size))
+    dc = (speech_meta or {}).get("decoder_config") or {}
+    k = cfg.codec
+    for ours, theirs in (("num_quantizers", ("num_quantizers",)), ("num_semantic", ("num_semantic_quantizers",)),
+                         ("codebook_size", ("codebook_size",)), ("latent_dim", ("latent_dim",)), ("tf_hidden", ("hidden_size",)),
+                         ("tf_intermediate", ("intermediate_size",)), ("tf_heads", ("num_attention_heads",)), ("tf_head_dim", ("head_dim",)),
+                         ("tf_layers", ("num_hidden_layers",)), ("sliding_window", ("sliding_window",)), ("decoder_dim", ("decoder_dim",))):
+        setattr(k, ours, int(_pick(dc, theirs, getattr(k, ours))))
+    if "codebook_dim" in dc:                     # upstream names the concatenated width (512); each codebook vector is half of it
+        k.rvq_out_dim = int(dc["codebook_dim"])
+        k.codebook_dim = int(_pick(dc, ("vector_quantization_hidden_dimension",), k.rvq_out_dim // 2))
+    k.tf_rope_theta = _rope_theta(dc, k.tf_rope_theta)
+    k.tf_rms_eps = float(_pick(dc, ("rms_norm_eps",), k.tf_rms_eps))
+    k.layer_scale = float(_pick(dc, ("layer_scale_initial_scale",), k.layer_scale))
+    for key in ("upsampling_ratios", "upsample_rates"):
+        if key in dc:
+            setattr(k, key, tuple(int(v) for v in dc[key]))
+    k.sample_rate = int(_pick(speech_meta or {}, ("output_sample_rate", "sample_rate"), k.sample_rate))
+    return cfg
+
+
 def full(tts_model_type: str = "custom_voice") -> ModelConfig:
     return ModelConfig(tts_model_type=tts_model_type)
 

@@ -182,9 +182,10 @@ class TalkerEngine:
         fa.use_mega = int(use_mega and self.B == 1)
         # tcgen05 GEMM path (more than two rows per contraction): bf16 activation scratch
         kmax = max(t.hidden_size, t.intermediate_size, c.hidden_size, c.intermediate_size, t.q_dim, c.q_dim)
-        self.gemm_xb = torch.empty(max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
+        # split bf16 rows [hi(K) | lo(K)]: the tcgen05 GEMM carries every operand as hi + lo (csrc/w8_gemm_tc.cu)
+        self.gemm_xb = torch.empty(2 * max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
         fa.gemm_xb = self.keep(self.gemm_xb)
-        self.gemm_xb2 = torch.empty(max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
+        self.gemm_xb2 = torch.empty(2 * max(B, 1) * kmax, device=dev, dtype=torch.bfloat16)
         fa.gemm_xb2 = self.keep(self.gemm_xb2)
         nmax = max(2 * t.intermediate_size, 2 * c.intermediate_size, V, Vc, t.q_dim + 2 * t.kv_dim)
         self.gemm_ws = torch.empty(8 * max(B, 1) * nmax, **f32)
@@ -375,7 +376,7 @@ class TalkerEngine:
         qkv = torch.empty(M, qkvd, **f32)
         attn = torch.empty(M, t.q_dim, **f32)
         gu = torch.empty(M, 2 * t.intermediate_size, **f32)
-        xb = torch.empty(M * max(t.hidden_size, t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)
+        xb = torch.empty(2 * M * max(t.hidden_size, t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)   # split rows
         work = torch.empty(M * t.num_kv_heads * rep * (t.head_dim + 2), **f32)
         counters = torch.zeros(M * t.num_kv_heads, device=dev, dtype=torch.int32)
         a = L.PrefillArgs()
@@ -389,7 +390,7 @@ class TalkerEngine:
             blocks += [(r0 + o, min(32, l - o)) for o in range(0, l, 32)]
             r0 += l
         blk = torch.tensor(blocks, dtype=torch.int32, device=dev).contiguous()
-        xb2 = torch.empty(M * max(t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)
+        xb2 = torch.empty(2 * M * max(t.intermediate_size, t.q_dim), device=dev, dtype=torch.bfloat16)
         if not os.environ.get("Q3T_PREFILL_ATTN_PER_ROW"):
             a.blocks, a.n_blocks = blk.data_ptr(), len(blocks)
             if not os.environ.get("Q3T_NO_BF16_CHAIN"):

@@ -103,7 +103,7 @@ class TapGemmArgs(C.Structure):
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemv_rows", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
-           "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_clamp_pcm16"]
+           "q3t_tapgemm_stats", "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_clamp_pcm16"]
 
 _lib = None
 
@@ -139,6 +139,8 @@ def load() -> C.CDLL:
     lib.q3t_talker_tail.argtypes = [C.POINTER(FrameArgs), vp]
     lib.q3t_rvq_gather_sum.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.q3t_tapgemm.argtypes = [C.POINTER(TapGemmArgs), vp]
+    lib.q3t_tapgemm_stats.argtypes = [C.POINTER(u64 * 3), i32]
+    lib.q3t_tapgemm_stats.restype = None
     lib.q3t_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, f32, i32, i32, i32, i32, vp, vp]
     lib.q3t_window_attn.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.q3t_snake.argtypes = [vp, vp, vp, i64, i32, vp, vp]
@@ -148,6 +150,13 @@ def load() -> C.CDLL:
         raise Q3TError("libq3tts_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+def tapgemm_stats(reset: bool = False):
+    """(tcgen05 launches, FP32-pipe launches of tensor-core-eligible channel counts, FP32-pipe launches of other shapes)."""
+    out = (u64 * 3)()
+    load().q3t_tapgemm_stats(C.byref(out), int(reset))
+    return tuple(int(v) for v in out)
 
 
 def check(rc: int, what: str = "") -> None:

@@ -192,16 +192,16 @@ def load_mlx_checkpoint(model_path: str, cfg: ModelConfig, device: str = "cpu", 
                         keep_fp: bool = False) -> WeightStore:
     """Reads `<model_path>/model.safetensors` (+ `speech_tokenizer/model.safetensors`) into a WeightStore.
 
-    `expected` (a store of the same config, e.g. `make_weights(cfg, device="meta")`-like shapes) is used for shape checks and
-    conv layout detection; when omitted the random-init factory provides the shapes."""
+    `expected` (a store of the same config; `weights.expected_shapes(cfg)` = meta tensors when omitted) is used for shape
+    checks and conv layout detection."""
     extra = {}
     km = os.path.join(model_path, "b200_key_map.json")
     if os.path.exists(km):
         with open(km) as f:
             extra = json.load(f)
     if expected is None:
-        from .weights import make_weights
-        expected = make_weights(cfg, seed=0, device="cpu", keep_fp=True, keep_q=True)
+        from .weights import expected_shapes
+        expected = expected_shapes(cfg)             # meta tensors: names + shapes only, nothing is materialised
     ws = WeightStore(cfg)
     raw: Dict[str, torch.Tensor] = {}
     unmapped: List[str] = []
@@ -218,6 +218,8 @@ def load_mlx_checkpoint(model_path: str, cfg: ModelConfig, device: str = "cpu", 
             if name is None:
                 unmapped.append(key)
                 continue
+            if name in raw:
+                raise ValueError(f"MLX checkpoint keys collide on '{name}' (second key: {key}); fix b200_key_map.json")
             raw[name] = t
     if unmapped:
         raise ValueError("MLX checkpoint holds tensors no rule maps (add them to b200_key_map.json or IGNORED): "

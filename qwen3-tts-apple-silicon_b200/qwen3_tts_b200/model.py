@@ -42,8 +42,9 @@ class GenerationResult:
 
 
 class ByteTokenizer:
-    """Stand-in text front end: the Qwen2 BPE vocabulary files are not available offline, so text
-    is mapped byte-wise into the text vocabulary.  A real `tokenizer.json` in the model directory replaces it."""
+    """Stand-in text front end for RANDOM-INIT runs only (bench, parity tests: the Qwen2 BPE vocabulary files are not
+    available offline): text is mapped byte-wise into the text vocabulary.  A folder that holds real weights
+    never gets this tokenizer - `_load_tokenizer` raises instead (a hashed id stream through trained weights is noise)."""
 
     def __init__(self, cfg: ModelConfig):
         self.cfg = cfg
@@ -53,24 +54,44 @@ class ByteTokenizer:
         return [(b * 2654435761 + 17) % max(v - 16, 1) for b in text.encode("utf-8")]
 
 
-def _load_tokenizer(path: Optional[str], cfg: ModelConfig):
+# the Qwen2 pre-tokenizer split (tokenization_qwen2.PRETOKENIZE_REGEX in the transformers cousin)
+_QWEN2_SPLIT = r"""(?i:'s|'t|'re|'ve|'m|'ll|'d)|[^\r\n\p{L}\p{N}]?\p{L}+|\p{N}| ?[^\s\p{L}\p{N}]+[\r\n]*|\s*[\r\n]+|\s+(?!\S)|\s+"""
+
+
+class _HFTokenizer:
+    def __init__(self, tok):
+        self.tok = tok
+
+    def encode(self, text: str) -> List[int]:
+        return self.tok.encode(text, add_special_tokens=False).ids
+
+
+def _load_tokenizer(path: Optional[str], cfg: ModelConfig, require: bool = False):
+    """`tokenizer.json` (fast-tokenizer file) or `vocab.json` + `merges.txt` (the files Qwen checkpoints ship: byte-level
+    BPE with the Qwen2 pre-tokenizer split) from the model folder.  `require`: the folder holds real weights, so a missing
+    tokenizer is an error (ValueError -> the reference prints "Failed to load model", io.py:115-117)."""
     if path:
-        tj = os.path.join(path, "tokenizer.json")
+        tj, vj, mt = (os.path.join(path, n) for n in ("tokenizer.json", "vocab.json", "merges.txt"))
         if os.path.exists(tj):
             from tokenizers import Tokenizer
-            tok = Tokenizer.from_file(tj)
-
-            class _T:
-                def encode(self, text):
-                    return tok.encode(text, add_special_tokens=False).ids
-            return _T()
+            return _HFTokenizer(Tokenizer.from_file(tj))
+        if os.path.exists(vj) and os.path.exists(mt):
+            from tokenizers import Regex, Tokenizer, decoders, models, pre_tokenizers
+            tok = Tokenizer(models.BPE.from_file(vj, mt))
+            tok.pre_tokenizer = pre_tokenizers.Sequence([
+                pre_tokenizers.Split(Regex(_QWEN2_SPLIT), behavior="isolated", invert=False),
+                pre_tokenizers.ByteLevel(add_prefix_space=False, use_regex=False)])
+            tok.decoder = decoders.ByteLevel()
+            return _HFTokenizer(tok)
+    if require:
+        raise ValueError(f"{path}: neither tokenizer.json nor vocab.json + merges.txt found next to the weights")
     return ByteTokenizer(cfg)
 
 
 class Model:
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", model_path: Optional[str] = None,
                  max_frames: int = 2048, max_ctx: int = 4096, batch: int = 1, max_trailing: int = 1024,
-                 prefill: str = "auto"):
+                 prefill: str = "auto", require_tokenizer: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("qwen3_tts_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
         self.cfg = cfg
@@ -79,7 +100,7 @@ class Model:
         self.engine = TalkerEngine(cfg, ws, device, batch=batch, max_frames=max_frames, max_ctx=max_ctx,
                                    max_trailing=max_trailing, prefill=prefill)
         self.codec = CodecDecoder(cfg, ws, device)
-        self.tokenizer = _load_tokenizer(model_path, cfg)
+        self.tokenizer = _load_tokenizer(model_path, cfg, require=require_tokenizer)
 
     # ---- prompt assembly (mirrors oracle.OracleModel.build_prefill) -------------------------
     def chat_ids(self, text: str) -> List[int]:
@@ -272,28 +293,43 @@ _MODE_BY_FOLDER = {"customvoice": "custom_voice", "voicedesign": "voice_design",
 def load_model(model_path: str, device: str = "cuda", **kw) -> Model:
     """Drop-in for `mlx_audio.tts.utils.load_model(model_path)` (reference io.py:111-112).
 
-    Reads `<model_path>/config.json` when present.  A directory holding `model.safetensors` (the `mlx-community/*-8bit`
-    layout the reference downloads, io.py:42-52) is read by `mlx_loader.load_mlx_checkpoint` - the affine 8-bit codes are
-    taken as they are; a malformed checkpoint raises ValueError/OSError, which the reference reports as "Failed to load
-    model" (io.py:115-117).  A directory without weights gets seeded random-init weights of the architecture its
-    config/folder names (the offline parity/benchmark set-up)."""
+    Reads `<model_path>/config.json` (+ `speech_tokenizer/config.json`): the checkpoint's own `talker_config` /
+    `code_predictor_config` / `spk_id` / `codec_language_id` / token ids / `quantization` drive every architecture constant
+    (config.from_hf_config).  `model.safetensors` (the `mlx-community/*-8bit` layout the reference downloads, io.py:42-52) is
+    read by `mlx_loader.load_mlx_checkpoint` - the affine 8-bit codes are taken as they are.  Anything that would make the
+    reference's "loaded" message a lie raises instead: a folder without weights (incomplete download) -> OSError, a
+    malformed checkpoint or a missing tokenizer next to real weights -> ValueError; the reference reports both as "Failed
+    to load model" (io.py:115-117).  Seeded random-init weights (the offline parity / benchmark set-up) are an explicit
+    opt-in: `random_init_seed` or `b200_size` in config.json, or Q3T_ALLOW_RANDOM_INIT=1."""
     if not os.path.isdir(model_path):
         raise OSError(f"model directory not found: {model_path}")
     has_ckpt = os.path.exists(os.path.join(model_path, "model.safetensors")) or \
         os.path.exists(os.path.join(model_path, "model.safetensors.index.json"))
-    cj = os.path.join(model_path, "config.json")
-    meta = {}
-    if os.path.exists(cj):
-        with open(cj) as f:
-            meta = json.load(f)
+
+    def read_json(*parts):
+        fn = os.path.join(model_path, *parts)
+        if not os.path.exists(fn):
+            return {}
+        with open(fn) as f:
+            return json.load(f)
+
+    meta, speech_meta = read_json("config.json"), read_json("speech_tokenizer", "config.json")
     folder = os.path.basename(os.path.normpath(model_path)).lower().replace("-", "")
     mode = meta.get("tts_model_type") or next((v for k, v in _MODE_BY_FOLDER.items() if k in folder), "custom_voice")
-    size = meta.get("b200_size", "full")
-    cfg = ModelConfig.from_dict(meta["b200_config"]) if "b200_config" in meta else getattr(cfgmod, size)(mode)
+    if "b200_config" in meta:                          # folders written by mlx_loader.export_mlx_checkpoint (fixtures)
+        cfg = ModelConfig.from_dict(meta["b200_config"])
+    elif "talker_config" in meta:                      # the checkpoint's own HF-style config tree
+        cfg = cfgmod.from_hf_config(meta, speech_meta)
+    else:
+        cfg = getattr(cfgmod, meta.get("b200_size", "full"))(mode)
     cfg.tts_model_type = mode
     if has_ckpt:
         from .mlx_loader import load_mlx_checkpoint
         ws = load_mlx_checkpoint(model_path, cfg, device=device)
     else:
+        if not ("random_init_seed" in meta or "b200_size" in meta or os.environ.get("Q3T_ALLOW_RANDOM_INIT") == "1"):
+            raise OSError(f"{model_path} holds no model.safetensors (incomplete download?); random-init weights need an explicit "
+                          "opt-in (random_init_seed / b200_size in config.json or Q3T_ALLOW_RANDOM_INIT=1)")
         ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False)
-    return Model(cfg, ws, device, model_path=model_path, **kw)
+    explicit_stub = bool(meta.get("b200_byte_tokenizer"))
+    return Model(cfg, ws, device, model_path=model_path, require_tokenizer=has_ckpt and not explicit_stub, **kw)

@@ -163,6 +163,12 @@ def _stack_layers(add_lin, add_norm, prefix: str, n_layers: int, hidden: int, q_
     add_norm(f"{prefix}.norm", hidden)
 
 
+def expected_shapes(cfg: ModelConfig) -> "WeightStore":
+    """The store of `cfg` with every tensor on the META device: names, shapes and which linears are W8, nothing
+    materialised (the checkpoint loader checks shapes and conv layouts against it)."""
+    return make_weights(cfg, device="meta", keep_fp=True, keep_q=True)
+
+
 def make_weights(cfg: ModelConfig, seed: int = 0, device: str = "cpu", keep_fp: bool = True,
                  keep_q: bool = True, head_std: float = 0.02, parts=("talker", "cp", "codec")) -> WeightStore:
     """Seeded N(0, 0.02^2) init of every tensor on the hot path (SURVEY 8d "Synthetic inputs").
@@ -171,15 +177,24 @@ def make_weights(cfg: ModelConfig, seed: int = 0, device: str = "cpu", keep_fp: 
     0.01, ConvNeXt gamma 1 so that every branch of the arithmetic is exercised by the parity tests.
     """
     ws = WeightStore(cfg)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
+    meta = str(device) == "meta"
+    gen = None if meta else torch.Generator(device=device)
+    if gen is not None:
+        gen.manual_seed(seed)
 
     def randn(*shape, std=0.02):
+        if meta:
+            return torch.empty(*shape, device="meta", dtype=torch.float32)
         return torch.randn(*shape, generator=gen, device=device, dtype=torch.float32) * std
 
     def add_lin(name, n, k, quant=True, std=0.02, bias=False):
         w = randn(n, k, std=std)
-        if quant and k % cfg.quant_group == 0:
+        if meta and quant and k % cfg.quant_group == 0:
+            g = cfg.quant_group
+            ws.q[name] = (torch.empty(n, k, device="meta", dtype=torch.uint8), torch.empty(n, k // g, device="meta", dtype=torch.bfloat16),
+                          torch.empty(n, k // g, device="meta", dtype=torch.bfloat16))
+            ws.fp[name + ".weight"] = w
+        elif quant and k % cfg.quant_group == 0:
             trip = quantize_w8(w, cfg.quant_group)
             if keep_q:
                 ws.q[name] = trip

@@ -49,8 +49,9 @@ def _bf16(x):
 @pytest.mark.parametrize("m,n,k", [(1, 128, 256), (5, 256, 512), (64, 2048, 2048), (64, 4096, 2048), (100, 2048, 6144),
                                    (300, 1024, 1024), (64, 3072, 2048), (17, 1024, 256)])
 def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
-    """tcgen05/TMEM W8 GEMM: exact against a reference that rounds both operands to bf16 (fp32 accumulation only),
-    and within the bf16 tolerance of BASELINE.json against the unrounded product."""
+    """tcgen05/TMEM W8 GEMM with split-bf16 operands (hi + lo, three MMAs per K block): within 5e-5 of the UNROUNDED fp64
+    product - a single bf16 rounding of the operands would be 200x worse (and 1.4e-2 on the logits of the 28-layer stack,
+    see tests/test_gpu_fullsize.py)."""
     lib = L.load()
     o, blob, wd = _w8(n, k, n + k + m, cuda)
     g = torch.Generator().manual_seed(3 * m + 1)
@@ -59,7 +60,7 @@ def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
     ref = x.double() @ wd.double().T
     xd = x.to(cuda)
     y = torch.full((m, n), float("nan"), device=cuda)
-    xb = torch.empty(m * k, device=cuda, dtype=torch.bfloat16)
+    xb = torch.empty(2 * m * k, device=cuda, dtype=torch.bfloat16)       # split rows [hi(K) | lo(K)]
     a = L.GemmArgs()
     a.w, a.M, a.prologue = o, m, L.PRO_RAW
     a.x, a.x_stride, a.y, a.y_stride, a.xb = xd.data_ptr(), k, y.data_ptr(), n, xb.data_ptr()
@@ -67,8 +68,8 @@ def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
     torch.cuda.synchronize()
     yd = y.cpu().double()
     assert torch.isfinite(yd).all()
-    assert (yd - ref_bf).abs().max() / ref_bf.abs().max() < 2e-5, "layout / accumulation error"
-    assert (yd - ref).abs().max() / ref.abs().max() < 1e-2, "bf16 tolerance"
+    assert (yd - ref).abs().max() / ref.abs().max() < 5e-5, "split-bf16 operands: expected ~1e-5 of the exact product"
+    assert (yd - ref).abs().max() < (yd - ref_bf).abs().max() / 20, "not better than single-bf16 operands?"
     # split-K (decode-sized problems): partial tiles summed in split order by the last CTA to arrive; twice, to check
     # that the arrival counters re-arm themselves and that the result is bit-reproducible
     ws = torch.empty(8 * m * n, device=cuda)
@@ -82,7 +83,7 @@ def test_w8_gemm_tcgen05_raw(cuda, m, n, k):
         outs.append(y.clone())
     assert torch.equal(outs[0], outs[1])
     assert int(cnt.abs().sum()) == 0
-    assert (outs[0].cpu().double() - ref_bf).abs().max() / ref_bf.abs().max() < 2e-5, "split-K"
+    assert (outs[0].cpu().double() - ref).abs().max() / ref.abs().max() < 5e-5, "split-K"
 
 
 def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
@@ -95,7 +96,7 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     nw = 1 + 0.1 * torch.randn(k, generator=g)
     bias = torch.randn(n, generator=g)
     resid = torch.randn(m, n, generator=g)
-    ref = _bf16(O.rms_norm(x, nw, 1e-6)) @ _bf16(wd).T + bias.double() + resid.double()
+    ref = O.rms_norm(x, nw, 1e-6).double() @ wd.double().T + bias.double() + resid.double()
     xd, nwd, bd, rd = x.to(cuda), nw.to(cuda), bias.to(cuda), resid.to(cuda)
     xb = torch.empty(m * 2 * k, device=cuda, dtype=torch.bfloat16)
     o.lin_bias = bd.data_ptr()
@@ -105,12 +106,12 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     a.resid, a.resid_stride, a.y, a.y_stride, a.xb = rd.data_ptr(), n, rd.data_ptr(), n, xb.data_ptr()
     L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
     torch.cuda.synchronize()
-    assert (rd.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+    assert (rd.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-4
     # SwiGLU prologue (interleaved gate/up input) + SiLU epilogue
     o.lin_bias = 0
     gu = torch.randn(m, 2 * k, generator=g)
     act = torch.nn.functional.silu(gu[:, :k]) * gu[:, k:]
-    ref = torch.nn.functional.silu(_bf16(act) @ _bf16(wd).T)
+    ref = torch.nn.functional.silu(act.double() @ wd.double().T)
     gud = torch.cat([gu[:, :k].reshape(m, -1, 8), gu[:, k:].reshape(m, -1, 8)], 2).reshape(m, 2 * k).contiguous().to(cuda)
     y = torch.empty(m, n, device=cuda)
     a = L.GemmArgs()
@@ -118,7 +119,7 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     a.x, a.x_stride, a.y, a.y_stride, a.xb = gud.data_ptr(), 2 * k, y.data_ptr(), n, xb.data_ptr()
     L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
     torch.cuda.synchronize()
-    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-4
     # SwiGLU OUTPUT epilogue: fused gate/up matrix with rows interleaved in blocks of 8
     half = n // 2
     wg, wu = wd[:half], wd[half:]
@@ -130,8 +131,8 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     blob2 = pack_w8(q[perm].contiguous().to(cuda), s[perm].contiguous().to(cuda), b[perm].contiguous().to(cuda))
     o2.w, o2.N, o2.K = blob2.data_ptr(), n, k
     xr = torch.randn(m, k, generator=g)
-    gate = _bf16(xr) @ _bf16(wd2[:half]).T
-    up = _bf16(xr) @ _bf16(wd2[half:]).T
+    gate = xr.double() @ wd2[:half].double().T
+    up = xr.double() @ wd2[half:].double().T
     ref = torch.nn.functional.silu(gate) * up
     y = torch.empty(m, half, device=cuda)
     xrd = xr.to(cuda)
@@ -140,7 +141,7 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     a.x, a.x_stride, a.y, a.y_stride, a.xb = xrd.data_ptr(), k, y.data_ptr(), half, xb.data_ptr()
     L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm")
     torch.cuda.synchronize()
-    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-3
+    assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-4
 
 
 def test_w8_gemv_prologues_epilogues(cuda):
@@ -310,7 +311,7 @@ def test_attn_prefill_ragged_causal(cuda, lens):
     out2 = torch.full((M, H * D), float("nan"), device=cuda)
     u.out, u.H, u.Hkv, u.D = out2.data_ptr(), H, Hkv, D
     L.check(lib.q3t_attn_prefill(C.byref(u), L.stream_ptr()), "attn_prefill")
-    out3 = torch.zeros(M, H * D, device=cuda, dtype=torch.bfloat16)
+    out3 = torch.zeros(M, 2 * H * D, device=cuda, dtype=torch.bfloat16)      # split rows [hi | lo]
     u.out, u.out_bf16 = 0, out3.data_ptr()
     L.check(lib.q3t_attn_prefill(C.byref(u), L.stream_ptr()), "attn_prefill bf16")
     torch.cuda.synchronize()
@@ -318,7 +319,28 @@ def test_attn_prefill_ragged_causal(cuda, lens):
     ref = out1.cpu().double()
     err = (out2.cpu().double() - ref).abs().amax(1) / ref.abs().amax(1)
     assert float(err.max()) < 1e-2, f"worst row {int(err.argmax())}: rel err {float(err.max()):.3e}"
-    assert torch.equal(out3.float(), out2.bfloat16().float())
+    # ... and against the ORACLE's attention arithmetic (oracle/qwen3_tts_oracle.py DecoderStack.forward: q/k RMSNorm, RoPE
+    # in the rotate_half convention, K/V rounded to bf16 where the cache stores them, fp32 softmax over the causal prefix),
+    # evaluated in fp64 per sequence - not against another CUDA kernel
+    r0 = 0
+    for l in lens:
+        x = qkv[r0:r0 + l].double()
+        q = x[:, :H * D].view(l, H, D); k = x[:, H * D:(H + Hkv) * D].view(l, Hkv, D); v = x[:, (H + Hkv) * D:].view(l, Hkv, D)
+        cos, sin = O.rope_cos_sin(torch.arange(l), D, theta)
+        rms = lambda t, w: w.double() * (t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps))
+        q = O.apply_rope(rms(q, qn), cos.double(), sin.double())
+        k = O.apply_rope(rms(k, kn), cos.double(), sin.double()).float().bfloat16().double()
+        v = v.float().bfloat16().double()
+        K, V = k.repeat_interleave(H // Hkv, 1), v.repeat_interleave(H // Hkv, 1)
+        sc = torch.einsum("thd,shd->hts", q, K) * D ** -0.5
+        sc = sc.masked_fill(~(torch.arange(l)[None, :] <= torch.arange(l)[:, None])[None], float("-inf"))
+        want = torch.einsum("hts,shd->thd", torch.softmax(sc, -1), V).reshape(l, H * D)
+        for name, got in (("attn_prefill", out2), ("attn_decode", out1)):
+            e_ = (got[r0:r0 + l].cpu().double() - want).abs().amax(1) / want.abs().amax(1)
+            assert float(e_.max()) < (1e-2 if name == "attn_prefill" else 1e-3), f"{name} vs oracle attention: {float(e_.max()):.3e}"
+        r0 += l
+    hi = out2.bfloat16()
+    assert torch.equal(out3[:, :H * D], hi) and torch.equal(out3[:, H * D:], (out2 - hi.float()).bfloat16())
     # pass 1 folded into the same call (k_norm_w given): the cache must come out bit-identical to the decode kernel's mode 1
     pool2 = torch.zeros_like(pool_d)
     out4 = torch.full((M, H * D), float("nan"), device=cuda)

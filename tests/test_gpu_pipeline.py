@@ -228,11 +228,17 @@ def _snr_db(x, ref):
 def test_codec_stages_and_waveform_snr(small_setup):
     cfg, ws, model, oracle = small_setup
     g = torch.Generator().manual_seed(8)
-    codes = torch.randint(0, cfg.codec.codebook_size, (2, 16, 21), generator=g)
+    from qwen3_tts_b200 import lib as L
+    codes = torch.randint(0, cfg.codec.codebook_size, (4, 16, 21), generator=g)      # 84 GEMM rows >= 64 in every layer
     so, sd = {}, {}
     wav_o = O.codec_forward(ws.fp, cfg, codes, so)[:, 0]
+    L.tapgemm_stats(reset=True)
     wav_d = model.codec.forward(codes, sd).cpu()
-    assert wav_d.shape == wav_o.shape == (2, cfg.codec.out_len(21))
+    tc, fb_eligible, fb_other = L.tapgemm_stats()
+    # which kernel ran is part of the test: every layer with Cin % 32 == 0 must be on the tcgen05 tap-GEMM; only the narrow
+    # vocoder tail of the SMALL config (48 / 24 / 12 channels) may use the FP32-pipe kernel (the full config has no such layer)
+    assert fb_eligible == 0 and tc > 0 and fb_other > 0, (tc, fb_eligible, fb_other)
+    assert wav_d.shape == wav_o.shape == (4, cfg.codec.out_len(21))
     for k in so:      # per-stage check; the convolutions run as TF32 implicit GEMMs on the tensor cores (2^-11 per operand)
         assert _rel(sd[k].cpu().transpose(1, 2), so[k]) < 3e-3, k
     assert _snr_db(wav_d, wav_o) >= WAV_SNR_DB
@@ -383,3 +389,40 @@ def test_long_text_is_generated_segment_by_segment(small_setup, tmp_path):
     import wave
     with wave.open(path) as w:
         assert w.getframerate() == 24000 and w.getnframes() == sum(r.samples for r in res)
+
+
+def test_in_kernel_stochastic_sampler_matches_oracle_with_shared_uniforms(small_setup):
+    """The DEFAULT product path of every reference session call (custom.py:163-170 passes no sampling kwargs): do_sample,
+    temperature 0.9, top-k 50, repetition penalty 1.05, min_new_tokens 2 for code 0 and temperature 0.9 / top-k 50 for the 15
+    code-predictor draws - all inside the persistent kernel (csrc/frame_ll.cu sample_here).  RNG streams cannot match across
+    frameworks, so the oracle is fed the kernel's own counter-based uniforms (tests/_parity.hash_uniform == sampler.cuh).
+    Teacher-forced on the oracle's stochastic trajectory: every one of the 16 x n device draws must equal the oracle's, or
+    its uniform must sit on a CDF boundary (<= 2e-3 of probability mass)."""
+    from _parity import check_stochastic_choices, hash_uniform
+    cfg, ws, model, oracle = small_setup
+    ids = _text_ids(cfg, 12, 41)
+    pre, tr = oracle.build_prefill(ids, speaker="ryan", language="english", instruct_ids=[3, 1, 4])
+    seed, n = 1234, 16
+    tsp = oracle.talker_sampling(O.SamplingParams(do_sample=True, temperature=0.9, top_k=50, top_p=1.0, repetition_penalty=1.05,
+                                                   min_new_tokens=2))
+    csp = O.SamplingParams(do_sample=True, temperature=0.9, top_k=50, top_p=1.0)
+    uni = lambda f, g: hash_uniform(seed if g == 0 else seed + 1, f, g)
+    codes_o, rec = oracle.generate(pre, tr, n, talker_sp=tsp, cp_sp=csp, record=True, uniforms=uni)
+    assert codes_o.shape[0] == n and len(set(codes_o[:, 0].tolist())) > 1
+    e = type(model.engine)(cfg, ws, "cuda", batch=1, max_frames=64, max_ctx=256, prefill="decode")
+    e.set_sampling(do_sample=True, temperature=0.9, top_k=50, top_p=1.0, repetition_penalty=1.05, min_new_tokens=2, seed=seed)
+    e.set_forced(codes_o[None])
+    e.prefill(pre[None], None, tr[None])
+    e.generate(n, check_every=0)
+    torch.cuda.synchronize()
+    own = e.own_codes[0, :n].cpu().long()
+    nb = check_stochastic_choices(own, rec, tsp, csp, uni)
+    assert nb <= 3, f"{nb} of {16 * n} draws sit on a CDF boundary: suspicious"
+    # free-running: identical codes until the first boundary case (after which the trajectories are different utterances)
+    e.set_forced(None)
+    e.prefill(pre[None], None, tr[None])
+    free = e.generate(n, check_every=0)[0].cpu().long()
+    diff = (free != codes_o).any(1).nonzero()
+    first = int(diff[0]) if diff.numel() else n
+    assert first >= 1 or nb > 0
+    assert cfg.talker.codec_eos_id not in free[:2, 0].tolist()        # min_new_tokens = 2 was in force

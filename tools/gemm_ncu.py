@@ -10,7 +10,7 @@ def blob(n, k):
     return pack_w8(q, s, b)
 for (n, k, m) in ((2048, 256, 64), (2048, 256, 256), (2048, 2048, 64), (12288, 2048, 64), (2048, 6144, 64), (4096, 2048, 4096)):
     w = blob(n, k)
-    x = torch.randn(m, k, device=dev); y = torch.empty(m, n, device=dev); xb = torch.empty(m * k, device=dev, dtype=torch.bfloat16)
+    x = torch.randn(m, k, device=dev); y = torch.empty(m, n, device=dev); xb = torch.empty(2 * m * k, device=dev, dtype=torch.bfloat16)
     a = L.GemmArgs(); o = L.W8(); o.w, o.N, o.K = w.data_ptr(), n, k
     a.w, a.M, a.prologue = o, m, L.PRO_RAW
     a.x, a.x_stride, a.y, a.y_stride, a.xb = x.data_ptr(), k, y.data_ptr(), n, xb.data_ptr()

@@ -16,7 +16,7 @@ for (n, k) in ((2048, 256), (2048, 512), (2048, 1024), (4096, 2048), (2048, 2048
         m, use_split = m
         nrep = 24 if m <= 256 else 4
         ws = [blob(n, k) for _ in range(nrep)]          # distinct weights per launch: nothing served from L2
-        x = torch.randn(m, k, device=dev); y = torch.empty(m, n, device=dev); xb = torch.empty(m * k, device=dev, dtype=torch.bfloat16)
+        x = torch.randn(m, k, device=dev); y = torch.empty(m, n, device=dev); xb = torch.empty(2 * m * k, device=dev, dtype=torch.bfloat16)
         sws = torch.empty(8 * m * n, device=dev); cnt = torch.zeros(1024, device=dev, dtype=torch.int32)
         args = []
         for w in ws:
