@@ -203,12 +203,28 @@ class OracleModel:
         return self.w["talker.codec_embedding"][ids.long()]
 
     # ---- prefill layout (SURVEY Appendix C; cousin qwen3_omni_moe:3838-3893) ---------
+    def ref_code_embeds(self, ref_codes: torch.Tensor) -> torch.Tensor:
+        """[T_ref, G] codes of a reference clip -> [T_ref, H]: per frame the same 16-way embedding sum the frame loop feeds back
+        (group 0 from the talker's codec table, groups 1.. from the code predictor's tables, added in order g = 0..15)."""
+        w = self.w
+        acc = w["talker.codec_embedding"][ref_codes[:, 0].long()]
+        for g in range(1, ref_codes.shape[1]):
+            acc = acc + w[f"cp.embeddings.{g - 1}"][ref_codes[:, g].long()]
+        return acc
+
     def build_prefill(self, text_ids: Sequence[int], instruct_ids: Optional[Sequence[int]] = None,
                       speaker: Optional[str] = None, language: Optional[str] = None,
-                      speaker_vec: Optional[torch.Tensor] = None, streaming: bool = False
+                      speaker_vec: Optional[torch.Tensor] = None, streaming: bool = False,
+                      ref_codes: Optional[torch.Tensor] = None, ref_text_ids: Optional[Sequence[int]] = None
                       ) -> Tuple[torch.Tensor, torch.Tensor]:
         """text_ids = chat-templated ids: ids[:3] role prefix, ids[3:-5] body, ids[-5:] template tail.
-        Returns (prefill embeds [L, H], trailing text embeds [n_trailing, H] whose LAST row is tts_pad)."""
+        Returns (prefill embeds [L, H], trailing text embeds [n_trailing, H] whose LAST row is tts_pad).
+
+        ICL (Base model + reference clip, SURVEY App. C last line; reference call site sessions/clone.py:218-224): with
+        `ref_codes` [T_ref, G] (+ `ref_text_ids` = chat-templated "<|im_start|>assistant\n{ref_text}<|im_end|>\n", body =
+        ids[3:-2]) the text side becomes P(ref body ++ text body) ++ eos and is paired position by position with the codec side
+        E(codec_bos) ++ [sum_g emb_g(ref_codes[t])]: streaming pairs them (the longer side's rest trails / is padded with
+        tts_pad), non-streaming lays the text block (on codec_pad) before the code block (on tts_pad)."""
         cfg, t = self.cfg, self.cfg.talker
         ids = torch.as_tensor(list(text_ids), dtype=torch.long)
         pad, bos, eos = self.text_embed(torch.tensor([cfg.tts_pad_token_id, cfg.tts_bos_token_id,
@@ -233,7 +249,24 @@ class OracleModel:
         if instruct_ids is not None and len(instruct_ids):
             segs.append(self.text_embed(torch.as_tensor(list(instruct_ids), dtype=torch.long)))
         segs += [head, mid]
-        if not streaming:
+        if ref_codes is not None:
+            ref_body = torch.as_tensor(list(ref_text_ids), dtype=torch.long)[3:-2] if ref_text_ids is not None \
+                else torch.zeros(0, dtype=torch.long)
+            text_all = torch.cat([self.text_embed(torch.cat([ref_body, body_ids])), eos[None]], 0)          # [T1, H]
+            codec_all = torch.cat([self.codec_embed(torch.tensor([t.codec_bos_id])), self.ref_code_embeds(ref_codes)], 0)
+            t1, t2 = text_all.shape[0], codec_all.shape[0]
+            if streaming:
+                if t1 > t2:
+                    segs.append(text_all[:t2] + codec_all)
+                    trailing = torch.cat([text_all[t2:], pad[None]], 0)
+                else:
+                    segs.append(torch.cat([text_all, pad[None].expand(t2 - t1, -1)], 0) + codec_all)
+                    trailing = pad[None]
+            else:
+                segs.append(text_all + self.codec_embed(torch.full((t1,), t.codec_pad_id)))
+                segs.append(codec_all + pad[None])
+                trailing = pad[None]
+        elif not streaming:
             body = torch.cat([self.text_embed(body_ids), eos[None]], 0) + \
                 self.codec_embed(torch.full((len(body_ids) + 1,), t.codec_pad_id))
             tail = pad[None] + self.codec_embed(torch.tensor([t.codec_bos_id]))

@@ -126,11 +126,65 @@ class CodecConfig:
 
 
 @dataclass
+class EncoderConfig:
+    """Speech-tokenizer ENCODER (24 kHz wav -> 12.5 Hz RVQ codes; voice cloning only).  Qwen3-TTS-Tokenizer-12Hz
+    encodes with a Mimi model; defaults = transformers MimiConfig."""
+    hidden_size: int = 512
+    num_filters: int = 64
+    ratios: Tuple[int, ...] = (8, 6, 5, 4)          # applied in REVERSE order by the encoder (mimi:466)
+    kernel_size: int = 7
+    last_kernel_size: int = 3
+    residual_kernel_size: int = 3
+    compress: int = 2
+    tf_layers: int = 8
+    tf_heads: int = 8
+    tf_head_dim: int = 64
+    tf_intermediate: int = 2048
+    sliding_window: int = 250
+    rope_theta: float = 1e4
+    norm_eps: float = 1e-5
+    layer_scale: float = 0.01
+    codebook_size: int = 2048
+    codebook_dim: int = 256
+    num_quantizers: int = 32                        # codebooks in the checkpoint
+    num_semantic: int = 1
+    valid_quantizers: int = 16                      # how many the TTS model consumes (encoder_valid_num_quantizers)
+
+    @property
+    def hop(self) -> int:
+        h = 2                                       # stride-2 downsample after the transformer (25 Hz -> 12.5 Hz)
+        for r in self.ratios:
+            h *= r
+        return h
+
+
+@dataclass
+class SpeakerEncoderConfig:
+    """Speaker encoder of the Base model: log-mel front end + ECAPA-TDNN -> one vector of the talker width."""
+    sample_rate: int = 24000
+    n_fft: int = 1024
+    hop: int = 256
+    win: int = 1024
+    n_mels: int = 128
+    fmin: float = 0.0
+    fmax: float = 12000.0
+    channels: Tuple[int, ...] = (512, 512, 512, 512, 1536)
+    kernel_sizes: Tuple[int, ...] = (5, 3, 3, 3, 1)
+    dilations: Tuple[int, ...] = (1, 2, 3, 4, 1)
+    attention_channels: int = 128
+    res2net_scale: int = 8
+    se_channels: int = 128
+    enc_dim: int = 2048
+
+
+@dataclass
 class ModelConfig:
     tts_model_type: str = "custom_voice"      # custom_voice | voice_design | base
     talker: TalkerConfig = field(default_factory=TalkerConfig)
     cp: CodePredictorConfig = field(default_factory=CodePredictorConfig)
     codec: CodecConfig = field(default_factory=CodecConfig)
+    enc: EncoderConfig = field(default_factory=EncoderConfig)
+    spk: SpeakerEncoderConfig = field(default_factory=SpeakerEncoderConfig)
     tts_pad_token_id: int = 151671
     tts_bos_token_id: int = 151672
     tts_eos_token_id: int = 151673
@@ -152,7 +206,9 @@ class ModelConfig:
         for key in ("upsampling_ratios", "upsample_rates"):
             if key in k:
                 k[key] = tuple(k[key])
-        return cls(talker=t, cp=c, codec=CodecConfig(**k), **d)
+        en = {kk: (tuple(v) if isinstance(v, list) else v) for kk, v in d.pop("enc", {}).items()}
+        sp = {kk: (tuple(v) if isinstance(v, list) else v) for kk, v in d.pop("spk", {}).items()}
+        return cls(talker=t, cp=c, codec=CodecConfig(**k), enc=EncoderConfig(**en), spk=SpeakerEncoderConfig(**sp), **d)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -233,7 +289,78 @@ def from_hf_config(meta: dict, speech_meta: dict = None) -> ModelConfig:
         if key in dc:
             setattr(k, key, tuple(int(v) for v in dc[key]))
     k.sample_rate = int(_pick(speech_meta or {}, ("output_sample_rate", "sample_rate"), k.sample_rate))
+    ec = (speech_meta or {}).get("encoder_config") or {}                   # a MimiConfig dict
+    en = cfg.enc
+    for ours, theirs in (("hidden_size", ("hidden_size",)), ("num_filters", ("num_filters",)), ("kernel_size", ("kernel_size",)),
+                         ("last_kernel_size", ("last_kernel_size",)), ("residual_kernel_size", ("residual_kernel_size",)),
+                         ("compress", ("compress",)), ("tf_layers", ("num_hidden_layers",)), ("tf_heads", ("num_attention_heads",)),
+                         ("tf_head_dim", ("head_dim",)), ("tf_intermediate", ("intermediate_size",)), ("sliding_window", ("sliding_window",)),
+                         ("codebook_size", ("codebook_size",)), ("codebook_dim", ("vector_quantization_hidden_dimension", "codebook_dim")),
+                         ("num_quantizers", ("num_quantizers",)), ("num_semantic", ("num_semantic_quantizers",))):
+        setattr(en, ours, int(_pick(ec, theirs, getattr(en, ours))))
+    if "upsampling_ratios" in ec:
+        en.ratios = tuple(int(v) for v in ec["upsampling_ratios"])
+    en.rope_theta = _rope_theta(ec, en.rope_theta)
+    en.norm_eps = float(_pick(ec, ("norm_eps",), en.norm_eps))
+    en.layer_scale = float(_pick(ec, ("layer_scale_initial_scale",), en.layer_scale))
+    en.valid_quantizers = int(_pick(speech_meta or {}, ("encoder_valid_num_quantizers",), min(en.valid_quantizers, en.num_quantizers)))
+    sc = meta.get("speaker_encoder_config") or {}
+    sp = cfg.spk
+    for ours, theirs in (("sample_rate", ("sample_rate",)), ("n_fft", ("n_fft",)), ("hop", ("hop_size", "hop_length")), ("win", ("win_size", "win_length")),
+                         ("n_mels", ("mel_dim", "num_mels")), ("attention_channels", ("enc_attention_channels",)),
+                         ("res2net_scale", ("enc_res2net_scale",)), ("se_channels", ("enc_se_channels",))):
+        setattr(sp, ours, int(_pick(sc, theirs, getattr(sp, ours))))
+    for ours, theirs in (("channels", "enc_channels"), ("kernel_sizes", "enc_kernel_sizes"), ("dilations", "enc_dilations")):
+        if theirs in sc:
+            setattr(sp, ours, tuple(int(v) for v in sc[theirs]))
+    sp.fmin, sp.fmax = float(_pick(sc, ("fmin",), sp.fmin)), float(_pick(sc, ("fmax",), sp.fmax))
+    sp.enc_dim = int(_pick(sc, ("enc_dim",), t.hidden_size))
     return cfg
+
+
+def to_hf_config(cfg: ModelConfig):
+    """Inverse of `from_hf_config` (fixtures: a folder in the checkpoint's own layout).  Returns (config.json dict,
+    speech_tokenizer/config.json dict)."""
+    t, c, k = cfg.talker, cfg.cp, cfg.codec
+    meta = {
+        "model_type": "qwen3_tts", "tts_model_type": cfg.tts_model_type, "tokenizer_type": "qwen3_tts_tokenizer_12hz",
+        "tts_pad_token_id": cfg.tts_pad_token_id, "tts_bos_token_id": cfg.tts_bos_token_id, "tts_eos_token_id": cfg.tts_eos_token_id,
+        "im_start_token_id": cfg.im_start_id, "im_end_token_id": cfg.im_end_id, "assistant_token_id": cfg.assistant_id,
+        "quantization": {"group_size": cfg.quant_group, "bits": cfg.quant_bits},
+        "talker_config": {
+            "hidden_size": t.hidden_size, "num_hidden_layers": t.num_layers, "num_attention_heads": t.num_heads,
+            "num_key_value_heads": t.num_kv_heads, "head_dim": t.head_dim, "intermediate_size": t.intermediate_size,
+            "vocab_size": t.vocab_size, "text_vocab_size": t.text_vocab_size, "text_hidden_size": t.text_hidden_size,
+            "rms_norm_eps": t.rms_norm_eps, "rope_theta": t.rope_theta, "num_code_groups": c.num_code_groups,
+            "codec_pad_id": t.codec_pad_id, "codec_bos_id": t.codec_bos_id, "codec_eos_token_id": t.codec_eos_id,
+            "codec_think_id": t.codec_think_id, "codec_nothink_id": t.codec_nothink_id, "codec_think_bos_id": t.codec_think_bos_id,
+            "codec_think_eos_id": t.codec_think_eos_id, "codec_language_id": dict(t.codec_language_id), "spk_id": dict(t.spk_id),
+            "code_predictor_config": {
+                "hidden_size": c.hidden_size, "num_hidden_layers": c.num_layers, "num_attention_heads": c.num_heads,
+                "num_key_value_heads": c.num_kv_heads, "head_dim": c.head_dim, "intermediate_size": c.intermediate_size,
+                "vocab_size": c.vocab_size, "num_code_groups": c.num_code_groups, "rms_norm_eps": c.rms_norm_eps,
+                "rope_theta": c.rope_theta}}}
+    en, sp = cfg.enc, cfg.spk
+    meta["speaker_encoder_config"] = {
+        "sample_rate": sp.sample_rate, "n_fft": sp.n_fft, "hop_size": sp.hop, "win_size": sp.win, "mel_dim": sp.n_mels, "fmin": sp.fmin,
+        "fmax": sp.fmax, "enc_channels": list(sp.channels), "enc_kernel_sizes": list(sp.kernel_sizes), "enc_dilations": list(sp.dilations),
+        "enc_attention_channels": sp.attention_channels, "enc_res2net_scale": sp.res2net_scale, "enc_se_channels": sp.se_channels,
+        "enc_dim": sp.enc_dim}
+    speech = {"output_sample_rate": k.sample_rate, "encoder_valid_num_quantizers": en.valid_quantizers, "encoder_config": {
+        "hidden_size": en.hidden_size, "num_filters": en.num_filters, "upsampling_ratios": list(en.ratios), "kernel_size": en.kernel_size,
+        "last_kernel_size": en.last_kernel_size, "residual_kernel_size": en.residual_kernel_size, "compress": en.compress,
+        "num_hidden_layers": en.tf_layers, "num_attention_heads": en.tf_heads, "head_dim": en.tf_head_dim,
+        "intermediate_size": en.tf_intermediate, "sliding_window": en.sliding_window, "rope_theta": en.rope_theta,
+        "norm_eps": en.norm_eps, "layer_scale_initial_scale": en.layer_scale, "codebook_size": en.codebook_size,
+        "vector_quantization_hidden_dimension": en.codebook_dim, "num_quantizers": en.num_quantizers,
+        "num_semantic_quantizers": en.num_semantic}, "decoder_config": {
+        "num_quantizers": k.num_quantizers, "num_semantic_quantizers": k.num_semantic, "codebook_size": k.codebook_size,
+        "codebook_dim": k.rvq_out_dim, "vector_quantization_hidden_dimension": k.codebook_dim, "latent_dim": k.latent_dim,
+        "hidden_size": k.tf_hidden, "intermediate_size": k.tf_intermediate, "num_attention_heads": k.tf_heads, "head_dim": k.tf_head_dim,
+        "num_hidden_layers": k.tf_layers, "sliding_window": k.sliding_window, "rope_theta": k.tf_rope_theta,
+        "rms_norm_eps": k.tf_rms_eps, "layer_scale_initial_scale": k.layer_scale, "upsampling_ratios": list(k.upsampling_ratios),
+        "upsample_rates": list(k.upsample_rates), "decoder_dim": k.decoder_dim}}
+    return meta, speech
 
 
 def full(tts_model_type: str = "custom_voice") -> ModelConfig:
@@ -256,7 +383,11 @@ def small(tts_model_type: str = "custom_voice") -> ModelConfig:
                             intermediate_size=512, embed_dim=512)
     k = CodecConfig(codebook_dim=64, rvq_out_dim=128, latent_dim=256, tf_hidden=128, tf_intermediate=256,
                     tf_heads=4, tf_head_dim=32, tf_layers=2, decoder_dim=192)
-    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k))
+    en = EncoderConfig(hidden_size=128, num_filters=16, tf_layers=2, tf_heads=4, tf_head_dim=32, tf_intermediate=256,
+                       sliding_window=20, codebook_dim=64, num_quantizers=18)
+    sp = SpeakerEncoderConfig(n_mels=32, channels=(64, 64, 64, 128), kernel_sizes=(5, 3, 3, 1), dilations=(1, 2, 3, 1),
+                              attention_channels=32, res2net_scale=4, se_channels=32, enc_dim=t.hidden_size)
+    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k, enc=en, spk=sp))
 
 
 def tiny(tts_model_type: str = "custom_voice") -> ModelConfig:
@@ -267,4 +398,8 @@ def tiny(tts_model_type: str = "custom_voice") -> ModelConfig:
                             intermediate_size=128, embed_dim=128)
     k = CodecConfig(codebook_dim=32, rvq_out_dim=64, latent_dim=64, tf_hidden=64, tf_intermediate=128,
                     tf_heads=4, tf_head_dim=16, tf_layers=2, decoder_dim=96)
-    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k))
+    en = EncoderConfig(hidden_size=64, num_filters=8, tf_layers=2, tf_heads=4, tf_head_dim=16, tf_intermediate=128,
+                       sliding_window=12, codebook_dim=32, num_quantizers=17)
+    sp = SpeakerEncoderConfig(n_fft=256, hop=64, win=256, n_mels=16, channels=(32, 32, 32, 64), kernel_sizes=(5, 3, 3, 1), dilations=(1, 2, 3, 1),
+                              attention_channels=16, res2net_scale=4, se_channels=16, enc_dim=t.hidden_size)
+    return _with_small_text_vocab(ModelConfig(tts_model_type=tts_model_type, talker=t, cp=c, codec=k, enc=en, spk=sp))

@@ -365,7 +365,12 @@ def export_mlx_checkpoint(ws: WeightStore, model_path: str, extra_config: Option
     save_file(out["model"], os.path.join(model_path, "model.safetensors"))
     if out["speech"]:
         save_file(out["speech"], os.path.join(model_path, "speech_tokenizer", "model.safetensors"))
-    meta = {"tts_model_type": ws.cfg.tts_model_type, "quantization": {"group_size": ws.cfg.quant_group, "bits": 8}}
+    # the checkpoint's own config layout (talker_config / code_predictor_config / spk_id / ... + speech_tokenizer/config.json):
+    # load_model reads the architecture back through config.from_hf_config, exactly as it would for a downloaded folder
+    from .config import to_hf_config
+    meta, speech = to_hf_config(ws.cfg)
     meta.update(extra_config or {})
     with open(os.path.join(model_path, "config.json"), "w") as f:
         json.dump(meta, f)
+    with open(os.path.join(model_path, "speech_tokenizer", "config.json"), "w") as f:
+        json.dump(speech, f)

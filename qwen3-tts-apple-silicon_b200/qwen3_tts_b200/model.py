@@ -116,9 +116,28 @@ class Model:
         user = self.tokenizer.encode("user")[:1] or [11]
         return [c.im_start_id, user[0], nl[0]] + list(self.tokenizer.encode(instruct)) + [c.im_end_id, nl[0]]
 
+    def ref_text_chat_ids(self, ref_text: str) -> List[int]:
+        """<|im_start|>assistant\n{ref_text}<|im_end|>\n  ->  ids[:3] prefix, ids[3:-2] body."""
+        c = self.cfg
+        nl = self.tokenizer.encode("\n")[:1] or [10]
+        return [c.im_start_id, c.assistant_id, nl[0]] + list(self.tokenizer.encode(ref_text)) + [c.im_end_id, nl[0]]
+
+    def ref_code_embeds(self, ref_codes: torch.Tensor) -> torch.Tensor:
+        """[T_ref, G] -> [T_ref, H]: the 16-way embedding sum of every reference frame, added in order g = 0..15 (a8)."""
+        e = self.engine
+        rc = ref_codes.to(e.dev).long()
+        acc = e.codec_embedding[rc[:, 0]]
+        for g in range(1, rc.shape[1]):
+            acc = acc + e.cp_embeddings[g - 1][rc[:, g]]
+        return acc
+
     def build_prefill(self, text_ids: Sequence[int], instruct_ids: Optional[Sequence[int]] = None,
                       speaker: Optional[str] = None, language: Optional[str] = None,
-                      speaker_vec: Optional[torch.Tensor] = None, streaming: bool = False):
+                      speaker_vec: Optional[torch.Tensor] = None, streaming: bool = False,
+                      ref_codes: Optional[torch.Tensor] = None, ref_text_ids: Optional[Sequence[int]] = None):
+        """Prompt embeddings; with `ref_codes` the in-context (voice cloning) layout: the text side
+        P(ref text ++ text) ++ eos paired with E(codec_bos) ++ per-frame code embedding sums of the reference clip
+        (reference call site sessions/clone.py:218-224; mirrors oracle.OracleModel.build_prefill)."""
         e, t, cfg = self.engine, self.cfg.talker, self.cfg
         dev = e.dev
         ids = torch.as_tensor(list(text_ids), dtype=torch.long, device=dev)
@@ -145,6 +164,24 @@ class Model:
         head = e.text_embed(ids[:3])
         mid = torch.cat([pad.expand(n - 2, -1), bos[None]], 0) + codec_seq[:-1]
         segs += [head, mid]
+        if ref_codes is not None:
+            ref_body = torch.as_tensor(list(ref_text_ids), dtype=torch.long, device=dev)[3:-2] if ref_text_ids is not None \
+                else torch.zeros(0, dtype=torch.long, device=dev)
+            text_all = torch.cat([e.text_embed(torch.cat([ref_body, body_ids])), eos[None]], 0)
+            codec_all = torch.cat([cemb([t.codec_bos_id]), self.ref_code_embeds(ref_codes)], 0)
+            t1, t2 = text_all.shape[0], codec_all.shape[0]
+            if streaming:
+                if t1 > t2:
+                    segs.append(text_all[:t2] + codec_all)
+                    trailing = torch.cat([text_all[t2:], pad[None]], 0)
+                else:
+                    segs.append(torch.cat([text_all, pad[None].expand(t2 - t1, -1)], 0) + codec_all)
+                    trailing = pad[None]
+            else:
+                segs.append(text_all + cemb([t.codec_pad_id] * t1))
+                segs.append(codec_all + pad[None])
+                trailing = pad[None]
+            return torch.cat(segs, 0), trailing
         body_e = e.text_embed(body_ids) if len(body_ids) else torch.zeros(0, t.hidden_size, device=dev)
         if not streaming:
             body = torch.cat([body_e, eos[None]], 0) + cemb([t.codec_pad_id] * (len(body_ids) + 1))

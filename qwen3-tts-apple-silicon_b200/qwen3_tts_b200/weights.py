@@ -227,7 +227,78 @@ def make_weights(cfg: ModelConfig, seed: int = 0, device: str = "cpu", keep_fp: 
             add_lin(f"cp.heads.{g}", c.vocab_size, c.hidden_size, std=head_std)
     if "codec" in parts:
         _make_codec(ws, cfg, randn)
+    if "enc" in parts:
+        _make_speech_encoder(ws, cfg, randn)
+    if "spk" in parts:
+        _make_speaker_encoder(ws, cfg, randn)
     return ws
+
+
+def _make_speech_encoder(ws: WeightStore, cfg: ModelConfig, randn):
+    """Speech-tokenizer encoder (Mimi layout, transformers mimi:454-496, 926-1141, 1296-1340), fp32."""
+    e, fp = cfg.enc, ws.fp
+
+    def conv(name, cout, cin, ksz, bias=True):
+        fp[name + ".weight"] = randn(cout, cin, ksz, std=(1.0 / (cin * ksz)) ** 0.5)
+        if bias:
+            fp[name + ".bias"] = randn(cout, std=0.02)
+
+    def lin(name, n, kk):
+        fp[name + ".weight"] = randn(n, kk, std=(1.0 / kk) ** 0.5)
+
+    conv("enc.conv_in", e.num_filters, 1, e.kernel_size)
+    dim = e.num_filters
+    for i, r in enumerate(reversed(e.ratios)):
+        p = f"enc.stages.{i}"
+        conv(p + ".res.conv1", dim // e.compress, dim, e.residual_kernel_size)
+        conv(p + ".res.conv2", dim, dim // e.compress, 1)
+        conv(p + ".down", 2 * dim, dim, 2 * r)
+        dim *= 2
+    conv("enc.conv_out", e.hidden_size, dim, e.last_kernel_size)
+    hd = e.tf_heads * e.tf_head_dim
+    for l in range(e.tf_layers):
+        p = f"enc.tf.layers.{l}"
+        for nm in ("input_norm", "post_norm"):
+            fp[f"{p}.{nm}.weight"] = 1.0 + randn(e.hidden_size, std=0.05)
+            fp[f"{p}.{nm}.bias"] = randn(e.hidden_size, std=0.02)
+        lin(p + ".q_proj", hd, e.hidden_size); lin(p + ".k_proj", hd, e.hidden_size); lin(p + ".v_proj", hd, e.hidden_size)
+        lin(p + ".o_proj", e.hidden_size, hd)
+        lin(p + ".fc1", e.tf_intermediate, e.hidden_size); lin(p + ".fc2", e.hidden_size, e.tf_intermediate)
+        for nm in ("attn_scale", "mlp_scale"):
+            # LayerScale is 0.01 at init (mimi:499-512); 0.3 here so that the branches matter in parity tests
+            fp[f"{p}.{nm}"] = 0.3 * (1.0 + randn(e.hidden_size, std=0.05))
+    conv("enc.downsample", e.hidden_size, e.hidden_size, 4, bias=False)
+    for grp, nq in (("semantic", e.num_semantic), ("acoustic", e.num_quantizers - e.num_semantic)):
+        lin(f"enc.rvq.{grp}.in_proj", e.codebook_dim, e.hidden_size)
+        for i in range(nq):
+            # residual levels shrink: later codebooks are drawn smaller, as trained RVQ codebooks are
+            fp[f"enc.rvq.{grp}.codebooks.{i}.embed_sum"] = randn(e.codebook_size, e.codebook_dim, std=1.0 * (0.7 ** i))
+            fp[f"enc.rvq.{grp}.codebooks.{i}.cluster_usage"] = randn(e.codebook_size, std=0.0) + 1.0
+
+
+def _make_speaker_encoder(ws: WeightStore, cfg: ModelConfig, randn):
+    """ECAPA-TDNN (transformers qwen2_5_omni:2499-2790), fp32."""
+    sc, fp = cfg.spk, ws.fp
+
+    def conv(name, cout, cin, ksz):
+        fp[name + ".weight"] = randn(cout, cin, ksz, std=(1.0 / (cin * ksz)) ** 0.5)
+        fp[name + ".bias"] = randn(cout, std=0.05)
+
+    ch = sc.channels
+    conv("spk.blocks.0.conv", ch[0], sc.n_mels, sc.kernel_sizes[0])
+    for i in range(1, len(ch) - 1):
+        p = f"spk.blocks.{i}"
+        conv(p + ".tdnn1.conv", ch[i], ch[i - 1], 1)
+        w = ch[i] // sc.res2net_scale
+        for j in range(sc.res2net_scale - 1):
+            conv(f"{p}.res2net.{j}.conv", w, w, sc.kernel_sizes[i])
+        conv(p + ".tdnn2.conv", ch[i], ch[i], 1)
+        conv(p + ".se.conv1", sc.se_channels, ch[i], 1)
+        conv(p + ".se.conv2", ch[i], sc.se_channels, 1)
+    conv("spk.mfa.conv", ch[-1], ch[-1], sc.kernel_sizes[-1])
+    conv("spk.asp.tdnn.conv", sc.attention_channels, 3 * ch[-1], 1)
+    conv("spk.asp.conv", ch[-1], sc.attention_channels, 1)
+    conv("spk.fc", sc.enc_dim, 2 * ch[-1], 1)
 
 
 def _make_codec(ws: WeightStore, cfg: ModelConfig, randn):

@@ -272,6 +272,17 @@ def test_generate_audio_writes_audio_000_wav(small_setup, tmp_path):
         assert w.getnframes() == cfg.codec.out_len(5)
 
 
+def _write_small_bpe(folder):
+    """A small byte-level BPE (vocab.json + merges.txt) trained on the spot: the Qwen vocabulary files are not available
+    offline, the code path (tokenizers BPE + Qwen2 pre-tokenizer split + byte-level alphabet) is the same."""
+    from tokenizers import Tokenizer, models, pre_tokenizers, trainers
+    tok = Tokenizer(models.BPE())
+    tok.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tr = trainers.BpeTrainer(vocab_size=600, initial_alphabet=pre_tokenizers.ByteLevel.alphabet(), special_tokens=[])
+    tok.train_from_iterator(["hello there general kenobi", "the quick brown fox jumps over the lazy dog 123 times!", "user assistant"] * 20, tr)
+    tok.model.save(folder)
+
+
 def test_mlx_checkpoint_folder_loads_and_generates_identical_codes(small_setup, tmp_path):
     """`load_model(<folder with model.safetensors>)` (reference io.py:111-112) reads the MLX affine 8-bit
     layout; the engine built from it must produce exactly the codes of the engine built from the in-memory store."""
@@ -280,8 +291,20 @@ def test_mlx_checkpoint_folder_loads_and_generates_identical_codes(small_setup, 
     cfg, ws, model, oracle = small_setup
     d = tmp_path / "models" / "Qwen3-TTS-12Hz-small-CustomVoice-8bit"
     d.mkdir(parents=True)
-    ML.export_mlx_checkpoint(ws, str(d), extra_config={"b200_config": cfg.to_dict(), "tts_model_type": "custom_voice"})
+    ML.export_mlx_checkpoint(ws, str(d))             # config.json in the checkpoint's own layout (talker_config, spk_id, ...)
+    import json
+    meta = json.load(open(d / "config.json"))
+    assert "talker_config" in meta and "b200_config" not in meta and meta["talker_config"]["spk_id"]["ryan"] == cfg.talker.spk_id["ryan"]
+    with pytest.raises(ValueError):                  # real weights without a tokenizer must not load
+        load_model(str(d), max_frames=64, max_ctx=256, max_trailing=64)
+    _write_small_bpe(str(d))                         # vocab.json + merges.txt, the files Qwen folders ship
     m2 = load_model(str(d), max_frames=64, max_ctx=256, max_trailing=64)
+    assert m2.cfg.to_dict() == cfg.to_dict()
+    # text -> ids through the real BPE path, then the whole reference-facing call
+    ids_bpe = m2.tokenizer.encode("Hello there, general Kenobi!")
+    assert len(ids_bpe) >= 4 and max(ids_bpe) < cfg.talker.text_vocab_size and m2.tokenizer.tok.decode(ids_bpe) == "Hello there, general Kenobi!"
+    res = list(m2.generate("Hello there, general Kenobi!", voice="ryan", greedy=True, max_tokens=4))
+    assert len(res) == 1 and res[0].samples == cfg.codec.out_len(4)
     ids = _text_ids(cfg, 9, 5)
     outs = []
     for m in (model, m2):

@@ -257,3 +257,115 @@ def test_next_input_sum_matches_cousin_driver(tiny):
     embs = [ws.fp["talker.codec_embedding"][5]] + [ws.fp[f"cp.embeddings.{g}"][c] for g, c in enumerate(codes)]
     assert len(codes) == cfg.cp.num_code_groups - 1
     assert torch.allclose(acc, torch.stack(embs).sum(0), rtol=1e-6, atol=1e-7)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# reference-clip side (voice cloning): speech-tokenizer ENCODER vs transformers MimiModel.encode, speaker encoder vs
+# transformers ECAPA_TimeDelayNet, mel filter bank vs transformers.audio_utils.mel_filter_bank
+# ------------------------------------------------------------------------------------------------------------------------
+def _mimi_from_store(cfg, w):
+    from transformers import MimiConfig, MimiModel
+    e = cfg.enc
+    mc = MimiConfig(hidden_size=e.hidden_size, num_filters=e.num_filters, upsampling_ratios=list(e.ratios), kernel_size=e.kernel_size,
+                    last_kernel_size=e.last_kernel_size, residual_kernel_size=e.residual_kernel_size, compress=e.compress,
+                    num_hidden_layers=e.tf_layers, num_attention_heads=e.tf_heads, num_key_value_heads=e.tf_heads, head_dim=e.tf_head_dim,
+                    intermediate_size=e.tf_intermediate, sliding_window=e.sliding_window, norm_eps=e.norm_eps,
+                    codebook_size=e.codebook_size, codebook_dim=e.codebook_dim, vector_quantization_hidden_dimension=e.codebook_dim,
+                    num_quantizers=e.num_quantizers, num_semantic_quantizers=e.num_semantic, upsample_groups=e.hidden_size,
+                    rope_parameters={"rope_type": "default", "rope_theta": e.rope_theta})
+    mc._attn_implementation = "eager"
+    m = MimiModel(mc).eval()
+    with torch.no_grad():
+        L = m.encoder.layers
+        L[0].conv.weight.copy_(w["enc.conv_in.weight"]); L[0].conv.bias.copy_(w["enc.conv_in.bias"])
+        for i in range(len(e.ratios)):
+            rb, dn, p = L[1 + 3 * i], L[3 + 3 * i], f"enc.stages.{i}"
+            rb.block[1].conv.weight.copy_(w[p + ".res.conv1.weight"]); rb.block[1].conv.bias.copy_(w[p + ".res.conv1.bias"])
+            rb.block[3].conv.weight.copy_(w[p + ".res.conv2.weight"]); rb.block[3].conv.bias.copy_(w[p + ".res.conv2.bias"])
+            dn.conv.weight.copy_(w[p + ".down.weight"]); dn.conv.bias.copy_(w[p + ".down.bias"])
+        L[-1].conv.weight.copy_(w["enc.conv_out.weight"]); L[-1].conv.bias.copy_(w["enc.conv_out.bias"])
+        for l, ly in enumerate(m.encoder_transformer.layers):
+            p = f"enc.tf.layers.{l}"
+            ly.input_layernorm.weight.copy_(w[p + ".input_norm.weight"]); ly.input_layernorm.bias.copy_(w[p + ".input_norm.bias"])
+            ly.post_attention_layernorm.weight.copy_(w[p + ".post_norm.weight"]); ly.post_attention_layernorm.bias.copy_(w[p + ".post_norm.bias"])
+            for nm in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                getattr(ly.self_attn, nm).weight.copy_(w[f"{p}.{nm}.weight"])
+            ly.mlp.fc1.weight.copy_(w[p + ".fc1.weight"]); ly.mlp.fc2.weight.copy_(w[p + ".fc2.weight"])
+            ly.self_attn_layer_scale.scale.copy_(w[p + ".attn_scale"]); ly.mlp_layer_scale.scale.copy_(w[p + ".mlp_scale"])
+        m.downsample.conv.weight.copy_(w["enc.downsample.weight"])
+        for grp, rvq in (("semantic", m.quantizer.semantic_residual_vector_quantizer), ("acoustic", m.quantizer.acoustic_residual_vector_quantizer)):
+            rvq.input_proj.weight.copy_(w[f"enc.rvq.{grp}.in_proj.weight"][..., None])
+            for i, ly in enumerate(rvq.layers):
+                ly.codebook.embed_sum.copy_(w[f"enc.rvq.{grp}.codebooks.{i}.embed_sum"])
+                ly.codebook.cluster_usage.copy_(w[f"enc.rvq.{grp}.codebooks.{i}.cluster_usage"])
+                ly.codebook._embed = None
+    return m
+
+
+@pytest.mark.parametrize("n_samples", [24000, 30001, 1919])
+def test_speech_encoder_matches_mimi_encode(n_samples):
+    """Oracle of SURVEY 8f-2 against the cousin: identical code indices for every quantizer and frame, ragged lengths
+    included (the right padding that completes the last frame, mimi:273-285)."""
+    from oracle import qwen3_tts_encoders_oracle as E
+    cfg = Cfg.small("base")
+    ws = make_weights(cfg, seed=4, parts=("enc",))
+    m = _mimi_from_store(cfg, ws.fp)
+    wav = torch.randn(2, n_samples, generator=torch.Generator().manual_seed(n_samples)) * 0.3
+    with torch.no_grad():
+        ref = m.encode(wav[:, None], num_quantizers=cfg.enc.valid_quantizers).audio_codes
+        rec = {}
+        got = E.speech_encode(ws.fp, cfg.enc, wav, rec)
+        emb_ref = m.downsample(m.encoder_transformer(m.encoder(wav[:, None]).transpose(1, 2))[0].transpose(1, 2))
+    assert got.shape == ref.shape == (2, cfg.enc.valid_quantizers, -(-n_samples // cfg.enc.hop))
+    assert float((rec["embeddings"] - emb_ref).abs().max()) <= 1e-5 * float(emb_ref.abs().max())
+    assert torch.equal(got, ref)
+
+
+def test_speaker_encoder_matches_ecapa_cousin():
+    """Oracle of SURVEY 8f-3 against transformers' ECAPA_TimeDelayNet (same blocks: TDNN with reflect 'same' padding,
+    Res2Net, squeeze-excitation, attentive statistics pooling, 1x1 output conv)."""
+    from oracle import qwen3_tts_encoders_oracle as E
+    from transformers.models.qwen2_5_omni.configuration_qwen2_5_omni import Qwen2_5OmniDiTConfig
+    from transformers.models.qwen2_5_omni.modeling_qwen2_5_omni import ECAPA_TimeDelayNet
+    cfg = Cfg.small("base")
+    sc = cfg.spk
+    ws = make_weights(cfg, seed=5, parts=("spk",))
+    w = ws.fp
+    dc = Qwen2_5OmniDiTConfig(mel_dim=sc.n_mels, enc_dim=sc.enc_dim, enc_channels=list(sc.channels), enc_kernel_sizes=list(sc.kernel_sizes),
+                              enc_dilations=list(sc.dilations), enc_attention_channels=sc.attention_channels,
+                              enc_res2net_scale=sc.res2net_scale, enc_se_channels=sc.se_channels)
+    m = ECAPA_TimeDelayNet(dc).eval()
+    with torch.no_grad():
+        def cp(conv, name):
+            conv.weight.copy_(w[name + ".weight"]); conv.bias.copy_(w[name + ".bias"])
+        cp(m.blocks[0].conv, "spk.blocks.0.conv")
+        for i in range(1, len(sc.channels) - 1):
+            b, p = m.blocks[i], f"spk.blocks.{i}"
+            cp(b.tdnn1.conv, p + ".tdnn1.conv"); cp(b.tdnn2.conv, p + ".tdnn2.conv")
+            for j, blk in enumerate(b.res2net_block.blocks):
+                cp(blk.conv, f"{p}.res2net.{j}.conv")
+            cp(b.se_block.conv1, p + ".se.conv1"); cp(b.se_block.conv2, p + ".se.conv2")
+        cp(m.mfa.conv, "spk.mfa.conv"); cp(m.asp.tdnn.conv, "spk.asp.tdnn.conv"); cp(m.asp.conv, "spk.asp.conv"); cp(m.fc, "spk.fc")
+    mel = torch.randn(2, 57, sc.n_mels, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref = m(mel)
+        got = E.ecapa_forward(w, sc, mel)
+    assert got.shape == ref.shape == (2, sc.enc_dim)
+    assert float((got - ref).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_mel_front_end_pins():
+    """Slaney mel filter bank == transformers.audio_utils.mel_filter_bank; the STFT magnitude of a pure tone peaks in the
+    right mel bin and the frame count follows the hop."""
+    from oracle import qwen3_tts_encoders_oracle as E
+    from transformers.audio_utils import mel_filter_bank
+    sc = Cfg.full("base").spk
+    fb = E.mel_filter_bank(sc.n_fft, sc.n_mels, sc.sample_rate, sc.fmin, sc.fmax)
+    ref = torch.from_numpy(mel_filter_bank(sc.n_fft // 2 + 1, sc.n_mels, sc.fmin, sc.fmax, sc.sample_rate, norm="slaney", mel_scale="slaney")).float()
+    assert fb.shape == ref.shape == (513, 128)
+    assert float((fb - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+    t = torch.arange(24000) / 24000.0
+    mel = E.log_mel(torch.sin(2 * torch.pi * 1000.0 * t)[None], sc)
+    assert mel.shape == (1, 24000 // sc.hop, sc.n_mels)
+    centers = E.mel_to_hz_slaney(torch.linspace(float(E.hz_to_mel_slaney(sc.fmin)), float(E.hz_to_mel_slaney(sc.fmax)), sc.n_mels + 2))[1:-1]
+    assert abs(float(centers[int(mel[0, 40].argmax())]) - 1000.0) < 60.0
