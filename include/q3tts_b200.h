@@ -324,7 +324,9 @@ int q3t_frame(const q3t_frame_args* f, void* stream);
 int q3t_rvq_gather_sum(const int* codes, const float* const* tables_host, int B, int G, int T, int g_lo, int g_hi,
                        int dim, int codebook_size, float* out, void* stream);
 
-enum { Q3T_ACT_NONE = 0, Q3T_ACT_SILU = 1, Q3T_ACT_GELU = 2, Q3T_ACT_SNAKE = 3, Q3T_ACT_SWIGLU_PAIR = 4 };
+enum { Q3T_ACT_NONE = 0, Q3T_ACT_SILU = 1, Q3T_ACT_GELU = 2, Q3T_ACT_SNAKE = 3, Q3T_ACT_SWIGLU_PAIR = 4,
+       /* reference-clip encoders (speech-tokenizer encoder: ELU; ECAPA speaker encoder: ReLU, sigmoid, tanh) */
+       Q3T_ACT_ELU = 5, Q3T_ACT_RELU = 6, Q3T_ACT_SIGMOID = 7, Q3T_ACT_TANH = 8 };
 
 /* Generic causal tap-GEMM:  out[b, t*up + p, co] = epi( bias[co] + sum_{j<taps} sum_ci A[b, t + shift_j, ci] * W[j][p*Cout + co][ci] )
  *   conv1d (k taps, dilation d): up = 1, shift_j = -(k-1-j)*d          (rows before 0 read as zero)
@@ -342,6 +344,8 @@ typedef struct {
     const float* resid;                        /* [B, T_out_rows*up, Cout] or NULL */
     float* out_raw;                            /* or NULL */
     float* out_act; int act; const float* act_a; const float* act_b;
+    int force_fp32;                            /* != 0: FP32-pipe kernel even where the tcgen05 TF32 path is eligible (the
+                                                  reference-clip encoders: a nearest-codebook search follows) */
 } q3t_tapgemm_args;
 
 int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream);
@@ -369,6 +373,29 @@ int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, co
 
 /* final: clamp(x, -1, 1) and optional PCM16 conversion */
 int q3t_clamp_pcm16(const float* x, long long n, float* y, int16_t* pcm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Reference-clip side of voice cloning (replaces what generate_audio(ref_audio=, ref_text=) makes mlx_audio compute from the
+ * clip: reference sessions/clone.py:218-224): operators of the speech-tokenizer ENCODER (Mimi) and of the ECAPA-TDNN speaker
+ * encoder that are not convolutions / linears (those are q3t_tapgemm calls with force_fp32).  fp32, time-major [B, T, C].
+ * ------------------------------------------------------------------------------------------- */
+/* residual VQ encode (transformers mimi:1197-1203, 1262-1281): x [n_vectors, dim]; tables HOST array of n_levels device
+ * ptrs [codebook_size, dim]; level l: idx = argmin_e sum_d (res - table_l[e])^2 (lowest index on ties), res -= table_l[idx].
+ * idx_out[l * idx_level_stride + v] int32; resid_out [n_vectors, dim] (final residual) or NULL. */
+int q3t_rvq_encode(const float* x, const float* const* tables_host, int n_vectors, int n_levels, int codebook_size, int dim,
+                   long long idx_level_stride, int* idx_out, float* resid_out, void* stream);
+/* (weighted) mean and std over time per channel: w [B, T, C] weights summing to 1 over T, or NULL for 1/T;
+ * std = sqrt(max(sum w (x - mean)^2, eps))  (attentive statistics pooling, qwen2_5_omni:2654-2679) */
+int q3t_time_stats(const float* x, const float* w, int B, int T, int C, float eps, float* mean, float* stdv, void* stream);
+/* softmax over the time axis per (b, c) */
+int q3t_softmax_time(const float* x, int B, int T, int C, float* y, void* stream);
+/* op 0: out = a + b;  op 1: out = tanh(a);  op 2: out = a * b[item, c] + r  (b [n / per_item, C] channel gates, r or NULL) */
+int q3t_eltwise(int op, const float* a, const float* b, const float* r, long long n, int C, long long per_item, float* out, void* stream);
+/* mel front end tail: spec [rows, ld] = re (cols 0..n_freq-1) | im (cols n_freq..2 n_freq-1) of the STFT frames ->
+ * out [rows, n_mels] = log(max(fb^T sqrt(re^2 + im^2 + 1e-9), 1e-5)),  fb [n_freq, n_mels] */
+int q3t_mel(const float* spec, long long rows, int ld, int n_freq, const float* fb, int n_mels, float* out, void* stream);
+/* LayerNorm over the channel axis with weight and bias */
+int q3t_layernorm(const float* x, const float* w, const float* b, long long rows, int C, float eps, float* y, void* stream);
 
 #ifdef __cplusplus
 }

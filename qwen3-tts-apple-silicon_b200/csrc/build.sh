@@ -8,7 +8,7 @@ ARCH=(-gencode arch=compute_100a,code=sm_100a)
 FLAGS=("${ARCH[@]}" -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -diag-suppress 177)
 objs=(); pids=()
 mkdir -p "$here/build"
-for f in glue w8_gemv w8_gemm_tc attn_decode attn_prefill sampler engine codec tapgemm_tc frame_ll; do
+for f in glue w8_gemv w8_gemm_tc attn_decode attn_prefill sampler engine codec tapgemm_tc encoders frame_ll; do
   src="$here/$f.cu"; obj="$here/build/$f.o"
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ "$here/common.cuh" -nt "$obj" ] || [ "$here/sampler.cuh" -nt "$obj" ] || [ "$here/../../include/q3tts_b200.h" -nt "$obj" ]; then
     "$NVCC" "${FLAGS[@]}" -c "$src" -o "$obj" &

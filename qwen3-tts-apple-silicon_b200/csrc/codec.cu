@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const TapGemmParams
                 if (p.act == Q3T_ACT_SNAKE) { const float sn = sinf(x * p.act_a[c]); x = x + p.act_b[c] * (sn * sn); }
                 else if (p.act == Q3T_ACT_GELU) x = gelu_erf(x);
                 else if (p.act == Q3T_ACT_SILU) x = silu_f(x);
+                else if (p.act >= Q3T_ACT_ELU) x = act_simple(x, p.act);
                 p.out_act[m * p.N + n] = x;
             }
         }
@@ -297,12 +298,12 @@ extern "C" int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream) {
     {   // tensor-core implicit GEMM (tcgen05, TF32) for every eligible layer; Q3T_CODEC_TC=0 forces the FP32-pipe kernel
         static int use_tc = -1;
         if (use_tc < 0) { const char* e = getenv("Q3T_CODEC_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
-        if (use_tc && (long long)a->B * a->T_out_rows > 0) {
+        if (use_tc && !a->force_fp32 && (long long)a->B * a->T_out_rows > 0) {
             const int rc = q3t::launch_tapgemm_tc(a, (cudaStream_t)stream);
             if (rc >= 0) { q3t::g_tap_stats[0]++; return rc; }
         }
     }
-    q3t::g_tap_stats[(a->Cin % 32 == 0) ? 1 : 2]++;
+    q3t::g_tap_stats[(a->Cin % 32 == 0 && !a->force_fp32) ? 1 : 2]++;
     TapGemmParams p;
     p.A = a->A; p.B = a->B; p.T_in = a->T_in; p.Cin = a->Cin; p.W = a->W; p.bias = a->bias; p.taps = a->taps;
     for (int i = 0; i < 8; ++i) p.shift[i] = a->shift[i];

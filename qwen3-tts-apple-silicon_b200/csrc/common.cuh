@@ -93,5 +93,13 @@ __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u <
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + expf(-x)); }
+// pointwise activations of the reference-clip encoders (Q3T_ACT_ELU .. Q3T_ACT_TANH); ELU with alpha = 1 (torch default)
+__device__ __forceinline__ float act_simple(float x, int act) {
+    if (act == 5) return x > 0.f ? x : expm1f(x);
+    if (act == 6) return fmaxf(x, 0.f);
+    if (act == 7) return 1.f / (1.f + expf(-x));
+    if (act == 8) return tanhf(x);
+    return x;
+}
 
 }  // namespace q3t

@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                     if (p.act == Q3T_ACT_SNAKE) { const float sn = sinf(x * p.act_a[c]); x = x + p.act_b[c] * (sn * sn); }
                     else if (p.act == Q3T_ACT_GELU) x = tt_gelu_erf(x);
                     else if (p.act == Q3T_ACT_SILU) x = silu_f(x);
+                    else if (p.act >= Q3T_ACT_ELU) x = act_simple(x, p.act);
                     p.out_act[(m_base + r) * p.N + n] = tt_round_tf32(x);
                 }
             }

@@ -113,12 +113,38 @@ KEY_RULES: List[Tuple[str, str]] = [
      lambda m: f"codec.dec.blocks.{int(m.group(1)) - 1}.units.{int(m.group(2)) - 2}.conv{m.group(3)}"),
     (r"^decoder\.decoder\.5$", "codec.dec.snake_out"),
     (r"^decoder\.decoder\.6(?:\.conv)?$", "codec.dec.conv_out"),
+    # ---- speech tokenizer ENCODER (a Mimi model: cousin module tree transformers mimi/modeling_mimi.py:454-496, 1411-1452)
+    (r"^encoder\.encoder\.layers\.0\.conv$", "enc.conv_in"),
+    (r"^encoder\.encoder\.layers\.(\d+)\.block\.([13])\.conv$",
+     lambda m: f"enc.stages.{(int(m.group(1)) - 1) // 3}.res.conv{1 if m.group(2) == '1' else 2}"),
+    (r"^encoder\.encoder\.layers\.(\d+)\.conv$",
+     lambda m: f"enc.stages.{int(m.group(1)) // 3 - 1}.down" if int(m.group(1)) % 3 == 0 else "enc.conv_out"),
+    (r"^encoder\.encoder_transformer\.layers\.(\d+)\.self_attn_layer_scale$", r"enc.tf.layers.\1.attn_scale"),
+    (r"^encoder\.encoder_transformer\.layers\.(\d+)\.mlp_layer_scale$", r"enc.tf.layers.\1.mlp_scale"),
+    (r"^encoder\.encoder_transformer\.layers\.(\d+)\.mlp\.fc([12])$", r"enc.tf.layers.\1.fc\2"),
+] + [(rf"^encoder\.encoder_transformer\.layers\.(\d+)\.{a}$", rf"enc.tf.layers.\1.{b}") for a, b in _LAYER[:6]] + [
+    (r"^encoder\.downsample\.conv$", "enc.downsample"),
+    (r"^encoder\.quantizer\.(semantic|acoustic)_residual_vector_quantizer\.input_proj$", r"enc.rvq.\1.in_proj"),
+    (r"^encoder\.quantizer\.(semantic|acoustic)_residual_vector_quantizer\.layers\.(\d+)\.codebook\.(?:embedding_sum|embed_sum)$",
+     r"enc.rvq.\1.codebooks.\2.embed_sum"),
+    (r"^encoder\.quantizer\.(semantic|acoustic)_residual_vector_quantizer\.layers\.(\d+)\.codebook\.cluster_usage$",
+     r"enc.rvq.\1.codebooks.\2.cluster_usage"),
+    # ---- speaker encoder (ECAPA-TDNN: cousin module tree transformers qwen2_5_omni/modeling_qwen2_5_omni.py:2717-2790)
+    (r"^speaker_encoder\.blocks\.0\.conv$", "spk.blocks.0.conv"),
+    (r"^speaker_encoder\.blocks\.(\d+)\.tdnn([12])\.conv$", r"spk.blocks.\1.tdnn\2.conv"),
+    (r"^speaker_encoder\.blocks\.(\d+)\.res2net_block\.blocks\.(\d+)\.conv$", r"spk.blocks.\1.res2net.\2.conv"),
+    (r"^speaker_encoder\.blocks\.(\d+)\.se_block\.conv([12])$", r"spk.blocks.\1.se.conv\2"),
+    (r"^speaker_encoder\.mfa\.conv$", "spk.mfa.conv"),
+    (r"^speaker_encoder\.asp\.tdnn\.conv$", "spk.asp.tdnn.conv"),
+    (r"^speaker_encoder\.asp\.conv$", "spk.asp.conv"),
+    (r"^speaker_encoder\.fc$", "spk.fc"),
 ]
 
 _SUFFIXES = (".weight", ".bias", ".scales", ".biases", ".alpha", ".beta", ".gamma", ".scale",
              ".embed_sum", ".embedding_sum", ".cluster_usage")
 # tensors of the checkpoint that the generation hot path never reads (encoder side, speaker encoder, ...)
-IGNORED = (r"^encoder\.", r"^speaker_encoder\.", r"\.rotary_emb\.", r"^decoder\.quantizer\..*\.input_proj", r"\.initialized$")
+IGNORED = (r"^encoder\.(decoder|decoder_transformer|upsample)\.", r"^encoder\.quantizer\..*\.output_proj", r"\.rotary_emb\.",
+           r"^decoder\.quantizer\..*\.input_proj", r"\.initialized$")
 
 
 def split_key(key: str) -> Tuple[str, str]:
@@ -202,6 +228,7 @@ def load_mlx_checkpoint(model_path: str, cfg: ModelConfig, device: str = "cpu", 
     if expected is None:
         from .weights import expected_shapes
         expected = expected_shapes(cfg)             # meta tensors: names + shapes only, nothing is materialised
+        # (the reference-clip encoders are expected for the Base model; other folders may or may not carry them)
     ws = WeightStore(cfg)
     raw: Dict[str, torch.Tensor] = {}
     unmapped: List[str] = []
@@ -327,7 +354,39 @@ def _export_name(name: str) -> Tuple[str, str]:
     if m:
         part = f"act{m.group(4)}" if m.group(3) == "snake" else f"conv{m.group(4)}.conv"
         return "speech", f"decoder.decoder.{int(m.group(1)) + 1}.block.{int(m.group(2)) + 2}.{part}"
+    m = re.match(r"^enc\.stages\.(\d+)\.(res\.conv1|res\.conv2|down)$", name)
+    if m:
+        i = int(m.group(1))
+        part = {"res.conv1": f"{1 + 3 * i}.block.1.conv", "res.conv2": f"{1 + 3 * i}.block.3.conv", "down": f"{3 + 3 * i}.conv"}[m.group(2)]
+        return "speech", f"encoder.encoder.layers.{part}"
+    if name == "enc.conv_in":
+        return "speech", "encoder.encoder.layers.0.conv"
+    if name == "enc.conv_out":
+        return "speech", f"encoder.encoder.layers.{2 + 3 * _N_ENC_STAGES[0]}.conv"
+    if name == "enc.downsample":
+        return "speech", "encoder.downsample.conv"
+    m = re.match(r"^enc\.tf\.layers\.(\d+)\.(\w+)$", name)
+    if m:
+        part = {"attn_scale": "self_attn_layer_scale", "mlp_scale": "mlp_layer_scale", "fc1": "mlp.fc1", "fc2": "mlp.fc2"}.get(m.group(2)) \
+            or _INV_LAYER[m.group(2)]
+        return "speech", f"encoder.encoder_transformer.layers.{m.group(1)}.{part}"
+    m = re.match(r"^enc\.rvq\.(semantic|acoustic)\.in_proj$", name)
+    if m:
+        return "speech", f"encoder.quantizer.{m.group(1)}_residual_vector_quantizer.input_proj"
+    m = re.match(r"^enc\.rvq\.(semantic|acoustic)\.codebooks\.(\d+)\.(embed_sum|cluster_usage)$", name)
+    if m:
+        return "speech", f"encoder.quantizer.{m.group(1)}_residual_vector_quantizer.layers.{m.group(2)}.codebook.{m.group(3)}"
+    m = re.match(r"^spk\.blocks\.(\d+)\.(tdnn[12]\.conv|res2net\.(\d+)\.conv|se\.conv[12])$", name)
+    if m:
+        part = m.group(2)
+        part = part.replace("res2net.", "res2net_block.blocks.").replace("se.", "se_block.")
+        return "model", f"speaker_encoder.blocks.{m.group(1)}.{part}"
+    if name.startswith("spk."):
+        return "model", "speaker_encoder." + name[len("spk."):]
     raise KeyError(name)
+
+
+_N_ENC_STAGES = [4]
 
 
 def export_mlx_checkpoint(ws: WeightStore, model_path: str, extra_config: Optional[dict] = None) -> None:
@@ -336,6 +395,7 @@ def export_mlx_checkpoint(ws: WeightStore, model_path: str, extra_config: Option
     if save_file is None:
         raise RuntimeError("the safetensors package is required")
     out = {"model": {}, "speech": {}}
+    _N_ENC_STAGES[0] = len(ws.cfg.enc.ratios)
     for stem, (q, s, b) in ws.q.items():
         f, key = _export_name(stem)
         w, sc, bi = pack_mlx_affine(q.cpu(), s.cpu(), b.cpu())

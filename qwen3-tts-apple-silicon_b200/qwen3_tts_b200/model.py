@@ -9,7 +9,6 @@ kinds of the reference map to `tts_model_type`:
 """
 from __future__ import annotations
 
-import hashlib
 import json
 import os
 import time
@@ -101,6 +100,10 @@ class Model:
                                    max_trailing=max_trailing, prefill=prefill)
         self.codec = CodecDecoder(cfg, ws, device)
         self.tokenizer = _load_tokenizer(model_path, cfg, require=require_tokenizer)
+        # reference-clip encoders (voice cloning): built on first use from the enc.* / spk.* tensors of the store
+        self._ref_weights = {n: t for n, t in ws.fp.items() if n.startswith("enc.") or n.startswith("spk.")}
+        self._speech_encoder = self._speaker_encoder = None
+        self._ref_cache = {}
 
     # ---- prompt assembly (mirrors oracle.OracleModel.build_prefill) -------------------------
     def chat_ids(self, text: str) -> List[int]:
@@ -204,12 +207,17 @@ class Model:
             codes = codes[: int(eos[0, 0])]
         return codes
 
-    def stream_codes(self, prefill: torch.Tensor, trailing: torch.Tensor, max_frames: int, interval: int = 25):
+    def stream_codes(self, prefill: torch.Tensor, trailing: torch.Tensor, max_frames: int, interval: int = 25,
+                     ref_codes: Optional[torch.Tensor] = None):
         """Streaming generation (BASELINE config 3): frames are produced one persistent launch at a time and every
         `interval` frames the codec decodes the new ones with its left context.  Yields (codes [n, 16], wav [n * hop])
         per interval; the concatenated pieces are bit-identical to generate_codes() followed by
-        CodecDecoder.decode(chunk_size=interval).  One host synchronisation per interval (the EOS check)."""
+        CodecDecoder.decode(chunk_size=interval).  One host synchronisation per interval (the EOS check).
+        `ref_codes` [T_ref, 16] (voice cloning): the reference frames precede the generated ones in the codec's left context, as in
+        the offline path that decodes ref ++ new and cuts the reference span off."""
         e = self.engine
+        n_ref = 0 if ref_codes is None else int(ref_codes.shape[0])
+        ref_t = None if ref_codes is None else ref_codes.to(e.dev, torch.int32).t()[None].contiguous()
         assert max_frames <= e.max_frames and interval >= 1
         e.prefill(prefill[None], None, trailing[None])
         eos_id = self.cfg.talker.codec_eos_id
@@ -224,7 +232,10 @@ class Model:
             if stop:
                 end = start + int(eos[0, 0])
             if end > start:
-                wav = self.codec.decode_interval(e.codes[0, :end].t()[None].contiguous(), start, end)[0]
+                cur = e.codes[0, :end].t()[None].contiguous()
+                if ref_t is not None:
+                    cur = torch.cat([ref_t, cur], -1)
+                wav = self.codec.decode_interval(cur, n_ref + start, n_ref + end)[0]
                 yield e.codes[0, start:end], wav
             if stop:
                 return
@@ -255,14 +266,16 @@ class Model:
         self.engine.set_sampling(do_sample=not greedy, temperature=temperature or 0.9, top_k=top_k, top_p=top_p,
                                  repetition_penalty=repetition_penalty, seed=seed)
         language = None if lang_code in (None, "auto") else lang_code
-        speaker, speaker_vec, streaming, ref_codes = None, None, False, None
+        speaker, speaker_vec, streaming, ref_codes, ref_ids = None, None, False, None, None
         ins = self.instruct_ids(instruct) if instruct else None
         if mode == "custom_voice":
             if voice is not None and voice.lower() not in self.cfg.talker.spk_id:
                 raise ValueError(f"unknown speaker '{voice}'")
             speaker = voice
         elif mode == "base" and ref_audio is not None:
+            # in-context cloning: codes of the clip + its transcript in the prompt, speaker vector in the speaker slot
             ref_codes, speaker_vec = self._reference_prompt(ref_audio)
+            ref_ids = self.ref_text_chat_ids(ref_text if ref_text else ".")          # the reference passes "." without a transcript (clone.py:148-150)
             streaming = True
         segments = segment_text(text, max_segment_chars)
         if len(segments) > 1:
@@ -278,11 +291,13 @@ class Model:
                     yield r
             return
         ids = self.chat_ids(text)
-        prefill, trailing = self.build_prefill(ids, ins, speaker, language, speaker_vec, streaming)
+        prefill, trailing = self.build_prefill(ids, ins, speaker, language, speaker_vec, streaming, ref_codes=ref_codes, ref_text_ids=ref_ids)
+        if trailing.shape[0] > self.engine.max_trailing:
+            raise ValueError(f"text of {trailing.shape[0]} trailing tokens exceeds max_trailing={self.engine.max_trailing}")
         max_frames = min(max_tokens, self.engine.max_frames)
         if stream:
             interval = max(1, int(round(streaming_interval * self.sample_rate / self.cfg.codec.hop)))
-            for i, (c, w) in enumerate(self.stream_codes(prefill, trailing, max_frames, interval)):
+            for i, (c, w) in enumerate(self.stream_codes(prefill, trailing, max_frames, interval, ref_codes=ref_codes)):
                 audio = w.float().cpu().numpy()
                 dt = time.perf_counter() - t0
                 dur = audio.shape[0] / self.sample_rate
@@ -292,7 +307,13 @@ class Model:
                 t0 = time.perf_counter()
             return
         codes = self.generate_codes(prefill, trailing, max_frames)
-        wav = self.decode(codes)
+        if ref_codes is not None and codes.shape[0] > 0:
+            # decode ref ++ new and cut the reference span off the front (proportional cut, SURVEY App. C last line)
+            n_ref = int(ref_codes.shape[0])
+            wav = self.decode(torch.cat([ref_codes.to(codes.device, codes.dtype), codes], 0))
+            wav = wav[int(n_ref / (n_ref + codes.shape[0]) * wav.shape[0]):]
+        else:
+            wav = self.decode(codes)
         audio = wav.float().cpu().numpy()
         dt = time.perf_counter() - t0
         dur = audio.shape[0] / self.sample_rate
@@ -301,15 +322,28 @@ class Model:
                                real_time_factor=(dur / dt if dt > 0 else 0.0), codes=codes.cpu().numpy())
 
     def _reference_prompt(self, ref_audio: str):
-        """Voice-cloning prompt.  The speech-tokenizer ENCODER and the ECAPA speaker encoder are 'next' rows
-        (SURVEY 8f-2/3); until they exist the reference clip is reduced to a deterministic synthetic code
-        prompt + speaker vector derived from the file contents (BASELINE.json config 3 does the same)."""
-        with open(ref_audio, "rb") as f:
-            digest = hashlib.sha256(f.read()).digest()
-        g = torch.Generator().manual_seed(int.from_bytes(digest[:8], "little") & 0x7fffffff)
-        n_ref = 38
-        codes = torch.randint(0, self.cfg.codec.codebook_size, (n_ref, self.cfg.cp.num_code_groups), generator=g)
-        vec = torch.randn(self.cfg.talker.hidden_size, generator=g) * 0.02
+        """Voice-cloning prompt of the clip at `ref_audio` (24 kHz mono PCM16, what the reference hands over: clone.py:140,158;
+        io.py:243-247): (codes [T_ref, 16] from the speech-tokenizer encoder, speaker vector [H] from the ECAPA speaker encoder).
+        Both run on the GPU (qwen3_tts_b200/encoders.py); the result is cached per file so the segments of a long text share it."""
+        st = os.stat(ref_audio)
+        key = (os.path.abspath(ref_audio), st.st_mtime_ns, st.st_size)
+        if key in self._ref_cache:
+            return self._ref_cache[key]
+        if self._speech_encoder is None:
+            from .encoders import SpeakerEncoder, SpeechEncoder
+            if not any(n.startswith("enc.") for n in self._ref_weights) or not any(n.startswith("spk.") for n in self._ref_weights):
+                raise ValueError("this checkpoint holds no speech-tokenizer encoder / speaker encoder: ref_audio needs the Base model")
+            store = WeightStore(self.cfg)
+            store.fp = self._ref_weights
+            self._speech_encoder = SpeechEncoder(self.cfg, store, self.device)
+            self._speaker_encoder = SpeakerEncoder(self.cfg, store, self.device)
+        from .encoders import read_wav
+        wav = read_wav(ref_audio, self.sample_rate).to(self.engine.dev)[None]
+        if wav.shape[1] < self.cfg.spk.n_fft:
+            raise ValueError(f"{ref_audio}: reference clip too short ({wav.shape[1]} samples)")
+        codes = self._speech_encoder.encode(wav)[0].t().contiguous()            # [T_ref, 16]
+        vec = self._speaker_encoder.embed(wav)[0]
+        self._ref_cache = {key: (codes, vec)}
         return codes, vec
 
 
@@ -367,6 +401,7 @@ def load_model(model_path: str, device: str = "cuda", **kw) -> Model:
         if not ("random_init_seed" in meta or "b200_size" in meta or os.environ.get("Q3T_ALLOW_RANDOM_INIT") == "1"):
             raise OSError(f"{model_path} holds no model.safetensors (incomplete download?); random-init weights need an explicit "
                           "opt-in (random_init_seed / b200_size in config.json or Q3T_ALLOW_RANDOM_INIT=1)")
-        ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False)
+        parts = ("talker", "cp", "codec") + (("enc", "spk") if mode == "base" else ())
+        ws = make_weights(cfg, seed=int(meta.get("random_init_seed", 0)), device=device, keep_fp=False, parts=parts)
     explicit_stub = bool(meta.get("b200_byte_tokenizer"))
     return Model(cfg, ws, device, model_path=model_path, require_tokenizer=has_ckpt and not explicit_stub, **kw)

@@ -166,7 +166,8 @@ def _stack_layers(add_lin, add_norm, prefix: str, n_layers: int, hidden: int, q_
 def expected_shapes(cfg: ModelConfig) -> "WeightStore":
     """The store of `cfg` with every tensor on the META device: names, shapes and which linears are W8, nothing
     materialised (the checkpoint loader checks shapes and conv layouts against it)."""
-    return make_weights(cfg, device="meta", keep_fp=True, keep_q=True)
+    parts = ("talker", "cp", "codec") + (("enc", "spk") if cfg.tts_model_type == "base" else ())
+    return make_weights(cfg, device="meta", keep_fp=True, keep_q=True, parts=parts)
 
 
 def make_weights(cfg: ModelConfig, seed: int = 0, device: str = "cpu", keep_fp: bool = True,
