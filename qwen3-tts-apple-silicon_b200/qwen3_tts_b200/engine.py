@@ -221,7 +221,12 @@ class TalkerEngine:
         cs.do_sample = int(do_sample if cp_do_sample is None else cp_do_sample)
         cs.temperature, cs.top_k, cs.top_p, cs.repetition_penalty = cp_temperature, cp_top_k, cp_top_p, 1.0
         cs.min_new_tokens, cs.suppress_lo, cs.suppress_hi, cs.eos_id, cs.seed = 0, -1, -1, -1, seed + 1
-        self._graphs = {}
+        # the sampling block is baked into the captured launches: re-capture only when a parameter actually changed
+        # (Model.generate calls this for every utterance and every long-text segment)
+        key = tuple(getattr(x, f) for x in (sp, cs) for f, _ in L.Sampling._fields_)
+        if key != getattr(self, "_sampling_key", None):
+            self._sampling_key = key
+            self._graphs = {}
 
     def set_mega(self, on: bool):
         """Switch between the persistent stack-pass kernel (batch 1) and the one-kernel-per-contraction path."""
