@@ -265,6 +265,8 @@ def bs64_leg(cfg, args, world, dist, timed):
 
     eng.prefill(emb, None, None)
     eng.generate(8, check_every=0)
+    # the codec's chunk shapes (300 + 25 context frames) once before the timed run: the caching allocator grows by several GB
+    codec.decode(torch.randint(0, cfg.codec.codebook_size, (B, cfg.codec.num_quantizers, min(T, 400)), device="cuda", dtype=torch.int32))
     ms, wav = timed(step_dev, 1)
     ms_e2e, wav_h = timed(step_e2e, 1)
     ev = lambda: torch.cuda.Event(enable_timing=True)

@@ -174,7 +174,7 @@ typedef struct {
     const float* logits; int B, V; long long logits_stride;
     q3t_sampling sp;
     unsigned int* seen;       /* [B, ceil(V/32)] bitmask of generated ids (NULL: no penalty, no update) */
-    const int* step;          /* device scalar: frames generated so far (min_new_tokens, RNG counter) */
+    const int* step;          /* frames generated so far (min_new_tokens, RNG counter): device scalar, or [B] with step_stride = 1 */
     int rng_stream;           /* distinguishes the 16 draws of a frame */
     const float* uniforms;    /* optional [B] externally supplied uniforms (tests) */
     int* out; long long out_stride;             /* out[b*out_stride] = chosen id (fixed address) */
@@ -182,6 +182,7 @@ typedef struct {
     const int* forced;        /* optional teacher forcing: overrides the choice */
     int* own;                 /* optional: what the sampler itself picked (before forcing) */
     int* done;                /* optional [B]: set to 1 when the chosen id == eos_id */
+    int step_stride;          /* 0: `step` is one scalar shared by the lock-step batch; 1: one frame counter per row */
 } q3t_sample_args;
 
 int q3t_sample(const q3t_sample_args* a, void* stream);
@@ -289,6 +290,12 @@ typedef struct {
      * fused q|k|v projection of RMSNorm(projected row) - equally a function of one code.  With it the first layer of those
      * passes starts at the attention (one more contraction phase less per pass).  NULL = compute in the kernel. */
     const float* const* cp_qkv0_rows_dev;
+    /* continuous batching (batched path, B > 2; qwen3_tts_b200/serving.py): rows of the batch are SLOTS that requests enter
+     * and leave at different frames.  step_per_row != 0: `step` is [B], one frame counter per slot (sampler, trailing-text row
+     * and the codes archive index by it).  active [B] (or NULL = all): only active slots advance their position and frame
+     * counter; an idle slot keeps pos = 0 over a scratch page and its outputs are ignored. */
+    int step_per_row;
+    const int* active;
 } q3t_frame_args;
 
 /* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).

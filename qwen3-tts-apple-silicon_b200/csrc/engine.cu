@@ -31,12 +31,15 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ 
     for (int i = threadIdx.x; i < H; i += blockDim.x) yr[i] = w[i] * (xr[i] * rstd);
 }
 
-__global__ void advance_kernel(int* pos, int B, int* step) {
+// step_per_row: one frame counter per slot (continuous batching); active (or NULL = all): only active slots advance
+__global__ void advance_kernel(int* pos, int B, int* step, int step_per_row, const int* active) {
     pdl_wait();
     pdl_launch_dependents();
     const int i = threadIdx.x;
-    if (i < B) pos[i] += 1;
-    if (step && i == 0) *step += 1;
+    const bool on = i < B && (!active || active[i]);
+    if (on) pos[i] += 1;
+    if (step && step_per_row) { if (on) step[i] += 1; }
+    else if (step && i == 0) *step += 1;
 }
 
 // next talker input: emb_talker[c0] + sum_{g=1..G-1} emb_cp[g-1][c_g] summed sequentially in
@@ -44,11 +47,11 @@ __global__ void advance_kernel(int* pos, int B, int* step) {
 __global__ void __launch_bounds__(256) next_input_kernel(const float* __restrict__ codec_emb,
                                                          const float* const* __restrict__ cp_emb, const int* cur_codes,
                                                          int G, int H, const float* __restrict__ trailing,
-                                                         int n_trailing, const int* step_p, float* x, int* codes,
+                                                         int n_trailing, const int* step_p, int step_per_row, float* x, int* codes,
                                                          int max_frames) {
     pdl_wait();
     pdl_launch_dependents();
-    const int b = blockIdx.x, step = *step_p;
+    const int b = blockIdx.x, step = step_p[step_per_row ? b : 0];
     const int* cc = cur_codes + b * G;
     const int trow = step < n_trailing - 1 ? step : n_trailing - 1;
     const float* tr = trailing + ((size_t)b * n_trailing + trow) * H;
@@ -191,7 +194,7 @@ static int talker_step(const q3t_frame_args* f, int want_logits, int bump_step, 
             Q3T_TRY(gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0,
                               nullptr, 0, f->logits, f->talker_vocab, s));
     }
-    launch_pdl(advance_kernel, dim3(1), dim3(1024), 0, s, f->pos, f->B, bump_step ? f->step : (int*)nullptr);
+    launch_pdl(advance_kernel, dim3(1), dim3(1024), 0, s, f->pos, f->B, bump_step ? f->step : (int*)nullptr, f->step_per_row, f->active);
     Q3T_CHECK_LAUNCH("advance");
     return 0;
 }
@@ -202,6 +205,7 @@ static int sample_into(const q3t_frame_args* f, const float* logits, int V, cons
     memset(&a, 0, sizeof(a));
     const int G = f->n_groups;
     a.logits = logits; a.B = f->B; a.V = V; a.logits_stride = V; a.sp = sp; a.seen = seen; a.step = f->step;
+    a.step_stride = f->step_per_row ? 1 : 0;
     a.rng_stream = g; a.out = f->cur_codes + g; a.out_stride = G;
     a.fo_stride = (long long)f->max_frames * G; a.fo_step_stride = G;
     a.forced = f->forced_codes ? f->forced_codes + g : nullptr;
@@ -238,7 +242,7 @@ static int frame(const q3t_frame_args* f, cudaStream_t s) {
         Q3T_TRY(sample_into(f, lg, f->cp_vocab, f->cp_sp, nullptr, g + 1, nullptr, s));
     }
     launch_pdl(next_input_kernel, dim3(B), dim3(256), 0, s, f->codec_embedding, f->cp_embeddings_dev,
-               (const int*)f->cur_codes, G, H, f->trailing, f->n_trailing, (const int*)f->step, f->x, f->codes,
+               (const int*)f->cur_codes, G, H, f->trailing, f->n_trailing, (const int*)f->step, f->step_per_row, f->x, f->codes,
                f->max_frames);
     Q3T_CHECK_LAUNCH("next_input");
     return talker_step(f, 1, 1, s);

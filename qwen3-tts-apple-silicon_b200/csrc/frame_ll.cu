@@ -977,8 +977,11 @@ __device__ LL_FN void attn_phase(CState& st, const LLStack& S, const LayerD& LD,
 struct StackOut { const u64* add; uint32_t tag; };
 
 // qkv0 != nullptr: q|k|v of the first layer come from a table row (plain fp32), its QKV phase is skipped
+// att_only: this CTA runs only the attention of the pass (code-predictor passes: the kv-head CTAs hold no row tiles of the
+// code predictor, so they poll their q|k|v words the moment they are published instead of after a QKV epilogue of their own:
+// 86-88 -> 82-83 us per pass, profiles/r02_ll_experiments.txt).  Phase tags advance identically on every CTA.
 __device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const LayerD* lay, int pos, const u64* first_add, uint32_t first_tag,
-                                        const float* qkv0 = nullptr) {
+                                        const float* qkv0 = nullptr, bool att_only = false) {
     const LLParams& p = ll_params();
     const LLSmem s = ll_smem();
     const int tid = threadIdx.x;
@@ -1008,7 +1011,7 @@ __device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const Laye
         uint32_t t_qkv = 0u;
         if (!plain_qkv) {
             t_qkv = ++st.gen;
-            gemv_phase(st, L.qkv, in_norm(add, add_tag, L.input_norm, S.hidden, S.eps), EPI_RAW, p.x_qkv, nullptr, t_qkv);
+            if (!att_only) gemv_phase(st, L.qkv, in_norm(add, add_tag, L.input_norm, S.hidden, S.eps), EPI_RAW, p.x_qkv, nullptr, t_qkv);
         }
         LL_STAMP(ST_QKV);
         // ---- attention (first n_kv*nsplit CTAs)
@@ -1016,6 +1019,13 @@ __device__ LL_FN StackOut stack_consume(CState& st, const LLStack& S, const Laye
         if (rep == 2) attn_phase<2>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att, plain_qkv);
         else attn_phase<1>(st, S, L, l, pos, p.x_qkv, t_qkv, p.x_attn, p.x_attnf, t_att, plain_qkv);
         LL_STAMP(ST_ATTN);
+        if (att_only) {
+            // no contraction on this CTA: a barrier of its own puts the reads of the staging buffer behind the next layer's copies
+            if (l + 1 < S.n_layers) { cbar(); attn_prefetch(st, S, l + 1, pos); }
+            st.gen += 3;
+            add = p.x_down; add_tag = st.gen;
+            continue;
+        }
         // ---- O projection
         const uint32_t t_o = ++st.gen;
         gemv_phase(st, L.o, in_ll(p.x_attnf, t_att), EPI_RAW, p.x_o, nullptr, t_o);
@@ -1159,21 +1169,27 @@ __device__ __noinline__ int cp_pass(CState& st, const float* src, const float* p
     const int tid = threadIdx.x, Hc = p.cp.hidden, G = p.n_groups;
     const u64* first_add = nullptr;
     uint32_t t_proj = 0u;
+    // the kv-head CTAs of the code predictor (its contexts never leave the one-CTA-per-kv-head path) run its attention only: they
+    // hold no row tiles of its matrices (see the kernel: build_mat with cp_skip)
+    const bool att_only = (int)blockIdx.x < p.cp.n_kv && (int)gridDim.x > 2 * p.cp.n_kv;
     if (prow) {
-        for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
-            reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = __ldcg(reinterpret_cast<const float4*>(prow) + k4);
+        if (!att_only)
+            for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
+                reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = __ldcg(reinterpret_cast<const float4*>(prow) + k4);
     } else {
         t_proj = ++st.gen;
-        gemv_phase(st, s.hd[0], in_plain(src), EPI_RAW, p.x_proj, nullptr, t_proj);
-        for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
-            reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!att_only) {
+            gemv_phase(st, s.hd[0], in_plain(src), EPI_RAW, p.x_proj, nullptr, t_proj);
+            for (int k4 = tid; k4 < (Hc >> 2); k4 += LL_CTHREADS)
+                reinterpret_cast<float4*>(s.resid + st.res_par * LL_MAXH)[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         first_add = p.x_proj;
     }
-    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, first_add, t_proj, prow ? qrow : nullptr);
+    const StackOut so = stack_consume(st, p.cp, s.lay + p.talker.n_layers, pos, first_add, t_proj, prow ? qrow : nullptr, att_only);
     if (g_head < 0) return 0;
     const uint32_t t_head = ++st.gen;
     float* lg = p.cp_logits ? (p.keep_cp_logits ? p.cp_logits + (size_t)g_head * p.cp_vocab : p.cp_logits) : nullptr;
-    gemv_phase(st, s.hd[2 + g_head], in_norm(so.add, so.tag, p.cp.final_norm, Hc, p.cp.eps), EPI_RAW, p.x_head, lg, t_head);
+    if (!att_only) gemv_phase(st, s.hd[2 + g_head], in_norm(so.add, so.tag, p.cp.final_norm, Hc, p.cp.eps), EPI_RAW, p.x_head, lg, t_head);
     int c;
     if (!p.cp_sp.do_sample) { st.red_par ^= 1; c = sample_greedy(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, st.red_par); }
     else c = sample_here(nullptr, p.x_head, t_head, p.cp_vocab, p.cp_sp, nullptr, step, g_head + 1);
@@ -1188,9 +1204,11 @@ __device__ __noinline__ int cp_pass(CState& st, const float* src, const float* p
     return c;
 }
 
+// cta / grid = index / count among the CTAs that share the matrix (cta < 0: this CTA holds none of its row tiles)
 __device__ __forceinline__ void build_mat(MatD& d, const q3t_w8& w, int cta, int grid) {
     d.w = reinterpret_cast<const uint8_t*>(w.w); d.bias = w.lin_bias; d.nkc = w.K >> 8; d.N = w.N;
     const unsigned nrt = (unsigned)(w.N >> 4);
+    if (cta < 0) { d.rb = d.re = 0; return; }
     d.rb = (int)((nrt * (unsigned)cta) / (unsigned)grid);
     d.re = (int)((nrt * (unsigned)(cta + 1)) / (unsigned)grid);
 }
@@ -1214,11 +1232,13 @@ __global__ void __launch_bounds__(LL_THREADS, 1) frame_ll_kernel(const LLParams 
     const int G = p_in.n_groups, nA = p_in.talker.n_layers, nB = p_in.mode == LL_MODE_FRAME ? p_in.cp.n_layers : 0;
     // descriptor tables (this CTA's row-tile ranges included)
     if (tid < nA) build_layer(s.lay[tid], p_in.talker.layers[tid], cta, gridDim.x);
-    else if (tid < nA + nB) build_layer(s.lay[tid], p_in.cp.layers[tid - nA], cta, gridDim.x);
+    // code-predictor matrices are dealt over the CTAs that are NOT its kv-head (attention) CTAs
+    const int cp_skip = (int)gridDim.x > 2 * p_in.cp.n_kv ? p_in.cp.n_kv : 0;
+    if (tid >= nA && tid < nA + nB) build_layer(s.lay[tid], p_in.cp.layers[tid - nA], cta - cp_skip, (int)gridDim.x - cp_skip);
     if (p_in.mode == LL_MODE_FRAME) {
-        if (tid == 64) build_mat(s.hd[0], p_in.cp_proj, cta, gridDim.x);
+        if (tid == 64) build_mat(s.hd[0], p_in.cp_proj, cta - cp_skip, (int)gridDim.x - cp_skip);
         if (tid == 65) build_mat(s.hd[1], p_in.codec_head, cta, gridDim.x);
-        if (tid >= 66 && tid < 66 + G - 1) build_mat(s.hd[2 + tid - 66], p_in.cp_heads[tid - 66], cta, gridDim.x);
+        if (tid >= 66 && tid < 66 + G - 1) build_mat(s.hd[2 + tid - 66], p_in.cp_heads[tid - 66], cta - cp_skip, (int)gridDim.x - cp_skip);
         if (p_in.cp_proj_rows && tid >= 96 && tid < 96 + G - 1) s.prows[tid - 96] = p_in.cp_proj_rows[tid - 96];
         if (p_in.cp_qkv0_rows && tid >= 128 && tid < 128 + G - 1) s.qrows[tid - 128] = p_in.cp_qkv0_rows[tid - 128];
     } else if (tid == 65 && p_in.head.w) build_mat(s.hd[1], p_in.head, cta, gridDim.x);

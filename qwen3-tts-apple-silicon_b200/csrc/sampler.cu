@@ -14,7 +14,7 @@ struct SampleParams {
     const float* logits; int V; long long logits_stride;
     q3t_sampling sp;
     unsigned int* seen;
-    const int* step;
+    const int* step; int step_stride;
     int rng_stream;
     const float* uniforms;
     int* out; long long out_stride; long long fo_stride, fo_step_stride;
@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) sample_kernel(const SamplePara
     pdl_launch_dependents();
     const int b = blockIdx.x, tid = threadIdx.x;
     const int V = p.V;
-    const int step = p.step ? *p.step : 0;
+    const int step = p.step ? p.step[(size_t)b * p.step_stride] : 0;
     const float* lg = p.logits + (size_t)b * p.logits_stride;
     const unsigned int* seen = p.seen ? p.seen + (size_t)b * ((V + 31) / 32) : nullptr;
     const q3t_sampling sp = p.sp;
@@ -60,7 +60,7 @@ int launch_sample(const q3t_sample_args* a, cudaStream_t stream) {
     Q3T_REQUIRE(a->V > 0 && a->V <= SAMPLE_MAXV, "sample: vocabulary larger than the shared-memory buffer (4096)");
     SampleParams p;
     p.logits = a->logits; p.V = a->V; p.logits_stride = a->logits_stride; p.sp = a->sp; p.seen = a->seen;
-    p.step = a->step; p.rng_stream = a->rng_stream; p.uniforms = a->uniforms; p.out = a->out;
+    p.step = a->step; p.step_stride = a->step_stride; p.rng_stream = a->rng_stream; p.uniforms = a->uniforms; p.out = a->out;
     p.out_stride = a->out_stride; p.fo_stride = a->fo_stride; p.fo_step_stride = a->fo_step_stride;
     p.forced = a->forced; p.own = a->own;
     p.done = a->done;

@@ -21,12 +21,16 @@ class _Tap:
     """One tap-GEMM layer: W [taps, N, Cin] + bias + shifts."""
 
     def __init__(self, W: torch.Tensor, bias: Optional[torch.Tensor], shifts: List[int], up: int, cout: int,
-                 rows_delta: int = 0):
+                 rows_delta: int = 0, device=None):
         # weights are rounded to TF32 (10-bit mantissa, round-to-nearest-even) once: the tcgen05 tap-GEMM reads its
         # operands as TF32 by truncation, so pre-rounded weights make that truncation exact (csrc/tapgemm_tc.cu)
         Wi = W.contiguous().view(torch.int32)
         W = ((Wi + 0x0FFF + ((Wi >> 13) & 1)) & ~0x1FFF).view(torch.float32)
-        self.W, self.bias, self.shifts, self.up, self.cout, self.rows_delta = W.contiguous(), bias, shifts, up, cout, rows_delta
+        # re-layout and rounding run where the checkpoint tensors live (a host store costs no device launches); the finished
+        # operands move to the device once
+        W = W.contiguous().to(device) if device is not None else W.contiguous()
+        bias = bias.to(device) if (bias is not None and device is not None) else bias
+        self.W, self.bias, self.shifts, self.up, self.cout, self.rows_delta = W, bias, shifts, up, cout, rows_delta
         self.taps, self.cin = W.shape[0], W.shape[2]
 
 
@@ -35,38 +39,40 @@ class CodecDecoder:
         self.lib = L.load()
         self.cfg, self.k, self.dev = cfg, cfg.codec, torch.device(device)
         k = self.k
-        w: Dict[str, torch.Tensor] = {n: t.to(self.dev, torch.float32) for n, t in ws.fp.items() if n.startswith("codec.")}
-        self.w = w
+        w: Dict[str, torch.Tensor] = {n: t.to(torch.float32) for n, t in ws.fp.items() if n.startswith("codec.")}   # source device
+        dev = self.dev
+        D = lambda t: t.to(dev).contiguous()
 
         def conv(name: str, dilation: int = 1) -> _Tap:
             W = w[name + ".weight"]                      # [Cout, Cin, k]
             ks = W.shape[2]
-            return _Tap(W.permute(2, 0, 1), w[name + ".bias"], [-(ks - 1 - j) * dilation for j in range(ks)], 1, W.shape[0])
+            return _Tap(W.permute(2, 0, 1), w[name + ".bias"], [-(ks - 1 - j) * dilation for j in range(ks)], 1, W.shape[0], device=dev)
 
         def tconv(name: str, stride: int) -> _Tap:
             W = w[name + ".weight"]                      # [Cin, Cout, k]
             cin, cout, ks = W.shape
             t0 = W[:, :, :stride].permute(2, 1, 0).reshape(stride * cout, cin)
             if ks == stride:
-                return _Tap(t0[None], w[name + ".bias"], [0], stride, cout)
+                return _Tap(t0[None], w[name + ".bias"], [0], stride, cout, device=dev)
             assert ks == 2 * stride
             t1 = W[:, :, stride:].permute(2, 1, 0).reshape(stride * cout, cin)
             if k.transconv_trim == "both":               # out[q*s+p] = x[q+1] W[p] + x[q] W[p+s]   (cousin :3319-3331)
-                return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [1, 0], stride, cout, rows_delta=-1)
-            return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [0, -1], stride, cout)
+                return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [1, 0], stride, cout, rows_delta=-1, device=dev)
+            return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [0, -1], stride, cout, device=dev)
 
         def lin(W: torch.Tensor, bias: Optional[torch.Tensor] = None) -> _Tap:
-            return _Tap(W[None], bias, [0], 1, W.shape[0])
+            return _Tap(W[None], bias, [0], 1, W.shape[0], device=dev)
 
         def snake(name: str):
-            return (torch.exp(w[name + ".alpha"]).contiguous(), (1.0 / (torch.exp(w[name + ".beta"]) + 1e-9)).contiguous())
+            # evaluated in fp64 and rounded once: the same fp32 constants whether the store lives on the host or on the device
+            return (D(torch.exp(w[name + ".alpha"].double()).float()), D((1.0 / (torch.exp(w[name + ".beta"].double()) + 1e-9)).float()))
 
         # RVQ tables: embed_sum / clamp(usage, 1e-5)  (mimi:1191-1195), one per quantizer
         self.tables = []
         for grp, nq in (("semantic", k.num_semantic), ("acoustic", k.num_quantizers - k.num_semantic)):
             for i in range(nq):
                 p = f"codec.rvq.{grp}.codebooks.{i}"
-                self.tables.append((w[p + ".embed_sum"] / w[p + ".cluster_usage"].clamp(min=1e-5)[:, None]).contiguous())
+                self.tables.append(D(w[p + ".embed_sum"] / w[p + ".cluster_usage"].clamp(min=1e-5)[:, None]))
         self._tab_ptrs = (L.vp * len(self.tables))(*[t.data_ptr() for t in self.tables])
         self.rvq_sem = lin(w["codec.rvq.semantic.out_proj.weight"])
         self.rvq_ac = lin(w["codec.rvq.acoustic.out_proj.weight"])
@@ -77,22 +83,22 @@ class CodecDecoder:
             p = f"codec.tf.layers.{i}"
             gu = torch.stack([w[p + ".gate_proj.weight"], w[p + ".up_proj.weight"]], 1).reshape(-1, k.tf_hidden)
             self.tf_layers.append(dict(
-                n1=w[p + ".input_norm.weight"].contiguous(),
+                n1=D(w[p + ".input_norm.weight"]),
                 qkv=lin(torch.cat([w[p + ".q_proj.weight"], w[p + ".k_proj.weight"], w[p + ".v_proj.weight"]], 0)),
-                o=lin(w[p + ".o_proj.weight"]), s1=w[p + ".attn_scale"].contiguous(),
-                n2=w[p + ".post_norm.weight"].contiguous(), gu=lin(gu), down=lin(w[p + ".down_proj.weight"]),
-                s2=w[p + ".mlp_scale"].contiguous()))
-        self.tf_norm = w["codec.tf.norm.weight"].contiguous()
+                o=lin(w[p + ".o_proj.weight"]), s1=D(w[p + ".attn_scale"]),
+                n2=D(w[p + ".post_norm.weight"]), gu=lin(gu), down=lin(w[p + ".down_proj.weight"]),
+                s2=D(w[p + ".mlp_scale"])))
+        self.tf_norm = D(w["codec.tf.norm.weight"])
         self.tf_out = lin(w["codec.tf.out_proj.weight"], w["codec.tf.out_proj.bias"])
         self.tf_inv_freq = (1.0 / (k.tf_rope_theta ** (torch.arange(0, k.tf_head_dim, 2, dtype=torch.float32) /
                                                       k.tf_head_dim))).to(self.dev)
         self.ups = []
         for i, r in enumerate(k.upsampling_ratios):
             p = f"codec.up.{i}"
-            self.ups.append(dict(tconv=tconv(p + ".tconv", r), dw_w=w[p + ".cnx.dw.weight"].reshape(k.latent_dim, -1).contiguous(),
-                                 dw_b=w[p + ".cnx.dw.bias"], ln_w=w[p + ".cnx.ln.weight"], ln_b=w[p + ".cnx.ln.bias"],
+            self.ups.append(dict(tconv=tconv(p + ".tconv", r), dw_w=D(w[p + ".cnx.dw.weight"].reshape(k.latent_dim, -1)),
+                                 dw_b=D(w[p + ".cnx.dw.bias"]), ln_w=D(w[p + ".cnx.ln.weight"]), ln_b=D(w[p + ".cnx.ln.bias"]),
                                  pw1=lin(w[p + ".cnx.pw1.weight"], w[p + ".cnx.pw1.bias"]),
-                                 pw2=lin(w[p + ".cnx.pw2.weight"], w[p + ".cnx.pw2.bias"]), gamma=w[p + ".cnx.gamma"]))
+                                 pw2=lin(w[p + ".cnx.pw2.weight"], w[p + ".cnx.pw2.bias"]), gamma=D(w[p + ".cnx.gamma"])))
         self.conv_in = conv("codec.dec.conv_in")
         self.blocks = []
         for i, r in enumerate(k.upsample_rates):
@@ -105,7 +111,7 @@ class CodecDecoder:
             self.blocks.append(dict(snake=snake(p + ".snake"), tconv=tconv(p + ".tconv", r), units=units))
         self.snake_out = snake("codec.dec.snake_out")
         self.conv_out = conv("codec.dec.conv_out")
-        self.conv_out_w = w["codec.dec.conv_out.weight"][0].t().contiguous()      # [taps, C] unrounded fp32 (FP32-pipe kernel)
+        self.conv_out_w = D(w["codec.dec.conv_out.weight"][0].t())      # [taps, C] unrounded fp32 (FP32-pipe kernel)
 
     # ---- operator wrappers ---------------------------------------------------------------------------------
     def _tap(self, layer: _Tap, A: torch.Tensor, scale=None, resid=None, want_raw=True, act=L.ACT_NONE, act_ab=None):

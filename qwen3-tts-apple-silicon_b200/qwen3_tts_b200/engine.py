@@ -43,7 +43,10 @@ class TalkerEngine:
 
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", batch: int = 1, max_frames: int = 512,
                  max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1,
-                 use_mega: bool = True, prefill: str = "auto", prefill_gemm_rows: int = 32):
+                 use_mega: bool = True, prefill: str = "auto", prefill_gemm_rows: int = 32, kv_pages: Optional[int] = None):
+        """kv_pages: size of the talker's K/V page POOL (pages of 16 tokens) when the block table is managed by a page
+        allocator (serving.ContinuousBatcher): page 0 is a scratch page idle slots point at, the table starts all-zero.  None:
+        every sequence owns max_ctx / 16 consecutive pages (identity table, lock-step batches)."""
         self.lib = L.load()
         self.cfg, self.dev, self.B = cfg, torch.device(device), batch
         self.max_frames, self.max_ctx, self.max_trailing = max_frames, max_ctx, max_trailing
@@ -61,18 +64,20 @@ class TalkerEngine:
             return ws.fp[name].to(dev, torch.float32).contiguous()
 
         def w8(names: Sequence[str], bias_name: Optional[str] = None, interleave8: bool = False) -> L.W8:
+            # fuse / interleave / pack WHERE THE CODES LIVE (host store: host work, no device launches before the first real
+            # kernel; device store: on the device), then move the finished tiles
             trips = [ws.q[n] for n in names]
-            q = torch.cat([x[0] for x in trips], 0).to(dev)
-            s = torch.cat([x[1] for x in trips], 0).to(dev)
-            b = torch.cat([x[2] for x in trips], 0).to(dev)
+            q = torch.cat([x[0] for x in trips], 0)
+            s = torch.cat([x[1] for x in trips], 0)
+            b = torch.cat([x[2] for x in trips], 0)
             if interleave8:
                 # fused gate/up: rows 16j..16j+7 = gate rows 8j.., rows 16j+8..16j+15 = the matching up rows, so one
                 # 16-row weight tile holds both operands of silu(gate) * up (SwiGLU runs in the GEMV epilogue)
                 half = q.shape[0] // 2
-                idx = torch.arange(half, device=dev).view(-1, 8)
+                idx = torch.arange(half, device=q.device).view(-1, 8)
                 perm = torch.cat([idx, idx + half], 1).reshape(-1)
                 q, s, b = q[perm].contiguous(), s[perm].contiguous(), b[perm].contiguous()
-            blob = pack_w8(q, s, b)
+            blob = pack_w8(q, s, b).to(dev)
             self.w_bytes += blob.numel()
             o = L.W8()
             o.w, o.N, o.K = self.keep(blob), q.shape[0], q.shape[1]
@@ -105,12 +110,17 @@ class TalkerEngine:
             pool = torch.zeros(sc.num_layers * layer_elems, device=dev, dtype=torch.bfloat16)
             st.kv_pool = self.keep(pool)
             st.kv_layer_stride_bytes = layer_elems * 2
-            tbl = torch.arange(self.B * pages_per_seq, **i32).reshape(self.B, pages_per_seq).contiguous()
+            if prefix == "talker" and kv_pages is not None:
+                tbl = torch.zeros(self.B, pages_per_seq, **i32)
+            else:
+                tbl = torch.arange(self.B * pages_per_seq, **i32).reshape(self.B, pages_per_seq).contiguous()
+            if prefix == "talker":
+                self.talker_tbl = tbl
             st.block_tbl, st.max_pages, st.attn_nsplit = self.keep(tbl), pages_per_seq, nsplit
             return st, layers
 
         pps = (max_ctx + L.KV_PAGE - 1) // L.KV_PAGE
-        self.talker_stack, self._tl = stack("talker", t, self.B * pps, pps, attn_nsplit)
+        self.talker_stack, self._tl = stack("talker", t, self.B * pps if kv_pages is None else kv_pages + 1, pps, attn_nsplit)
         cp_pps = (self.G + 1 + L.KV_PAGE - 1) // L.KV_PAGE
         self.cp_stack, self._cl = stack("cp", c, self.B * cp_pps, cp_pps, 1)
 
@@ -373,9 +383,22 @@ class TalkerEngine:
         B, Lmax, H = embeds.shape
         dev = self.dev
         rows = torch.cat([embeds[b, Lmax - l:] for b, l in enumerate(lengths)], 0).contiguous()
+        rows = self.prefill_rows(rows, lengths, list(range(B)))
+        last = torch.tensor([sum(lengths[:b + 1]) - 1 for b in range(B)], device=dev)
+        self.x.copy_(rows[last])
+        L.check(self.lib.q3t_talker_tail(C.byref(self.fa), L.stream_ptr()), "talker_tail")
+        torch.cuda.synchronize()          # the temporaries must outlive the enqueued kernels
+
+    def prefill_rows(self, rows: torch.Tensor, lengths: Sequence[int], slots: Sequence[int]) -> torch.Tensor:
+        """rows [M, H] = the prompt tokens of len(lengths) sequences, concatenated; sequence i occupies block-table row
+        slots[i].  Writes their K/V pages and returns the residual stream after the last layer (pre final norm) [M, H]."""
+        t = self.cfg.talker
+        dev = self.dev
+        rows = rows.to(dev, torch.float32).contiguous()
         M = rows.shape[0]
+        assert M == sum(lengths)
         pos = torch.cat([torch.arange(l, dtype=torch.int32) for l in lengths]).to(dev)
-        seq = torch.cat([torch.full((l,), b, dtype=torch.int32) for b, l in enumerate(lengths)]).to(dev)
+        seq = torch.cat([torch.full((l,), b, dtype=torch.int32) for b, l in zip(slots, lengths)]).to(dev)
         qkvd, rep = t.q_dim + 2 * t.kv_dim, t.num_heads // t.num_kv_heads
         f32 = dict(device=dev, dtype=torch.float32)
         qkv = torch.empty(M, qkvd, **f32)
@@ -401,10 +424,8 @@ class TalkerEngine:
             if not os.environ.get("Q3T_NO_BF16_CHAIN"):
                 a.xb2 = xb2.data_ptr()
         L.check(self.lib.q3t_talker_prefill(C.byref(a), L.stream_ptr()), "talker_prefill")
-        last = torch.tensor([sum(lengths[:b + 1]) - 1 for b in range(B)], device=dev)
-        self.x.copy_(rows[last])
-        L.check(self.lib.q3t_talker_tail(C.byref(self.fa), L.stream_ptr()), "talker_tail")
         torch.cuda.synchronize()          # the temporaries above must outlive the enqueued kernels
+        return rows
 
     def generate(self, n_frames: int, check_every: int = 16) -> torch.Tensor:
         """Runs up to n_frames frames (stops early once every sequence sampled EOS). Returns codes [B, T, G]."""

@@ -57,7 +57,7 @@ class Sampling(C.Structure):
 class SampleArgs(C.Structure):
     _fields_ = [("logits", vp), ("B", i32), ("V", i32), ("logits_stride", i64), ("sp", Sampling), ("seen", vp),
                 ("step", vp), ("rng_stream", i32), ("uniforms", vp), ("out", vp), ("out_stride", i64),
-                ("fo_stride", i64), ("fo_step_stride", i64), ("forced", vp), ("own", vp), ("done", vp)]
+                ("fo_stride", i64), ("fo_step_stride", i64), ("forced", vp), ("own", vp), ("done", vp), ("step_stride", i32)]
 
 
 class Layer(C.Structure):
@@ -81,7 +81,7 @@ class FrameArgs(C.Structure):
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
                 ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("gemm_ws", vp), ("gemm_ws_floats", i64), ("gemm_counters", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
-                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp), ("gemm_xb2", vp), ("cp_proj_rows_dev", vp), ("cp_qkv0_rows_dev", vp)]
+                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp), ("gemm_xb2", vp), ("cp_proj_rows_dev", vp), ("cp_qkv0_rows_dev", vp), ("step_per_row", i32), ("active", vp)]
 
 
 class PrefillArgs(C.Structure):
