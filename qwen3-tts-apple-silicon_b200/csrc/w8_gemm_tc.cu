@@ -354,7 +354,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                         }
                     }
                 } else {
-                    for (int i = dt; i < nt * 32; i += 512) {
+                    // residual rows of all of this thread's items first (at most 8 float4): issued together, they cost one
+                    // memory round trip instead of one per item between the stores
+                    float4 rres[8];
+                    if (p.resid) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int i = dt + q * 512, tok = i >> 5, q4 = i & 31, m = m0 + t0 + tok;
+                            if (i < nt * 32 && m < p.M) rres[q] = *reinterpret_cast<const float4*>(p.resid + (size_t)m * p.resid_stride + n0 + 4 * q4);
+                        }
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < 8; ++qq) {
+                        const int i = dt + qq * 512;
+                        if (i >= nt * 32) break;
                         const int tok = i >> 5, q4 = i & 31, m = m0 + t0 + tok;
                         if (m >= p.M) continue;
                         float4 x;
@@ -373,10 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
                             x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
                         }
                         if (p.act == Q3T_ACT_SILU) { x.x = silu_f(x.x); x.y = silu_f(x.y); x.z = silu_f(x.z); x.w = silu_f(x.w); }
-                        if (p.resid) {
-                            const float4 r = *reinterpret_cast<const float4*>(p.resid + (size_t)m * p.resid_stride + n0 + 4 * q4);
-                            x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
-                        }
+                        if (p.resid) { const float4 r = rres[qq]; x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w; }
                         if (p.yb) {
                             uint2 ob, ol; split_bf16x4(x, ob, ol);
                             __nv_bfloat16* yr = p.yb + (size_t)m * 2 * p.N + n0 + 4 * q4;
