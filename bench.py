@@ -157,6 +157,9 @@ class CpuOracle:
 
 
 def cpu_sample_text(n):
+    if n >= FRAMES:
+        return (f"PyTorch-CPU fp32 oracle (oracle/qwen3_tts_oracle.py): the WHOLE utterance - prompt prefill, all {FRAMES} frames (talker step, sampler, "
+                "15 code-predictor passes, next-input sum), codec of all frames; nothing projected")
     return (f"PyTorch-CPU fp32 oracle (oracle/qwen3_tts_oracle.py): real prompt prefill + {n} real frames (talker step, sampler, 15 "
             f"code-predictor passes, next-input sum; context growing from the prompt) + codec of those frames, projected to {FRAMES} frames")
 
@@ -304,6 +307,7 @@ def cfg5_leg(cfg, args, world, rank, dist, eng, codec):
 
     torch.cuda.synchronize()
     if dist is not None:
+        dp.run_sharded(list(range(world)), lambda i: i, dist)      # first gather sets up the point-to-point channels: not part of the job
         dist.barrier()
     t0 = time.perf_counter()
     out = dp.run_sharded(list(range(n_batches)), run_batch, dist)
@@ -324,7 +328,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", default="full", choices=["full", "small"])
-    ap.add_argument("--ref-frames", type=int, default=24)
+    ap.add_argument("--ref-frames", type=int, default=FRAMES, help="frames the reference arm really runs per step (240 = the whole utterance, no projection)")
     ap.add_argument("--cpu-frames", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bs64", action="store_true")
