@@ -102,6 +102,15 @@ typedef struct {
      *   x_bf16: the input rows are ALREADY split rows [M, 2K] (prologue must be Q3T_PRO_RAW, x is ignored);
      *   y_bf16: the epilogue writes split rows [M, 2N] (or [M, 2(N/2)] with swiglu_out) INSTEAD of fp32 y. */
     const void* x_bf16;  void* y_bf16;
+    /* optional DEFERRED RMSNorm between two GEMMs of a residual stream (no prologue launch, no fp32 re-read of the row):
+     *   producer (y_norm_w != NULL; needs y, y_bf16, y_rowss; not with swiglu_out): besides the fp32 rows y the epilogue writes
+     *     split rows of y[m, n] * y_norm_w[n] - weighted, NOT yet normalised - to y_bf16, and the sum of squares of y[m, :] over
+     *     each block of 128 features to y_rowss[m * (N/128) + n/128];
+     *   consumer (x_rowss != NULL; needs x_bf16): the contraction of row m is multiplied by
+     *     rsqrt(sum_j x_rowss[m * x_rowss_parts + j] / K + eps) before bias / activation / SwiGLU - the normalisation commutes
+     *     with the contraction, so the pair computes W . RMSNorm(y) with the row statistics summed in a fixed order. */
+    const float* y_norm_w;  float* y_rowss;
+    const float* x_rowss;  int x_rowss_parts;
 } q3t_gemm_args;
 
 int q3t_w8_gemm(const q3t_gemm_args* a, void* stream);
@@ -296,6 +305,9 @@ typedef struct {
      * counter; an idle slot keeps pos = 0 over a scratch page and its outputs are ignored. */
     int step_per_row;
     const int* active;
+    /* optional [B, 32] fp32: row statistics of the deferred RMSNorm between the GEMMs of the batched path (q3t_gemm_args.y_rowss);
+     * NULL = every norm is a prologue launch (act_prep_kernel) */
+    float* gemm_rowss;
 } q3t_frame_args;
 
 /* Talker prefill as GEMMs: M rows = the prompt tokens of all sequences, concatenated (no padding).
@@ -311,6 +323,7 @@ typedef struct {
     const int* blocks; int n_blocks;         /* optional row blocks for q3t_attn_prefill (see there); 0 = per-row decode kernel */
     void* xb2;                               /* optional second bf16 scratch of split rows [M, 2*max(H*D, inter)]: attention output and SwiGLU
                                                 activations stay bf16 between kernels (needs `blocks`) */
+    float* rowss;                            /* optional [M, 32] fp32: deferred RMSNorm statistics (needs xb2; see q3t_gemm_args.y_rowss) */
 } q3t_prefill_args;
 int q3t_talker_prefill(const q3t_prefill_args* a, void* stream);
 /* final RMSNorm of `x` [B, H] -> `hidden`, codec head -> `logits` (the tail of a talker step) */

@@ -93,6 +93,7 @@ int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float
 static void* g_xb = nullptr;    // bf16 scratch of the call in flight (set by the entry points below)
 static void* g_xb2 = nullptr;   // second bf16 scratch: attention output / SwiGLU activations handed from kernel to kernel as bf16
 static float* g_ws = nullptr; static long long g_ws_floats = 0; static int* g_counters = nullptr;
+static float* g_rowss = nullptr;   // row statistics of the deferred RMSNorm ([rows, 32] fp32); NULL = norms are prologue launches
 static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
                      const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
                      float* y, long long ys, cudaStream_t s) {
@@ -119,16 +120,42 @@ static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long 
     return 0;
 }
 
-// tcgen05 GEMM whose input rows are already bf16 (x_bf16) and / or whose output stays bf16 (y_bf16): no prologue launch
+// tcgen05 GEMM whose input rows are already bf16 (x_bf16) and / or whose output stays bf16 (y_bf16): no prologue launch.
+// x_rowss: the input rows are weighted but not yet normalised (deferred RMSNorm, consumer half); y_norm_w: write fp32 y AND
+// the weighted split rows + statistics for the next GEMM (producer half) - q3t_gemm_args in include/q3tts_b200.h.
 static int gemm_bf16(const q3t_w8& w, int M, const void* x_bf16, int prologue, const float* x, long long xs, const float* norm_w,
                      float eps, int swiglu_out, const float* resid, long long rs, float* y, long long ys, void* y_bf16,
-                     cudaStream_t s) {
+                     cudaStream_t s, const float* x_rowss = nullptr, int x_parts = 0, const float* y_norm_w = nullptr,
+                     float* y_rowss = nullptr) {
     q3t_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.w = w; a.M = M; a.prologue = prologue; a.x = x; a.x_stride = xs; a.norm_w = norm_w; a.eps = eps; a.swiglu_out = swiglu_out;
     a.resid = resid; a.resid_stride = rs; a.y = y; a.y_stride = ys; a.xb = g_xb; a.x_bf16 = x_bf16; a.y_bf16 = y_bf16;
     a.splitk_ws = g_ws; a.splitk_ws_floats = g_ws_floats; a.splitk_counters = g_counters;
+    a.x_rowss = x_rowss; a.x_rowss_parts = x_parts; a.y_norm_w = y_norm_w; a.y_rowss = y_rowss;
     return launch_w8_gemm(&a, s);
+}
+
+// layers l .. of a dense Qwen3 stack on the batched path, from the O projection on: attention output (split rows in xb2) ->
+// x updated in place.  With `rowss` the two RMSNorms that follow a residual GEMM are deferred: the O projection hands the
+// gate/up GEMM split rows of x * post_norm in xb, the down projection hands the next layer's q|k|v GEMM split rows of
+// x * input_norm - 5 launches per layer instead of 7.  Returns through *x_ready whether xb holds the next layer's input.
+static int layer_tail_bf16(const q3t_stack& st, int l, int M, float* x, void* xb, void* xb2, float* rowss, bool* x_ready,
+                           cudaStream_t s) {
+    const q3t_layer& L = st.layers_host[l];
+    const int hid = st.hidden, parts = hid / 128;
+    const bool defer = rowss != nullptr && hid % 128 == 0 && parts <= 32;
+    const float* next_norm = (defer && l + 1 < st.n_layers) ? st.layers_host[l + 1].input_norm : nullptr;
+    Q3T_TRY(gemm_bf16(L.o, M, xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, defer ? xb : nullptr, s,
+                      nullptr, 0, defer ? L.post_norm : nullptr, defer ? rowss : nullptr));
+    if (defer)
+        Q3T_TRY(gemm_bf16(L.gate_up, M, xb, Q3T_PRO_RAW, nullptr, 0, nullptr, st.eps, 1, nullptr, 0, nullptr, 0, xb2, s, rowss, parts));
+    else
+        Q3T_TRY(gemm_bf16(L.gate_up, M, nullptr, Q3T_PRO_RMSNORM, x, hid, L.post_norm, st.eps, 1, nullptr, 0, nullptr, 0, xb2, s));
+    Q3T_TRY(gemm_bf16(L.down, M, xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, next_norm ? xb : nullptr, s,
+                      nullptr, 0, next_norm, next_norm ? rowss : nullptr));
+    *x_ready = next_norm != nullptr;
+    return 0;
 }
 
 // one token through a dense Qwen3 stack; x [B, hidden] is updated in place (residual stream)
@@ -136,11 +163,16 @@ static int gemm_bf16(const q3t_w8& w, int M, const void* x_bf16, int prologue, c
 static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x, const int* pos, cudaStream_t s, bool skip_qkv0 = false) {
     const int B = f->B, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim;
     const int qkvd = qd + 2 * kvd;
+    bool x_ready = false;       // g_xb holds split rows of x * input_norm of this layer + g_rowss its statistics (deferred RMSNorm)
     for (int l = 0; l < st.n_layers; ++l) {
         const q3t_layer& L = st.layers_host[l];
-        if (!(skip_qkv0 && l == 0))
+        if (x_ready)
+            Q3T_TRY(gemm_bf16(L.qkv, B, g_xb, Q3T_PRO_RAW, nullptr, 0, nullptr, st.eps, 0, nullptr, 0, f->qkv, qkvd, nullptr, s,
+                              g_rowss, hid / 128));
+        else if (!(skip_qkv0 && l == 0))
             Q3T_TRY(gemv_rows(L.qkv, B, Q3T_PRO_RMSNORM, x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, f->qkv,
                               qkvd, s));
+        x_ready = false;
         q3t_attn_args a;
         memset(&a, 0, sizeof(a));
         a.qkv = f->qkv; a.q_norm_w = L.q_norm; a.k_norm_w = L.k_norm; a.eps = st.eps; a.inv_freq = st.inv_freq;
@@ -154,9 +186,8 @@ static int stack_forward(const q3t_frame_args* f, const q3t_stack& st, float* x,
         if (chain) a.out_bf16 = g_xb2;
         Q3T_TRY(launch_attn_decode(&a, s));
         if (chain) {
-            Q3T_TRY(gemm_bf16(L.o, B, g_xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, nullptr, s));
-            Q3T_TRY(gemm_bf16(L.gate_up, B, nullptr, Q3T_PRO_RMSNORM, x, hid, L.post_norm, st.eps, 1, nullptr, 0, nullptr, 0, g_xb2, s));
-            Q3T_TRY(gemm_bf16(L.down, B, g_xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, x, hid, x, hid, nullptr, s));
+            const bool next_ok = l + 1 < st.n_layers && st.layers_host[l + 1].qkv.N % 128 == 0;
+            Q3T_TRY(layer_tail_bf16(st, l, B, x, g_xb, g_xb2, next_ok || l + 1 == st.n_layers ? g_rowss : nullptr, &x_ready, s));
             continue;
         }
         Q3T_TRY(gemv_rows(L.o, B, Q3T_PRO_RAW, f->attn, qd, nullptr, 0.f, nullptr, 0, 0, 0, x, hid, x, hid, s));
@@ -254,10 +285,16 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
     const q3t_stack& st = f->talker;
     const int M = a->M, hid = st.hidden, qd = st.n_heads * st.head_dim, kvd = st.n_kv_heads * st.head_dim, qkvd = qd + 2 * kvd;
     Q3T_REQUIRE(M >= 1 && a->x && a->pos && a->seq_of_row && a->qkv && a->attn && a->gu && a->xb, "talker_prefill: arguments");
-    g_xb = a->xb; g_xb2 = nullptr; g_ws = nullptr; g_ws_floats = 0; g_counters = nullptr;
+    g_xb = a->xb; g_xb2 = nullptr; g_ws = nullptr; g_ws_floats = 0; g_counters = nullptr; g_rowss = nullptr;
+    bool x_ready = false;
     for (int l = 0; l < st.n_layers; ++l) {
         const q3t_layer& L = st.layers_host[l];
-        Q3T_TRY(gemv_rows(L.qkv, M, Q3T_PRO_RMSNORM, a->x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->qkv, qkvd, s));
+        if (x_ready)
+            Q3T_TRY(gemm_bf16(L.qkv, M, a->xb, Q3T_PRO_RAW, nullptr, 0, nullptr, st.eps, 0, nullptr, 0, a->qkv, qkvd, nullptr, s,
+                              a->rowss, hid / 128));
+        else
+            Q3T_TRY(gemv_rows(L.qkv, M, Q3T_PRO_RMSNORM, a->x, hid, L.input_norm, st.eps, nullptr, 0, 0, 0, nullptr, 0, a->qkv, qkvd, s));
+        x_ready = false;
         q3t_attn_args t;
         memset(&t, 0, sizeof(t));
         t.qkv = a->qkv; t.q_norm_w = L.q_norm; t.k_norm_w = L.k_norm; t.eps = st.eps; t.inv_freq = st.inv_freq;
@@ -281,9 +318,8 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
             if (chain) { u.out = nullptr; u.out_bf16 = a->xb2; }
             Q3T_TRY(launch_attn_prefill(&u, s));
             if (chain) {          // attention output and SwiGLU activations go on as bf16 rows (as in the decode frames)
-                Q3T_TRY(gemm_bf16(L.o, M, a->xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, a->x, hid, a->x, hid, nullptr, s));
-                Q3T_TRY(gemm_bf16(L.gate_up, M, nullptr, Q3T_PRO_RMSNORM, a->x, hid, L.post_norm, st.eps, 1, nullptr, 0, nullptr, 0, a->xb2, s));
-                Q3T_TRY(gemm_bf16(L.down, M, a->xb2, Q3T_PRO_RAW, nullptr, 0, nullptr, 0.f, 0, a->x, hid, a->x, hid, nullptr, s));
+                const bool next_ok = l + 1 < st.n_layers && st.layers_host[l + 1].qkv.N % 128 == 0;
+                Q3T_TRY(layer_tail_bf16(st, l, M, a->x, a->xb, a->xb2, next_ok || l + 1 == st.n_layers ? a->rowss : nullptr, &x_ready, s));
                 continue;
             }
         } else {
@@ -300,7 +336,7 @@ static int talker_prefill(const q3t_prefill_args* a, cudaStream_t s) {
 
 static int talker_tail(const q3t_frame_args* f, cudaStream_t s) {
     const q3t_stack& t = f->talker;
-    g_xb = f->gemm_xb; g_xb2 = nullptr; g_ws = f->gemm_ws; g_ws_floats = f->gemm_ws_floats; g_counters = f->gemm_counters;
+    g_xb = f->gemm_xb; g_xb2 = nullptr; g_ws = f->gemm_ws; g_ws_floats = f->gemm_ws_floats; g_counters = f->gemm_counters; g_rowss = nullptr;
     Q3T_TRY(launch_rmsnorm(f->x, t.final_norm, f->hidden, f->B, t.hidden, t.eps, s));
     return gemv_rows(f->codec_head, f->B, Q3T_PRO_RAW, f->hidden, t.hidden, nullptr, 0.f, nullptr, 0, 0, 0, nullptr, 0, f->logits,
                      f->talker_vocab, s);
@@ -312,11 +348,11 @@ extern "C" int q3t_rmsnorm(const float* x, const float* w, float* y, int M, int 
     return q3t::launch_rmsnorm(x, w, y, M, H, eps, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_step(const q3t_frame_args* f, int want_logits, void* stream) {
-    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
+    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters; q3t::g_rowss = q3t::g_xb2 ? f->gemm_rowss : nullptr;
     return q3t::talker_step(f, want_logits, 0, (cudaStream_t)stream);
 }
 extern "C" int q3t_frame(const q3t_frame_args* f, void* stream) {
-    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters;
+    q3t::g_xb = f->gemm_xb; q3t::g_xb2 = getenv("Q3T_NO_BF16_CHAIN") ? nullptr : f->gemm_xb2; q3t::g_ws = f->gemm_ws; q3t::g_ws_floats = f->gemm_ws_floats; q3t::g_counters = f->gemm_counters; q3t::g_rowss = q3t::g_xb2 ? f->gemm_rowss : nullptr;
     return q3t::frame(f, (cudaStream_t)stream);
 }
 extern "C" int q3t_talker_prefill(const q3t_prefill_args* a, void* stream) { return q3t::talker_prefill(a, (cudaStream_t)stream); }

@@ -201,6 +201,10 @@ class TalkerEngine:
         self.gemm_ws = torch.empty(8 * max(B, 1) * nmax, **f32)
         self.gemm_counters = torch.zeros(1024, **i32)
         fa.gemm_ws, fa.gemm_ws_floats, fa.gemm_counters = self.keep(self.gemm_ws), self.gemm_ws.numel(), self.keep(self.gemm_counters)
+        # row statistics of the deferred RMSNorm between the GEMMs of the batched path (include/q3tts_b200.h: q3t_gemm_args.y_rowss)
+        self.gemm_rowss = torch.zeros(32 * max(B, 1), **f32)
+        if not os.environ.get("Q3T_NO_NORM_DEFER"):
+            fa.gemm_rowss = self.keep(self.gemm_rowss)
         # prompt rows go through the tcgen05 W8 GEMM (bf16 operands, the logit tolerance of BASELINE.json) when there are
         # enough of them; "decode" pins the token-by-token path through the decode kernels (exact-integer contractions)
         assert prefill in ("auto", "gemm", "decode")
@@ -423,6 +427,9 @@ class TalkerEngine:
             a.blocks, a.n_blocks = blk.data_ptr(), len(blocks)
             if not os.environ.get("Q3T_NO_BF16_CHAIN"):
                 a.xb2 = xb2.data_ptr()
+                if not os.environ.get("Q3T_NO_NORM_DEFER"):
+                    rowss = torch.empty(32 * M, **f32)
+                    a.rowss = rowss.data_ptr()
         L.check(self.lib.q3t_talker_prefill(C.byref(a), L.stream_ptr()), "talker_prefill")
         torch.cuda.synchronize()          # the temporaries above must outlive the enqueued kernels
         return rows

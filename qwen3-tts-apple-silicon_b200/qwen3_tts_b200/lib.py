@@ -33,7 +33,8 @@ class GemmArgs(C.Structure):
     _fields_ = [("w", W8), ("M", i32), ("prologue", i32), ("x", vp), ("x_stride", i64), ("norm_w", vp), ("eps", f32),
                 ("gather_idx", vp), ("gather_idx_stride", i32), ("gather_row_stride", i64), ("act", i32),
                 ("swiglu_out", i32), ("resid", vp), ("resid_stride", i64), ("y", vp), ("y_stride", i64), ("xb", vp),
-                ("splitk_ws", vp), ("splitk_ws_floats", i64), ("splitk_counters", vp), ("x_bf16", vp), ("y_bf16", vp)]
+                ("splitk_ws", vp), ("splitk_ws_floats", i64), ("splitk_counters", vp), ("x_bf16", vp), ("y_bf16", vp),
+                ("y_norm_w", vp), ("y_rowss", vp), ("x_rowss", vp), ("x_rowss_parts", i32)]
 
 
 class AttnArgs(C.Structure):
@@ -81,12 +82,13 @@ class FrameArgs(C.Structure):
                 ("attn_counters", vp), ("pos", vp), ("cp_pos", vp), ("step", vp), ("cur_codes", vp), ("codes", vp),
                 ("own_codes", vp), ("max_frames", i32), ("seen", vp), ("done", vp), ("trailing", vp),
                 ("n_trailing", i32), ("forced_codes", vp), ("gemm_xb", vp), ("gemm_ws", vp), ("gemm_ws_floats", i64), ("gemm_counters", vp), ("use_mega", i32), ("cp_heads_dev", vp), ("ll_work", vp),
-                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp), ("gemm_xb2", vp), ("cp_proj_rows_dev", vp), ("cp_qkv0_rows_dev", vp), ("step_per_row", i32), ("active", vp)]
+                ("ll_work_bytes", i64), ("ll_state", vp), ("ll_timing", vp), ("gemm_xb2", vp), ("cp_proj_rows_dev", vp), ("cp_qkv0_rows_dev", vp), ("step_per_row", i32), ("active", vp),
+                ("gemm_rowss", vp)]
 
 
 class PrefillArgs(C.Structure):
     _fields_ = [("f", C.POINTER(FrameArgs)), ("M", i32), ("x", vp), ("pos", vp), ("seq_of_row", vp), ("qkv", vp), ("attn", vp),
-                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp), ("blocks", vp), ("n_blocks", i32), ("xb2", vp)]
+                ("gu", vp), ("xb", vp), ("attn_work", vp), ("attn_counters", vp), ("blocks", vp), ("n_blocks", i32), ("xb2", vp), ("rowss", vp)]
 
 
 class StackPassArgs(C.Structure):

@@ -144,6 +144,83 @@ def test_w8_gemm_tcgen05_prologues_epilogues(cuda):
     assert (y.cpu().double() - ref).abs().max() / ref.abs().max() < 1e-4
 
 
+@pytest.mark.parametrize("m,splitk", [(64, True), (37, False), (300, False)])
+def test_w8_gemm_deferred_rmsnorm_pair(cuda, m, splitk):
+    """Two GEMMs of a residual stream with the RMSNorm between them deferred (q3t_gemm_args.y_norm_w / x_rowss): the first
+    writes y = W1 a + resid (fp32), split rows of y * w and per-128-feature sums of y^2; the second contracts those rows and
+    scales by rsqrt(mean(y^2) + eps).  Against the fp64 arithmetic of the oracle's RMSNorm (O.rms_norm), plain and SwiGLU."""
+    lib = L.load()
+    hid, kin, n2 = 1024, 2048, 2048
+    o1, blob1, wd1 = _w8(hid, kin, 21, cuda)
+    g = torch.Generator().manual_seed(100 + m)
+    a_in = torch.randn(m, kin, generator=g) * 0.5
+    resid = torch.randn(m, hid, generator=g)
+    nw = 1 + 0.2 * torch.randn(hid, generator=g)
+    y_ref = a_in.double() @ wd1.double().T + resid.double()
+    yn_ref = (y_ref * torch.rsqrt((y_ref * y_ref).mean(-1, keepdim=True) + 1e-6)) * nw.double()
+    o2, blob2, wd2 = _w8(n2, hid, 22, cuda)
+    z_ref = yn_ref @ wd2.double().T
+    # the fused gate/up flavour of the consumer (rows interleaved in blocks of 8)
+    half = n2 // 2
+    idx = torch.arange(half).view(-1, 8)
+    perm = torch.cat([idx, idx + half], 1).reshape(-1)
+    q, sc, bi = quantize_w8(wd2)
+    wd2b = dequantize_w8(q, sc, bi)
+    o3 = L.W8()
+    blob3 = pack_w8(q[perm].contiguous().to(cuda), sc[perm].contiguous().to(cuda), bi[perm].contiguous().to(cuda))
+    o3.w, o3.N, o3.K = blob3.data_ptr(), n2, hid
+    sw_ref = torch.nn.functional.silu(yn_ref @ wd2b[:half].double().T) * (yn_ref @ wd2b[half:].double().T)
+
+    xd, rd, nwd = a_in.to(cuda), resid.to(cuda), nw.to(cuda)
+    xb = torch.empty(2 * m * kin, device=cuda, dtype=torch.bfloat16)
+    yb = torch.full((m, 2 * hid), float("nan"), device=cuda, dtype=torch.bfloat16)
+    rowss = torch.full((m, hid // 128), float("nan"), device=cuda)
+    ws = torch.empty(8 * m * max(hid, n2), device=cuda)
+    cnt = torch.zeros(1024, device=cuda, dtype=torch.int32)
+    a = L.GemmArgs()
+    a.w, a.M, a.prologue = o1, m, L.PRO_RAW
+    a.x, a.x_stride, a.xb = xd.data_ptr(), kin, xb.data_ptr()
+    a.resid, a.resid_stride, a.y, a.y_stride = rd.data_ptr(), hid, rd.data_ptr(), hid            # in place, like the engine
+    a.y_bf16, a.y_norm_w, a.y_rowss = yb.data_ptr(), nwd.data_ptr(), rowss.data_ptr()
+    if splitk:
+        a.splitk_ws, a.splitk_ws_floats, a.splitk_counters = ws.data_ptr(), ws.numel(), cnt.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(a), L.stream_ptr()), "gemm producer")
+    torch.cuda.synchronize()
+    y = rd.cpu().double()
+    assert (y - y_ref).abs().max() / y_ref.abs().max() < 5e-5
+    ss = rowss.cpu().double().sum(-1)
+    assert ((ss - (y * y).sum(-1)).abs() / (y * y).sum(-1)).max() < 1e-5
+    rows = yb.float().cpu().double()
+    assert ((rows[:, :hid] + rows[:, hid:]) - y * nw.double()).abs().max() / (y * nw.double()).abs().max() < 2e-5, "split rows of y * w"
+
+    z = torch.full((m, n2), float("nan"), device=cuda)
+    b = L.GemmArgs()
+    b.w, b.M, b.prologue, b.eps = o2, m, L.PRO_RAW, 1e-6
+    b.x_bf16, b.x_rowss, b.x_rowss_parts, b.xb = yb.data_ptr(), rowss.data_ptr(), hid // 128, xb.data_ptr()
+    b.y, b.y_stride = z.data_ptr(), n2
+    if splitk:
+        b.splitk_ws, b.splitk_ws_floats, b.splitk_counters = ws.data_ptr(), ws.numel(), cnt.data_ptr()
+    L.check(lib.q3t_w8_gemm(C.byref(b), L.stream_ptr()), "gemm consumer")
+    torch.cuda.synchronize()
+    assert (z.cpu().double() - z_ref).abs().max() / z_ref.abs().max() < 1e-4
+
+    sw = torch.full((m, half), float("nan"), device=cuda)
+    b.w, b.swiglu_out, b.y, b.y_stride = o3, 1, sw.data_ptr(), half
+    L.check(lib.q3t_w8_gemm(C.byref(b), L.stream_ptr()), "gemm consumer swiglu")
+    torch.cuda.synchronize()
+    assert (sw.cpu().double() - sw_ref).abs().max() / sw_ref.abs().max() < 1e-4
+    # the same pair through the prologue launch (act_prep_kernel) agrees to the rounding of the operands
+    z2 = torch.empty(m, n2, device=cuda)
+    c = L.GemmArgs()
+    c.w, c.M, c.prologue = o2, m, L.PRO_RMSNORM
+    c.x, c.x_stride, c.norm_w, c.eps, c.xb = rd.data_ptr(), hid, nwd.data_ptr(), 1e-6, xb.data_ptr()
+    c.y, c.y_stride = z2.data_ptr(), n2
+    L.check(lib.q3t_w8_gemm(C.byref(c), L.stream_ptr()), "gemm prologue")
+    torch.cuda.synchronize()
+    assert (z2 - z).abs().max() / z.abs().max() < 5e-5
+    assert int(cnt.abs().sum()) == 0
+
+
 def test_w8_gemv_prologues_epilogues(cuda):
     lib = L.load()
     n, k = 2048, 1024

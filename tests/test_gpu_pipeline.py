@@ -351,7 +351,9 @@ def test_batch1_prompt_on_the_gemm_matches_oracle(cuda):
 
 def test_bf16_chaining_between_batched_kernels_is_bit_identical(cuda, monkeypatch):
     """Batched path: attention output and SwiGLU activations are handed to the next GEMM as bf16 rows (no act_prep
-    launch).  The GEMM rounds its operands to bf16 either way, so logits and codes must not change by a single bit."""
+    launch).  The GEMM splits its operands into bf16 planes either way, so logits and codes must not change by a single
+    bit.  On top of that the RMSNorm after a residual GEMM is deferred (weighted rows + row statistics out of the producer's
+    epilogue, the scale in the consumer's): fewer launches again, same numbers to the rounding of the operands."""
     from qwen3_tts_b200.engine import TalkerEngine
     cfg = Cfg.small("voice_design")
     ws = make_weights(cfg, seed=6, head_std=0.2)
@@ -359,16 +361,29 @@ def test_bf16_chaining_between_batched_kernels_is_bit_identical(cuda, monkeypatc
     torch.manual_seed(3)
     emb = torch.randn(B, Lp, cfg.talker.hidden_size) * 0.02
     outs = []
-    for off in (False, True):
-        if off:
-            monkeypatch.setenv("Q3T_NO_BF16_CHAIN", "1")
+    for env in ((), ("Q3T_NO_NORM_DEFER",), ("Q3T_NO_NORM_DEFER", "Q3T_NO_BF16_CHAIN")):
+        for k in env:
+            monkeypatch.setenv(k, "1")
         e = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=16, max_ctx=64)
         e.set_sampling(do_sample=False)
         e.prefill(emb, None, None)
+        logits0 = e.logits.clone()
         codes = e.generate(5).clone()
-        outs.append((e.logits.clone(), codes, e.launches_per_frame))
-    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
-    assert outs[0][2] < outs[1][2], "the chained path must need fewer launches per frame"
+        outs.append((e.logits.clone(), codes, e.launches_per_frame, logits0))
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
+    assert outs[0][2] < outs[1][2] < outs[2][2], "each hand-over must need fewer launches per frame"
+    # the deferred norm changes WHERE the operands are rounded (x * w is split before the row scale instead of after): both
+    # variants sit at the same distance from the fp32 oracle, and that distance is the noise floor between them
+    oracle = O.OracleModel(cfg, ws.fp, kv_dtype=torch.bfloat16)
+    tr = torch.zeros(1, cfg.talker.hidden_size)
+    err = [[], []]
+    for b in range(B):
+        _, rec = oracle.generate(emb[b], tr, 1, record=True)
+        for v in (0, 1):
+            err[v].append(_rel(outs[v][3][b].cpu(), rec["talker_logits"][0]))
+    assert max(err[0]) < LOGIT_RTOL / 2 and max(err[1]) < LOGIT_RTOL / 2, (err[0], err[1])      # measured: 2.7e-3 both
+    assert max(err[0]) < 2 * max(err[1]) + 1e-4, f"deferred RMSNorm is less accurate than the prologue launch: {err[0]} vs {err[1]}"
+    assert _rel(outs[0][3], outs[1][3]) < 4 * max(err[1]) + 1e-4
 
 
 def test_streaming_generation_equals_offline_chunked_decode(small_setup):
