@@ -24,6 +24,7 @@ struct AttnParams {
     int B, H, Hkv, nsplit;
     int mode;                 // 0 fused decode, 1 write K/V of the row only, 2 attention only (K/V already in the cache)
     const int* seq_of_row;    // optional: block-table row of launch row b (prefill: many rows share one sequence)
+    int cluster;              // the nsplit CTAs of one (kv head, sequence) were launched as one thread-block cluster
 };
 
 template <int EPL> struct KvVec;
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
     constexpr int PSTR = D + 2;   // partial record: acc[D], m, l
     __shared__ float q_s[REP][D];
     __shared__ float part_s[8][REP][PSTR];
+    __shared__ float rec_s[REP][PSTR];   // this slice's merged record
     __shared__ int is_last;
 
     const int kvh = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
@@ -194,8 +196,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
     }
     __syncthreads();
 
-    // ---- stage 3: merge the 8 half-warps, publish the slice partial ---------------------------
-    float* wbase = p.work + ((size_t)(b * p.Hkv + kvh) * p.nsplit) * REP * PSTR;
+    // ---- stage 3: merge the 8 half-warps into this slice's record {acc[D], m, l} per query head ---------------------------
     for (int i = tid; i < REP * D; i += 128) {
         const int r = i / D, d = i % D;
         float M = -INFINITY;
@@ -209,10 +210,57 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
             L = fmaf(part_s[h][r][D + 1], w, L);
             A = fmaf(part_s[h][r][d], w, A);
         }
-        float* rec = wbase + ((size_t)split * REP + r) * PSTR;
-        rec[d] = A;
-        if (d == 0) { rec[D] = M; rec[D + 1] = L; }
+        rec_s[r][d] = A;
+        if (d == 0) { rec_s[r][D] = M; rec_s[r][D + 1] = L; }
     }
+    auto store_out = [&](int r, int d, float v) {
+        const size_t oi = (size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d;
+        if (p.out_bf16) {          // feeds the O-projection GEMM without an fp32 round trip: split row [hi(H*D) | lo(H*D)]
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            const size_t si = oi + (size_t)b * p.H * D;
+            p.out_bf16[si] = hi;
+            p.out_bf16[si + (size_t)p.H * D] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        } else p.out[oi] = v;
+    };
+    // ---- stage 4: merge the slices in slice order (deterministic, no float atomics) -----------------------------------------
+    // One slice: the record is the result.  Up to 8 slices: the CTAs of one (kv head, sequence) are a thread-block cluster and
+    // slice 0 reads the records of its peers through distributed shared memory - no global round trip (write, fence, atomic,
+    // re-read: ~3 us of a ~12 us CTA).  More slices: records through the L2 workspace, last CTA to arrive merges.
+    if (p.nsplit == 1) {
+        __syncthreads();
+        for (int i = tid; i < REP * D; i += 128) { const int r = i / D, d = i % D; store_out(r, d, rec_s[r][d] / rec_s[r][D + 1]); }
+        return;
+    }
+    if (p.cluster) {
+        asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");
+        if (split == 0) {
+            const uint32_t rec_u32 = (uint32_t)__cvta_generic_to_shared(&rec_s[0][0]);
+            auto ld_rec = [&](int s, int off) -> float {
+                uint32_t ra; float v;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(rec_u32 + (uint32_t)off * 4u), "r"(s));
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+                return v;
+            };
+            for (int i = tid; i < REP * D; i += 128) {
+                const int r = i / D, d = i % D;
+                float M = -INFINITY;
+                for (int s = 0; s < p.nsplit; ++s) M = fmaxf(M, ld_rec(s, r * PSTR + D));
+                float L = 0.f, A = 0.f;
+                for (int s = 0; s < p.nsplit; ++s) {
+                    const float ms = ld_rec(s, r * PSTR + D);
+                    const float w = (ms == -INFINITY) ? 0.f : __expf(ms - M);
+                    L = fmaf(ld_rec(s, r * PSTR + D + 1), w, L);
+                    A = fmaf(ld_rec(s, r * PSTR + d), w, A);
+                }
+                store_out(r, d, A / L);
+            }
+        }
+        asm volatile("barrier.cluster.arrive.release;\nbarrier.cluster.wait.acquire;" ::: "memory");   // records stay alive until slice 0 has read them
+        return;
+    }
+    __syncthreads();
+    float* wbase = p.work + ((size_t)(b * p.Hkv + kvh) * p.nsplit) * REP * PSTR;
+    for (int i = tid; i < REP * PSTR; i += 128) wbase[(size_t)split * REP * PSTR + i] = (&rec_s[0][0])[i];
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -234,14 +282,7 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
             L = fmaf(__ldcg(rec + D + 1), w, L);
             A = fmaf(__ldcg(rec + d), w, A);
         }
-        const size_t oi = (size_t)b * p.H * D + (size_t)(kvh * REP + r) * D + d;
-        if (p.out_bf16) {          // feeds the O-projection GEMM without an fp32 round trip: split row [hi(H*D) | lo(H*D)]
-            const float v = A / L;
-            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-            const size_t si = oi + (size_t)b * p.H * D;
-            p.out_bf16[si] = hi;
-            p.out_bf16[si + (size_t)p.H * D] = __float2bfloat16_rn(v - __bfloat162float(hi));
-        } else p.out[oi] = A / L;
+        store_out(r, d, A / L);
     }
     if (tid == 0) p.counters[b * p.Hkv + kvh] = 0;   // re-arm for the next launch / graph replay
 }
@@ -249,7 +290,20 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnParams p) {
 template <int D, int REP>
 static int launch_attn_t(const AttnParams& p, cudaStream_t stream) {
     dim3 grid(p.Hkv, p.nsplit, p.B);
-    launch_pdl(attn_decode_kernel<D, REP>, grid, dim3(128), 0, stream, p);
+    AttnParams q = p;
+    q.cluster = (p.nsplit > 1 && p.nsplit <= 8 && p.mode != 1) ? 1 : 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(128); cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (g_use_pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; ++na; }
+    if (q.cluster) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)p.nsplit; attr[na].val.clusterDim.z = 1; ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    cudaLaunchKernelEx(&cfg, attn_decode_kernel<D, REP>, q);
     Q3T_CHECK_LAUNCH("attn_decode");
     return 0;
 }

@@ -296,7 +296,7 @@ def _attn_ref(qkv, qn, kn, eps, theta, H, Hkv, D, kcache, vcache, pos):
     return torch.einsum("hs,shd->hd", torch.softmax(s, -1), V).reshape(-1), k, v
 
 
-@pytest.mark.parametrize("pos,nsplit", [(0, 1), (0, 16), (5, 4), (16, 16), (17, 1), (250, 16), (1000, 16), (1000, 3)])
+@pytest.mark.parametrize("pos,nsplit", [(0, 1), (0, 16), (5, 4), (16, 16), (17, 1), (250, 16), (1000, 16), (1000, 3), (300, 8), (40, 2), (299, 4)])
 def test_attn_decode(cuda, pos, nsplit):
     lib = L.load()
     H, Hkv, D, B, theta, eps = 4, 2, 128, 2, 1e6, 1e-6
