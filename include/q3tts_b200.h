@@ -366,9 +366,16 @@ typedef struct {
     float* out_act; int act; const float* act_a; const float* act_b;
     int force_fp32;                            /* != 0: FP32-pipe kernel even where the tcgen05 TF32 path is eligible (the
                                                   reference-clip encoders: a nearest-codebook search follows) */
+    /* 16-bit operands between the layers of the vocoder (tcgen05 path only; ask q3t_tapgemm_tc_eligible first):
+     *   a_f16   != 0: A and W point to IEEE fp16 data of the same shapes (kind::f16: 11 significant bits - one more than the
+     *                 TF32 read of fp32 data - at half the bytes through HBM, L2 and shared memory; fp32 accumulation);
+     *   act_f16 != 0: out_act is written as fp16 (saturating at +-65504) for such a consumer; out_raw / resid stay fp32. */
+    int a_f16;  int act_f16;
 } q3t_tapgemm_args;
 
 int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream);
+/* 1 when q3t_tapgemm would run this call on the tcgen05 kernel (shape rule of csrc/tapgemm_tc.cu), else 0 */
+int q3t_tapgemm_tc_eligible(const q3t_tapgemm_args* a);
 /* which kernel served the q3t_tapgemm calls so far: out3[0] tcgen05 TF32 tap-GEMM, out3[1] FP32-pipe kernel although
  * Cin % 32 == 0 (fewer than 64 GEMM rows, N not a multiple of 16), out3[2] FP32-pipe kernel because Cin % 32 != 0.
  * reset != 0 zeroes the counters after reading.  (Test / evidence aid: parity at the BASELINE shapes asserts out3[1] == 0.) */
@@ -390,6 +397,9 @@ int q3t_snake(const float* x, const float* a, const float* b, long long rows, in
  * act [B, T, C] fp32 time-major, W [taps, C] (tap j reads row t - (taps-1-j)), bias [1] or NULL -> wav [B, T] */
 int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
                        void* stream);
+/* the same with act as fp16 (written by a q3t_tapgemm with act_f16) */
+int q3t_conv_out_clamp_h(const void* act_f16, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                         void* stream);
 
 /* final: clamp(x, -1, 1) and optional PCM16 conversion */
 int q3t_clamp_pcm16(const float* x, long long n, float* y, int16_t* pcm, void* stream);

@@ -9,6 +9,7 @@
 // Round-1 implementation runs the contraction on the FP32 pipe with fused bias / LayerScale / residual /
 // SnakeBeta / GELU / SwiGLU epilogues; the tcgen05 implicit-GEMM version replaces `tapgemm_kernel` only.
 #include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
@@ -236,18 +237,26 @@ __global__ void clamp_pcm_kernel(const float* __restrict__ x, long long n, float
 // of a warp hit 32 different banks) and every thread produces one sample; the weights are broadcast reads.
 constexpr int CO_TT = 256;
 
-__global__ void __launch_bounds__(CO_TT) conv_out_clamp_kernel(const float* __restrict__ act, int T, int C, const float* __restrict__ W,
+template <bool F16>      // F16: act is fp16 (written by a tap-GEMM with act_f16), staged to fp32 in shared memory
+__global__ void __launch_bounds__(CO_TT) conv_out_clamp_kernel(const void* __restrict__ act_v, int T, int C, const float* __restrict__ W,
                                                                 const float* __restrict__ bias, int taps, float* __restrict__ wav) {
     extern __shared__ float co_s[];
     const int ld = C + 1, nrow = CO_TT + taps - 1;
     float* w_s = co_s + (size_t)nrow * ld;
     const int b = blockIdx.y, t0 = blockIdx.x * CO_TT, tid = threadIdx.x;
-    const float* src = act + (size_t)b * T * C;
     const int c4n = C >> 2;
     for (int i = tid; i < nrow * c4n; i += CO_TT) {
         const int r = i / c4n, c4 = i - r * c4n, t = t0 - (taps - 1) + r;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                    // rows before 0 are the causal left padding
-        if (t >= 0 && t < T) v = __ldcs(reinterpret_cast<const float4*>(src + (size_t)t * C) + c4);
+        if (t >= 0 && t < T) {
+            if (F16) {
+                const uint2 h = __ldcs(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(act_v) + ((size_t)b * T + t) * C) + c4);
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                v = __ldcs(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(act_v) + ((size_t)b * T + t) * C) + c4);
+            }
+        }
         float* d = co_s + (size_t)r * ld + 4 * c4;
         d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
@@ -282,6 +291,13 @@ extern "C" int q3t_rvq_gather_sum(const int* codes, const float* const* tables_h
 
 namespace q3t {
 int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream);
+bool tapgemm_tc_eligible(const q3t_tapgemm_args* a);
+// tensor-core implicit GEMM (tcgen05) for every eligible layer; Q3T_CODEC_TC=0 forces the FP32-pipe kernel
+static bool tc_enabled() {
+    static int use_tc = -1;
+    if (use_tc < 0) { const char* e = getenv("Q3T_CODEC_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
+    return use_tc != 0;
+}
 // which kernel served q3t_tapgemm: [0] tcgen05 tap-GEMM, [1] FP32-pipe kernel although Cin % 32 == 0 (too few rows / odd N /
 // Q3T_CODEC_TC=0), [2] FP32-pipe kernel because Cin % 32 != 0.  Tests assert [1] == 0 at the BASELINE shapes.
 static unsigned long long g_tap_stats[3] = {0, 0, 0};
@@ -295,14 +311,11 @@ extern "C" int q3t_tapgemm(const q3t_tapgemm_args* a, void* stream) {
     Q3T_REQUIRE(a->taps >= 1 && a->taps <= 8, "tapgemm: taps in [1,8]");
     Q3T_REQUIRE(a->Cin % 4 == 0, "tapgemm: Cin % 4");
     Q3T_REQUIRE(a->act != Q3T_ACT_SWIGLU_PAIR || (a->up * a->Cout) % 2 == 0, "tapgemm: SWIGLU_PAIR needs even N");
-    {   // tensor-core implicit GEMM (tcgen05, TF32) for every eligible layer; Q3T_CODEC_TC=0 forces the FP32-pipe kernel
-        static int use_tc = -1;
-        if (use_tc < 0) { const char* e = getenv("Q3T_CODEC_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
-        if (use_tc && !a->force_fp32 && (long long)a->B * a->T_out_rows > 0) {
-            const int rc = q3t::launch_tapgemm_tc(a, (cudaStream_t)stream);
-            if (rc >= 0) { q3t::g_tap_stats[0]++; return rc; }
-        }
+    if (q3t::tc_enabled() && !a->force_fp32 && (long long)a->B * a->T_out_rows > 0) {
+        const int rc = q3t::launch_tapgemm_tc(a, (cudaStream_t)stream);
+        if (rc >= 0) { q3t::g_tap_stats[0]++; return rc; }
     }
+    Q3T_REQUIRE(!a->a_f16 && !a->act_f16, "tapgemm: fp16 operands only exist on the tcgen05 path (q3t_tapgemm_tc_eligible)");
     q3t::g_tap_stats[(a->Cin % 32 == 0 && !a->force_fp32) ? 1 : 2]++;
     TapGemmParams p;
     p.A = a->A; p.B = a->B; p.T_in = a->T_in; p.Cin = a->Cin; p.W = a->W; p.bias = a->bias; p.taps = a->taps;
@@ -350,21 +363,34 @@ extern "C" int q3t_snake(const float* x, const float* a, const float* b, long lo
     return 0;
 }
 
-extern "C" int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
-                                  void* stream) {
+static int conv_out_clamp_any(const void* act, bool f16, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                              void* stream) {
     Q3T_REQUIRE(C % 4 == 0 && taps >= 1 && taps <= 16, "conv_out_clamp: C % 4, 1 <= taps <= 16");
-    if ((long long)B * T == 0) return 0;
+    if (B * T == 0) return 0;
     const size_t smem = ((size_t)(CO_TT + taps - 1) * (C + 1) + (size_t)taps * C) * sizeof(float);
     Q3T_REQUIRE(smem <= 227 * 1024, "conv_out_clamp: too many channels for one CTA");
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(conv_out_clamp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        smem_set = smem;
+    static size_t smem_set[2] = {0, 0};
+    if (smem > smem_set[f16]) {
+        if (f16) cudaFuncSetAttribute(conv_out_clamp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else cudaFuncSetAttribute(conv_out_clamp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        smem_set[f16] = smem;
     }
-    conv_out_clamp_kernel<<<dim3((unsigned)((T + CO_TT - 1) / CO_TT), (unsigned)B), CO_TT, smem, (cudaStream_t)stream>>>(
-        act, T, C, W, bias, taps, wav);
+    const dim3 grid((unsigned)((T + CO_TT - 1) / CO_TT), (unsigned)B);
+    if (f16) conv_out_clamp_kernel<true><<<grid, CO_TT, smem, (cudaStream_t)stream>>>(act, T, C, W, bias, taps, wav);
+    else conv_out_clamp_kernel<false><<<grid, CO_TT, smem, (cudaStream_t)stream>>>(act, T, C, W, bias, taps, wav);
     Q3T_CHECK_LAUNCH("conv_out_clamp");
     return 0;
+}
+extern "C" int q3t_conv_out_clamp(const float* act, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                                  void* stream) {
+    return conv_out_clamp_any(act, false, B, T, C, W, bias, taps, wav, stream);
+}
+extern "C" int q3t_conv_out_clamp_h(const void* act_f16, int B, int T, int C, const float* W, const float* bias, int taps, float* wav,
+                                    void* stream) {
+    return conv_out_clamp_any(act_f16, true, B, T, C, W, bias, taps, wav, stream);
+}
+extern "C" int q3t_tapgemm_tc_eligible(const q3t_tapgemm_args* a) {
+    return (q3t::tc_enabled() && (long long)a->B * a->T_out_rows > 0 && q3t::tapgemm_tc_eligible(a)) ? 1 : 0;
 }
 
 extern "C" int q3t_clamp_pcm16(const float* x, long long n, float* y, int16_t* pcm, void* stream) {

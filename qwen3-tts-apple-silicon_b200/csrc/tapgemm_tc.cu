@@ -15,6 +15,7 @@
 //   * epilogue: 4 warps move the accumulator TMEM -> shared memory, then all 16 epilogue warps apply bias / LayerScale /
 //     residual / SnakeBeta / GELU / SiLU / SwiGLU-pair and store coalesced rows.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
@@ -35,6 +36,8 @@ struct TapTcParams {
     int B, T_in, Cin, taps, shift[8], N, Cout, rows, tiles_per_item;
     const float* bias; const float* scale; const float* resid;
     float* out_raw; float* out_act; int act; const float* act_a; const float* act_b;
+    int f16;          // operands are IEEE fp16 (kind::f16, 64 channels per 128-byte stage row) instead of fp32 read as TF32
+    int act_f16;      // out_act is written as fp16 (the operand of an fp16 consumer)
 };
 
 __device__ __forceinline__ uint32_t tt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -73,7 +76,9 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x / p.tiles_per_item, t0 = (blockIdx.x % p.tiles_per_item) * TT_BM, n0 = blockIdx.y * TT_BN;
-    const int nkb = p.Cin / TT_BK, nst = p.taps * nkb;
+    // fp16 operands: 64 channels per stage row; a partial last block (Cin = 96) is the tensor map's zero fill
+    const int bk = p.f16 ? 2 * TT_BK : TT_BK;
+    const int nkb = (p.Cin + bk - 1) / bk, nst = p.taps * nkb;
 
     if (tid == 0) {
         for (int i = 0; i < TT_STAGES; ++i) { tt_mbar_init(tt_smem_u32(&full[i]), 1); tt_mbar_init(tt_smem_u32(&empty[i]), 1); }
@@ -102,17 +107,18 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                     tt_mbar_expect_tx(fb, TT_STAGE_BYTES);
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                                  ::"r"(tt_smem_u32(smem + st * TT_STAGE_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_a)),
-                                   "r"(kb * TT_BK), "r"(ta), "r"(b), "r"(fb) : "memory");
+                                   "r"(kb * bk), "r"(ta), "r"(b), "r"(fb) : "memory");
                     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                                  ::"r"(tt_smem_u32(smem + st * TT_STAGE_BYTES + TT_A_BYTES)), "l"(reinterpret_cast<uint64_t>(&tm_w)),
-                                   "r"(kb * TT_BK), "r"(tap * p.N + n0), "r"(fb) : "memory");
+                                   "r"(kb * bk), "r"(tap * p.N + n0), "r"(fb) : "memory");
                 }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ===================== MMA issuer: kind::tf32, M = 128, N = 128, K = 8 per instruction ========================
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TT_BN >> 3) << 17) | ((uint32_t)(TT_BM >> 4) << 24);
+            // ===================== MMA issuer: M = 128, N = 128, 32 bytes of K per instruction (8 tf32 / 16 fp16) =========
+            const uint32_t fmt = p.f16 ? 0u : 2u;         // operand format field: F16 (kind::f16) / TF32 (kind::tf32)
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TT_BN >> 3) << 17) | ((uint32_t)(TT_BM >> 4) << 24);
             for (int s = 0; s < nst; ++s) {
                 const int st = s % TT_STAGES, par = (s / TT_STAGES) & 1;
                 tt_mbar_wait(tt_smem_u32(&full[st]), par);
@@ -120,13 +126,20 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                 const uint64_t a_desc = tt_smem_desc(tt_smem_u32(smem + st * TT_STAGE_BYTES));
                 const uint64_t b_desc = tt_smem_desc(tt_smem_u32(smem + st * TT_STAGE_BYTES + TT_A_BYTES));
 #pragma unroll
-                for (int k = 0; k < TT_BK / 8; ++k) {     // 8 tf32 = 32 bytes = 2 descriptor units along K
+                for (int k = 0; k < TT_BK / 8; ++k) {     // 32 bytes = 2 descriptor units along K
                     const uint32_t acc = (s | k) != 0;
-                    asm volatile(
-                        "{\n.reg .pred p;\n"
-                        "setp.ne.b32 p, %4, 0;\n"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
-                        ::"r"(tmem_d), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"(acc) : "memory");
+                    if (p.f16)
+                        asm volatile(
+                            "{\n.reg .pred p;\n"
+                            "setp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                            ::"r"(tmem_d), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"(acc) : "memory");
+                    else
+                        asm volatile(
+                            "{\n.reg .pred p;\n"
+                            "setp.ne.b32 p, %4, 0;\n"
+                            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+                            ::"r"(tmem_d), "l"(a_desc + 2 * k), "l"(b_desc + 2 * k), "r"(idesc), "r"(acc) : "memory");
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tt_smem_u32(&empty[st])) : "memory");
             }
@@ -226,7 +239,16 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x[e] = act_simple(x[e], p.act);
                     }
-                    *reinterpret_cast<float4*>(p.out_act + o) = make_float4(tt_round_tf32(x[0]), tt_round_tf32(x[1]), tt_round_tf32(x[2]), tt_round_tf32(x[3]));
+                    if (p.act_f16) {
+                        // fp16 keeps 11 significant bits (TF32: 10); saturate instead of overflowing to inf
+                        __half2 h01 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
+                        __half2 h23 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
+                        uint2 hv;
+                        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_act) + o) = hv;
+                    } else {
+                        *reinterpret_cast<float4*>(p.out_act + o) = make_float4(tt_round_tf32(x[0]), tt_round_tf32(x[1]), tt_round_tf32(x[2]), tt_round_tf32(x[3]));
+                    }
                 }
             }
             }
@@ -243,12 +265,21 @@ typedef CUresult (*TtEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+bool tapgemm_tc_eligible(const q3t_tapgemm_args* a) {
+    const int N = a->up * a->Cout;
+    if (a->force_fp32 || a->Cin % TT_BK != 0 || N % 16 != 0 || N < 32 || a->Cout % 4 != 0) return false;
+    const long long Mtot = (long long)a->B * a->T_out_rows;
+    return Mtot >= 64 && a->T_in >= 1;
+}
+
 // returns 0 on success, > 0 on error, -1 when the shape is not eligible (caller falls back to the FP32-pipe kernel)
 int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream) {
     const int N = a->up * a->Cout;
-    if (a->Cin % TT_BK != 0 || N % 16 != 0 || N < 32 || a->Cout % 4 != 0) return -1;
-    const long long Mtot = (long long)a->B * a->T_out_rows;
-    if (Mtot < 64 || a->T_in < 1) return -1;
+    if (!tapgemm_tc_eligible(a)) return -1;
+    if (a->act == Q3T_ACT_SWIGLU_PAIR && (a->a_f16 || a->act_f16)) return -1;
+    const CUtensorMapDataType dt = a->a_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const cuuint64_t esz = a->a_f16 ? 2 : 4;
+    const cuuint32_t bk = a->a_f16 ? 2 * TT_BK : TT_BK;
     static TtEncodeFn encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -259,16 +290,16 @@ int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream) {
     CUtensorMap tm_a, tm_w;
     {
         const cuuint64_t gdim[3] = {(cuuint64_t)a->Cin, (cuuint64_t)a->T_in, (cuuint64_t)a->B};
-        const cuuint64_t gstr[2] = {(cuuint64_t)a->Cin * 4, (cuuint64_t)a->T_in * a->Cin * 4};
-        const cuuint32_t box[3] = {TT_BK, TT_BM, 1}, es[3] = {1, 1, 1};
-        if (encode(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)a->A, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const cuuint64_t gstr[2] = {(cuuint64_t)a->Cin * esz, (cuuint64_t)a->T_in * a->Cin * esz};
+        const cuuint32_t box[3] = {bk, TT_BM, 1}, es[3] = {1, 1, 1};
+        if (encode(&tm_a, dt, 3, (void*)a->A, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
     }
     {
         const cuuint64_t gdim[2] = {(cuuint64_t)a->Cin, (cuuint64_t)a->taps * N};
-        const cuuint64_t gstr[1] = {(cuuint64_t)a->Cin * 4};
-        const cuuint32_t box[2] = {TT_BK, TT_BN}, es[2] = {1, 1};
-        if (encode(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a->W, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        const cuuint64_t gstr[1] = {(cuuint64_t)a->Cin * esz};
+        const cuuint32_t box[2] = {bk, TT_BN}, es[2] = {1, 1};
+        if (encode(&tm_w, dt, 2, (void*)a->W, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return -1;
     }
     TapTcParams p;
@@ -277,7 +308,7 @@ int launch_tapgemm_tc(const q3t_tapgemm_args* a, cudaStream_t stream) {
     for (int i = 0; i < 8; ++i) p.shift[i] = a->shift[i];
     p.N = N; p.Cout = a->Cout; p.rows = a->T_out_rows; p.tiles_per_item = (a->T_out_rows + TT_BM - 1) / TT_BM;
     p.bias = a->bias; p.scale = a->scale; p.resid = a->resid; p.out_raw = a->out_raw; p.out_act = a->out_act; p.act = a->act;
-    p.act_a = a->act_a; p.act_b = a->act_b;
+    p.act_a = a->act_a; p.act_b = a->act_b; p.f16 = a->a_f16; p.act_f16 = a->act_f16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(tapgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TT_SMEM_BYTES);

@@ -8,6 +8,7 @@ libq3tts_b200.so (csrc/codec.cu).  Structure follows the cousin `Code2Wav` forwa
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -21,7 +22,10 @@ class _Tap:
     """One tap-GEMM layer: W [taps, N, Cin] + bias + shifts."""
 
     def __init__(self, W: torch.Tensor, bias: Optional[torch.Tensor], shifts: List[int], up: int, cout: int,
-                 rows_delta: int = 0, device=None):
+                 rows_delta: int = 0, device=None, f16: bool = False):
+        # vocoder layers also keep an fp16 copy of the (unrounded) weights: between those layers the activations travel as
+        # fp16 - 11 significant bits, one more than the TF32 read of fp32 data, at half the bytes (csrc/tapgemm_tc.cu, a_f16)
+        self.W16 = (W.contiguous().to(torch.float16).to(device) if device is not None else W.contiguous().to(torch.float16)) if f16 else None
         # weights are rounded to TF32 (10-bit mantissa, round-to-nearest-even) once: the tcgen05 tap-GEMM reads its
         # operands as TF32 by truncation, so pre-rounded weights make that truncation exact (csrc/tapgemm_tc.cu)
         Wi = W.contiguous().view(torch.int32)
@@ -38,6 +42,7 @@ class CodecDecoder:
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda"):
         self.lib = L.load()
         self.cfg, self.k, self.dev = cfg, cfg.codec, torch.device(device)
+        self.f16 = os.environ.get("Q3T_CODEC_F16", "1") != "0"     # fp16 activations between the vocoder's tensor-core layers
         k = self.k
         w: Dict[str, torch.Tensor] = {n: t.to(torch.float32) for n, t in ws.fp.items() if n.startswith("codec.")}   # source device
         dev = self.dev
@@ -46,19 +51,21 @@ class CodecDecoder:
         def conv(name: str, dilation: int = 1) -> _Tap:
             W = w[name + ".weight"]                      # [Cout, Cin, k]
             ks = W.shape[2]
-            return _Tap(W.permute(2, 0, 1), w[name + ".bias"], [-(ks - 1 - j) * dilation for j in range(ks)], 1, W.shape[0], device=dev)
+            return _Tap(W.permute(2, 0, 1), w[name + ".bias"], [-(ks - 1 - j) * dilation for j in range(ks)], 1, W.shape[0], device=dev,
+                        f16=name.startswith("codec.dec."))
 
         def tconv(name: str, stride: int) -> _Tap:
             W = w[name + ".weight"]                      # [Cin, Cout, k]
             cin, cout, ks = W.shape
             t0 = W[:, :, :stride].permute(2, 1, 0).reshape(stride * cout, cin)
+            f16 = name.startswith("codec.dec.")
             if ks == stride:
-                return _Tap(t0[None], w[name + ".bias"], [0], stride, cout, device=dev)
+                return _Tap(t0[None], w[name + ".bias"], [0], stride, cout, device=dev, f16=f16)
             assert ks == 2 * stride
             t1 = W[:, :, stride:].permute(2, 1, 0).reshape(stride * cout, cin)
             if k.transconv_trim == "both":               # out[q*s+p] = x[q+1] W[p] + x[q] W[p+s]   (cousin :3319-3331)
-                return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [1, 0], stride, cout, rows_delta=-1, device=dev)
-            return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [0, -1], stride, cout, device=dev)
+                return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [1, 0], stride, cout, rows_delta=-1, device=dev, f16=f16)
+            return _Tap(torch.stack([t0, t1]), w[name + ".bias"], [0, -1], stride, cout, device=dev, f16=f16)
 
         def lin(W: torch.Tensor, bias: Optional[torch.Tensor] = None) -> _Tap:
             return _Tap(W[None], bias, [0], 1, W.shape[0], device=dev)
@@ -114,25 +121,37 @@ class CodecDecoder:
         self.conv_out_w = D(w["codec.dec.conv_out.weight"][0].t())      # [taps, C] unrounded fp32 (FP32-pipe kernel)
 
     # ---- operator wrappers ---------------------------------------------------------------------------------
-    def _tap(self, layer: _Tap, A: torch.Tensor, scale=None, resid=None, want_raw=True, act=L.ACT_NONE, act_ab=None):
-        """A [B, T, Cin] -> (raw [B, rows*up, Cout] or None, act or None)."""
+    def _shape_args(self, layer: _Tap, B: int, T: int) -> "L.TapGemmArgs":
+        a = L.TapGemmArgs()
+        a.B, a.T_in, a.Cin, a.taps = B, T, layer.cin, layer.taps
+        a.up, a.Cout, a.T_out_rows = layer.up, layer.cout, T + layer.rows_delta
+        return a
+
+    def _want16(self, layer: _Tap, B: int, T: int) -> bool:
+        """May the producer of this layer's input write fp16?  Only if the layer will run on the tcgen05 kernel."""
+        return self.f16 and layer.W16 is not None and bool(self.lib.q3t_tapgemm_tc_eligible(C.byref(self._shape_args(layer, B, T))))
+
+    def _tap(self, layer: _Tap, A: torch.Tensor, scale=None, resid=None, want_raw=True, act=L.ACT_NONE, act_ab=None, act16=False):
+        """A [B, T, Cin] (fp32, or fp16 from a producer that was asked for it) -> (raw [B, rows*up, Cout] fp32 or None, act or
+        None; act is fp16 when act16 is set and this layer runs on the tcgen05 kernel)."""
         B, T, Cin = A.shape
         assert Cin == layer.cin and A.is_contiguous()
         rows = T + layer.rows_delta
         N = layer.up * layer.cout
-        a = L.TapGemmArgs()
-        a.A, a.B, a.T_in, a.Cin = A.data_ptr(), B, T, Cin
-        a.W, a.bias, a.taps = layer.W.data_ptr(), L.ptr(layer.bias), layer.taps
+        a = self._shape_args(layer, B, T)
+        a16 = A.dtype == torch.float16
+        a.A, a.a_f16 = A.data_ptr(), int(a16)
+        a.W, a.bias = (layer.W16 if a16 else layer.W).data_ptr(), L.ptr(layer.bias)
+        act16 = bool(act16 and act not in (L.ACT_NONE, L.ACT_SWIGLU_PAIR) and self.lib.q3t_tapgemm_tc_eligible(C.byref(a)))
         for i, s in enumerate(layer.shifts):
             a.shift[i] = s
-        a.up, a.Cout, a.T_out_rows = layer.up, layer.cout, rows
         a.scale, a.resid = L.ptr(scale), L.ptr(resid)
         raw = torch.empty(B, rows * layer.up, layer.cout, device=self.dev, dtype=torch.float32) if want_raw else None
         out_act = None
         if act != L.ACT_NONE:
             shape = (B, rows, N // 2) if act == L.ACT_SWIGLU_PAIR else (B, rows * layer.up, layer.cout)
-            out_act = torch.empty(*shape, device=self.dev, dtype=torch.float32)
-        a.out_raw, a.out_act, a.act = L.ptr(raw), L.ptr(out_act), act
+            out_act = torch.empty(*shape, device=self.dev, dtype=torch.float16 if act16 else torch.float32)
+        a.out_raw, a.out_act, a.act, a.act_f16 = L.ptr(raw), L.ptr(out_act), act, int(act16)
         if act_ab is not None:
             a.act_a, a.act_b = act_ab[0].data_ptr(), act_ab[1].data_ptr()
         L.check(self.lib.q3t_tapgemm(C.byref(a), L.stream_ptr()), "tapgemm")
@@ -194,30 +213,35 @@ class CodecDecoder:
             x, _ = self._tap(up["pw2"], g, scale=up["gamma"], resid=x)
         if stages is not None:
             stages["upsample"] = x
-        # vocoder: every conv writes the SnakeBeta of its consumer in its epilogue
-        _, act = self._tap(self.conv_in, x, want_raw=False, act=L.ACT_SNAKE, act_ab=self.blocks[0]["snake"])
+        # vocoder: every conv writes the SnakeBeta of its consumer in its epilogue - as fp16 wherever that consumer runs on the
+        # tcgen05 kernel (all of them at the BASELINE shapes); the residual stream `u` stays fp32
+        co = self.conv_out
+        co_direct = co.cout == 1 and co.cin % 4 == 0 and co.shifts == [-(co.taps - 1 - j) for j in range(co.taps)]
+        Bn, T, _ = x.shape
+        _, act = self._tap(self.conv_in, x, want_raw=False, act=L.ACT_SNAKE, act_ab=self.blocks[0]["snake"],
+                           act16=self._want16(self.blocks[0]["tconv"], Bn, T))
         for bi, blk in enumerate(self.blocks):
-            u, act = self._tap(blk["tconv"], act, act=L.ACT_SNAKE, act_ab=blk["units"][0]["s1"])
+            tc = blk["tconv"]
+            T = (T + tc.rows_delta) * tc.up
+            u, act = self._tap(tc, act, act=L.ACT_SNAKE, act_ab=blk["units"][0]["s1"], act16=self._want16(blk["units"][0]["c1"], Bn, T))
             for ui, unit in enumerate(blk["units"]):
-                _, a2 = self._tap(unit["c1"], act, want_raw=False, act=L.ACT_SNAKE, act_ab=unit["s2"])
+                _, a2 = self._tap(unit["c1"], act, want_raw=False, act=L.ACT_SNAKE, act_ab=unit["s2"], act16=self._want16(unit["c2"], Bn, T))
                 if ui + 1 < len(blk["units"]):
-                    nxt = blk["units"][ui + 1]["s1"]
+                    nxt, nxt16 = blk["units"][ui + 1]["s1"], self._want16(blk["units"][ui + 1]["c1"], Bn, T)
                 elif bi + 1 < len(self.blocks):
-                    nxt = self.blocks[bi + 1]["snake"]
+                    nxt, nxt16 = self.blocks[bi + 1]["snake"], self._want16(self.blocks[bi + 1]["tconv"], Bn, T)
                 else:
-                    nxt = self.snake_out
-                want_raw = ui + 1 < len(blk["units"]) or stages is not None
-                u2, act = self._tap(unit["c2"], a2, resid=u, want_raw=True, act=L.ACT_SNAKE, act_ab=nxt)
-                u = u2
+                    nxt, nxt16 = self.snake_out, self.f16 and co_direct
+                u, act = self._tap(unit["c2"], a2, resid=u, want_raw=True, act=L.ACT_SNAKE, act_ab=nxt, act16=nxt16)
             if stages is not None:
                 stages[f"block{bi}"] = u
-        co = self.conv_out
         Bn, Tn, Cn = act.shape
         out = torch.empty(Bn, Tn, device=self.dev, dtype=torch.float32)
-        if co.cout == 1 and Cn % 4 == 0 and co.shifts == [-(co.taps - 1 - j) for j in range(co.taps)]:
+        if co_direct:
             # one output channel is not GEMM-shaped: dedicated HBM-bound kernel, clamp fused
-            L.check(self.lib.q3t_conv_out_clamp(act.data_ptr(), Bn, Tn, Cn, self.conv_out_w.data_ptr(), L.ptr(co.bias), co.taps,
-                                                out.data_ptr(), L.stream_ptr()), "conv_out_clamp")
+            fn = self.lib.q3t_conv_out_clamp_h if act.dtype == torch.float16 else self.lib.q3t_conv_out_clamp
+            L.check(fn(act.data_ptr(), Bn, Tn, Cn, self.conv_out_w.data_ptr(), L.ptr(co.bias), co.taps, out.data_ptr(), L.stream_ptr()),
+                    "conv_out_clamp")
             return out
         wav, _ = self._tap(co, act)                                         # [B, n, 1]
         L.check(self.lib.q3t_clamp_pcm16(wav.data_ptr(), wav.numel(), out.data_ptr(), 0, L.stream_ptr()), "clamp")

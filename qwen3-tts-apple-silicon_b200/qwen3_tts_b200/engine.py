@@ -42,13 +42,17 @@ class TalkerEngine:
     """Talker + code predictor on one GPU for a fixed batch of `B` lock-step sequences."""
 
     def __init__(self, cfg: ModelConfig, ws: WeightStore, device: str = "cuda", batch: int = 1, max_frames: int = 512,
-                 max_ctx: int = 2048, attn_nsplit: int = 16, keep_cp_logits: bool = False, max_trailing: int = 1,
+                 max_ctx: int = 2048, attn_nsplit: Optional[int] = None, keep_cp_logits: bool = False, max_trailing: int = 1,
                  use_mega: bool = True, prefill: str = "auto", prefill_gemm_rows: int = 32, kv_pages: Optional[int] = None):
         """kv_pages: size of the talker's K/V page POOL (pages of 16 tokens) when the block table is managed by a page
         allocator (serving.ContinuousBatcher): page 0 is a scratch page idle slots point at, the table starts all-zero.  None:
         every sequence owns max_ctx / 16 consecutive pages (identity table, lock-step batches)."""
         self.lib = L.load()
         self.cfg, self.dev, self.B = cfg, torch.device(device), batch
+        if attn_nsplit is None:
+            # context slices per (kv head, sequence) of the decode attention: few sequences need many CTAs; from 8 sequences on
+            # the slices of a head form a thread-block cluster (<= 8) and four fill the machine (csrc/attn_decode.cu)
+            attn_nsplit = 16 if batch <= 2 else (8 if batch < 32 else 4)
         self.max_frames, self.max_ctx, self.max_trailing = max_frames, max_ctx, max_trailing
         self.keep = _Keep()
         t, c = cfg.talker, cfg.cp

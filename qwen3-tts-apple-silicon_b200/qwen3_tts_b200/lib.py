@@ -99,13 +99,14 @@ class StackPassArgs(C.Structure):
 class TapGemmArgs(C.Structure):
     _fields_ = [("A", vp), ("B", i32), ("T_in", i32), ("Cin", i32), ("W", vp), ("bias", vp), ("taps", i32),
                 ("shift", i32 * 8), ("up", i32), ("Cout", i32), ("T_out_rows", i32), ("scale", vp), ("resid", vp),
-                ("out_raw", vp), ("out_act", vp), ("act", i32), ("act_a", vp), ("act_b", vp), ("force_fp32", i32)]
+                ("out_raw", vp), ("out_act", vp), ("act", i32), ("act_a", vp), ("act_b", vp), ("force_fp32", i32),
+                ("a_f16", i32), ("act_f16", i32)]
 
 
 # every symbol include/q3tts_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = ["q3t_abi_version", "q3t_last_error", "q3t_launch_count", "q3t_w8_gemv", "q3t_w8_gemv_rows", "q3t_w8_gemm", "q3t_rmsnorm", "q3t_attn_decode", "q3t_attn_prefill",
            "q3t_sample", "q3t_stack_pass", "q3t_ll_work_bytes", "q3t_talker_step", "q3t_frame", "q3t_talker_prefill", "q3t_talker_tail", "q3t_rvq_gather_sum", "q3t_tapgemm", "q3t_dwconv_ln",
-           "q3t_tapgemm_stats", "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_clamp_pcm16",
+           "q3t_tapgemm_stats", "q3t_window_attn", "q3t_snake", "q3t_conv_out_clamp", "q3t_conv_out_clamp_h", "q3t_tapgemm_tc_eligible", "q3t_clamp_pcm16",
            "q3t_rvq_encode", "q3t_time_stats", "q3t_softmax_time", "q3t_eltwise", "q3t_mel", "q3t_layernorm"]
 
 _lib = None
@@ -148,6 +149,8 @@ def load() -> C.CDLL:
     lib.q3t_window_attn.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, vp]
     lib.q3t_snake.argtypes = [vp, vp, vp, i64, i32, vp, vp]
     lib.q3t_conv_out_clamp.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    lib.q3t_conv_out_clamp_h.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp]
+    lib.q3t_tapgemm_tc_eligible.argtypes = [C.POINTER(TapGemmArgs)]
     lib.q3t_clamp_pcm16.argtypes = [vp, i64, vp, vp, vp]
     lib.q3t_rvq_encode.argtypes = [vp, C.POINTER(vp), i32, i32, i32, i32, i64, vp, vp, vp]
     lib.q3t_time_stats.argtypes = [vp, vp, i32, i32, i32, f32, vp, vp, vp]
