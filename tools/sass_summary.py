@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "qwen3-tts-apple-silicon_b200", "qwen3_tts_b200", "libq3tts_b200.so")
-PAT = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "IMMA", "HMMA", "LDGSTS", "LDSM", "SYNCS"]
+PAT = ["UTCHMMA", "UTCQMMA", "UTCIMMA", "UTCOMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "IMMA", "HMMA", "LDGSTS", "LDSM", "SYNCS", "UCGABAR", "MAPA"]
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 cur, counts, total = None, collections.OrderedDict(), collections.Counter()
 for line in out.splitlines():
