@@ -208,7 +208,7 @@ def cfg2_leg(model, cfg, timed, bf16_peak):
         flops = B * 375 * 4.96e9
         out[f"B{B}"] = {"ms_per_clip_batch": ms, "rtfx": B * 30.0 / (ms / 1e3), "tflops": flops / (ms / 1e3) / 1e12,
                         "frac_of_bf16_sustained": flops / (ms / 1e3) / 1e12 / bf16_peak, "samples": int(wav.shape[-1])}
-    out["note"] = "chunked decode (300 + 75 frames, 25 frames of left context); every conv / linear on the tcgen05 TF32 tap-GEMM"
+    out["note"] = "chunked decode (300 + 75 frames, 25 frames of left context); every conv / linear on the tcgen05 tap-GEMM (fp16 operands between the vocoder layers, TF32 elsewhere)"
     return out
 
 
@@ -284,8 +284,9 @@ def bs64_leg(cfg, args, world, dist, timed):
                                         "d2h_bytes_per_step": int(wav_h.numel() * 4)},
             "ms_total": ms, "ms_prefill": a.elapsed_time(b), "ms_per_frame_first32": first32,
             "ms_per_frame_mean": (ms - a.elapsed_time(b)) / T, "launches_per_frame": eng.launches_per_frame,
-            "note": "greedy, random-init; talker/CP contractions on the tcgen05 W8 GEMM (split-bf16 operands), codec convolutions on the "
-                    "tcgen05 TF32 tap-GEMM; prefill and codec counted inside the timed region (ms_per_frame_mean includes the codec)"}, eng, codec
+            "note": "greedy, random-init; talker/CP contractions on the tcgen05 W8 GEMM (split-bf16 operands, split-K as thread-block clusters), codec "
+                    "convolutions on the tcgen05 tap-GEMM (fp16 operands between the vocoder layers, TF32 elsewhere, fp32 accumulate); prefill and "
+                    "codec counted inside the timed region (ms_per_frame_mean includes the codec)"}, eng, codec
 
 
 def cfg5_leg(cfg, args, world, rank, dist, eng, codec):
@@ -321,6 +322,70 @@ def cfg5_leg(cfg, args, world, rank, dist, eng, codec):
             "note": "sharded by dp.run_sharded over the ranks, batches of 64 utterances x 120-token prompts x 375 frames, waveforms copied to the host"}
 
 
+def serve_leg(cfg, args, world, dist, codec):
+    """BASELINE config 4's "paged KV cache" made to mean something: `serve_requests` requests with ragged
+    prompts (60..180 rows) and ragged frame budgets (100..500 frames; a random-init model never samples EOS, so the budget stands
+    in for the utterance length) through the 64 SLOTS of qwen3_tts_b200.serving.ContinuousBatcher: K/V pages from a free list that
+    cannot hold 64 worst-case requests, admission mid-flight (one ragged tcgen05 prefill per boundary), pages returned the moment
+    a request ends; then the codec over the finished requests in length-sorted batches of 32.  Lock-step batches of 64 would run
+    every batch to its longest member: `lockstep_slot_frames` is what that would have cost."""
+    from qwen3_tts_b200.engine import TalkerEngine
+    from qwen3_tts_b200.serving import ContinuousBatcher, Request
+    from qwen3_tts_b200.weights import make_weights
+    B, n_req, H = 64, args.serve_requests, cfg.talker.hidden_size
+    g = torch.Generator().manual_seed(11)
+    lens = torch.randint(60, 181, (n_req,), generator=g).tolist()
+    budgets = torch.randint(100, 501, (n_req,), generator=g).tolist()
+    per_seq = (180 + 500 + 8 + 15) // 16 + 1
+    pool_pages = int(0.7 * B * per_seq)                        # 70 % of the worst case: admission also waits for pages
+    ws = make_weights(cfg, seed=0, device="cuda", keep_fp=False)
+    eng = TalkerEngine(cfg, ws, "cuda", batch=B, max_frames=512, max_ctx=per_seq * 16, kv_pages=pool_pages)
+    del ws
+    eng.set_sampling(do_sample=False)
+    cb = ContinuousBatcher(eng, pool_pages=pool_pages, sync_every=8)
+    tr = torch.zeros(1, H)
+    reqs = [Request(i, torch.randn(lens[i], H, generator=g) * 0.02, tr, budgets[i]) for i in range(n_req)]
+    cb.run([Request(10_000 + i, torch.randn(64, H, generator=g) * 0.02, tr, 16) for i in range(B)])      # warm-up: every slot once
+    cb.stats = dict(admitted=0, retired=0, prefill_calls=0, frames=0, slot_frames_active=0)
+    cb.frame = 0
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    done = cb.run(reqs)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    order = sorted(range(n_req), key=lambda i: budgets[i])
+    n_samples = 0
+    for o in range(0, n_req, 32):
+        grp = order[o:o + 32]
+        T = max(budgets[i] for i in grp)
+        codes = torch.zeros(len(grp), cfg.codec.num_quantizers, T, dtype=torch.int32)
+        for j, i in enumerate(grp):
+            c = done[i].codes.clamp(0, cfg.codec.codebook_size - 1)
+            codes[j, :, :c.shape[0]] = c.t()
+        wav = codec.decode(codes.cuda()).cpu()
+        n_samples += sum(int(done[i].codes.shape[0]) * cfg.codec.hop for i in grp)
+    sec = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([sec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    audio_s = sum(budgets) * 0.08
+    lock = sum(max(budgets[o:o + B]) * B for o in range(0, n_req, B))
+    assert sorted(done) == list(range(n_req)) and cb.pool.free == pool_pages
+    out = {"value": world * audio_s / sec, "unit": UNIT, "requests": n_req, "slots": B, "prompt_rows": [min(lens), max(lens)],
+           "frame_budgets": [min(budgets), max(budgets)], "pool_pages": pool_pages, "worst_case_pages": B * per_seq,
+           "peak_pages_used": cb.pool.peak_used, "seconds": sec, "seconds_generation": t_gen, "scheduler_frames": cb.stats["frames"],
+           "prefill_calls": cb.stats["prefill_calls"], "slot_utilisation": cb.stats["slot_frames_active"] / max(1, cb.stats["frames"] * B),
+           "slot_frames": sum(budgets), "lockstep_slot_frames": lock, "audio_samples": n_samples,
+           "note": "continuous batching: per-slot frame counters, K/V pages from a free list (16 tokens each), ragged tcgen05 prefill at admission, "
+                   "one host look at the done flags / counters every 8 frames; codec of the finished requests inside the timed region"}
+    del cb, eng
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -334,6 +399,7 @@ def main():
     ap.add_argument("--no-bs64", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg2 / cfg3 / cfg5 legs")
     ap.add_argument("--bs64-frames", type=int, default=960)
+    ap.add_argument("--serve-requests", type=int, default=160, help="requests of the continuous-batching leg")
     ap.add_argument("--cfg5-batches", type=int, default=1)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -478,7 +544,13 @@ def main():
             c5 = cfg5_leg(cfg, args, world, rank, dist, eng, codec)
             if c5 is not None:
                 line["cfg5"] = c5
-        del eng, codec
+        del eng
+        torch.cuda.empty_cache()
+        if not args.no_extra:
+            sv = serve_leg(cfg, args, world, dist, codec)
+            if rank == 0:
+                line["serve"] = sv
+        del codec
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, detail = CpuOracle(args.size).sample(args.cpu_frames)

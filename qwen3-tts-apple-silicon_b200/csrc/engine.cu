@@ -90,10 +90,12 @@ int launch_rmsnorm(const float* x, const float* w, float* y, int M, int H, float
 #define Q3T_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
 
 // rows through one W8 matrix: B <= 2 -> exact-integer GEMV (two rows per launch); more rows -> tcgen05 GEMM (bf16 operands)
-static void* g_xb = nullptr;    // bf16 scratch of the call in flight (set by the entry points below)
-static void* g_xb2 = nullptr;   // second bf16 scratch: attention output / SwiGLU activations handed from kernel to kernel as bf16
-static float* g_ws = nullptr; static long long g_ws_floats = 0; static int* g_counters = nullptr;
-static float* g_rowss = nullptr;   // row statistics of the deferred RMSNorm ([rows, 32] fp32); NULL = norms are prologue launches
+// scratch of the call in flight, set by the entry points below; thread_local: two engines driven from two host threads (ctypes
+// releases the GIL) must not see each other's buffers
+static thread_local void* g_xb = nullptr;    // bf16 scratch
+static thread_local void* g_xb2 = nullptr;   // second bf16 scratch: attention output / SwiGLU activations handed from kernel to kernel as bf16
+static thread_local float* g_ws = nullptr; static thread_local long long g_ws_floats = 0; static thread_local int* g_counters = nullptr;
+static thread_local float* g_rowss = nullptr;   // row statistics of the deferred RMSNorm ([rows, 32] fp32); NULL = norms are prologue launches
 static int gemv_rows(const q3t_w8& w, int B, int prologue, const float* x, long long xs, const float* norm_w, float eps,
                      const int* gidx, int gidx_stride, long long grow, int act, const float* resid, long long rs,
                      float* y, long long ys, cudaStream_t s) {
