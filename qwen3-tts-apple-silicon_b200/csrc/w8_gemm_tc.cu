@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
         const int dw = (warp - 2) >> 1;           // row tile of this warp pair inside the 128-row block
         const int jh = (warp - 2) & 1;            // which 32-wide half of the 64-wide K block this warp converts
         const int g = lane >> 2, t = lane & 3;
-        pdl_wait();                               // activations come from the previous kernel
+        // (no griddepcontrol.wait here: the weight operand does not depend on the previous kernel, so the first stages are
+        // dequantised under its tail; these warps wait right before the epilogue, which reads residual rows and row statistics)
         for (int kb = 0; kb < nkb; ++kb) {
             const int st = kb % TC_A_STAGES, par = (kb / TC_A_STAGES) & 1;
             const int kc = kb >> 2, j4 = kb & 3, rs = kc % TC_RAW_STAGES, rpar = (kc / TC_RAW_STAGES) & 1;
@@ -318,6 +319,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) w8_gemm_tc_kernel(const GemmPar
     const int dt = tid - 64;                                   // 0..511 for the epilogue warps
     const int n0 = nb * TC_BM, nt = bn;
     if (warp >= 2) {
+        pdl_wait();                               // residual rows / row statistics / the rows this epilogue overwrites
         if (warp < 6) {
             tc_mbar_wait(tc_smem_u32(tmem_full), 0);
             if (tid == 64) TC_STAMP(5);
