@@ -15,6 +15,7 @@
 //   * epilogue: 4 warps move the accumulator TMEM -> shared memory, then all 16 epilogue warps apply bias / LayerScale /
 //     residual / SnakeBeta / GELU / SiLU / SwiGLU-pair and store coalesced rows.
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
@@ -56,10 +57,39 @@ __device__ __forceinline__ void tt_mbar_wait(uint32_t bar, uint32_t parity) {
         "bra TT_WAIT;\n"
         "TT_DONE:\n}\n" ::"r"(bar), "r"(parity) : "memory");
 }
+// long waits (the epilogue warps wait microseconds for an accumulator): try_wait with a suspend-time hint parks the warp in
+// hardware until the phase flips instead of re-issuing the probe - 16 to 32 spinning warps per SM otherwise compete for issue
+// slots with the warps of the other resident CTA that are doing the epilogue arithmetic
+__device__ __forceinline__ void tt_mbar_wait_parked(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "TT_PWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra TT_PDONE;\n"
+        "bra TT_PWAIT;\n"
+        "TT_PDONE:\n}\n" ::"r"(bar), "r"(parity), "r"(1000000u) : "memory");
+}
 __device__ __forceinline__ uint64_t tt_smem_desc(uint32_t saddr) {      // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 __device__ __forceinline__ float tt_gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+// sin(x) for the SnakeBeta epilogue: two-constant Cody-Waite reduction to [-pi, pi], then the SFU's sine (abs error 2^-21.4 on
+// that interval).  sinf()'s full-accuracy path costs ~25 instructions per element and the epilogue of every vocoder layer is
+// bound by exactly those issue slots (ncu launch lists: halving the bytes a tile pulls did not move the kernel, see
+// profiles/r02_ll_experiments.txt); the error left (~5e-7 absolute for |x| < 1e4) is three orders below the fp16 / TF32
+// rounding of the stored activation.
+__device__ __forceinline__ float tt_sin(float x) {
+    const float k = rintf(x * 0.15915494309189535f);                    // x / 2 pi
+    float r = fmaf(-k, 6.2831854820251465f, x);                         // 2 pi, high part (fp32(2 pi))
+    r = fmaf(-k, -1.7484555e-7f, r);                                    // 2 pi - fp32(2 pi)
+    return __sinf(r);
+}
+// two fp32 -> packed fp16x2, round to nearest, saturating at +-65504 (one F2FP.SATFINITE instead of four min / max + convert)
+__device__ __forceinline__ uint32_t tt_pack_h2_sat(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ float tt_round_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -97,10 +127,11 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
     if (warp == 0) {
         if (lane == 0) {
             // ===================== producer: A through the 3-D map at (ci, t0 + shift, b), W through the 2-D map ==========
+            // K blocks outermost, taps inside
             int s = 0;
-            for (int tap = 0; tap < p.taps; ++tap) {
-                const int ta = t0 + p.shift[tap];
-                for (int kb = 0; kb < nkb; ++kb, ++s) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                for (int tap = 0; tap < p.taps; ++tap, ++s) {
+                    const int ta = t0 + p.shift[tap];
                     const int st = s % TT_STAGES, par = (s / TT_STAGES) & 1;
                     tt_mbar_wait(tt_smem_u32(&empty[st]), par ^ 1);
                     const uint32_t fb = tt_smem_u32(&full[st]);
@@ -149,9 +180,12 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
         // ===================== epilogue =====================================================================================
         float* stg = reinterpret_cast<float*>(smem);               // the operand ring is free once the accumulator is complete
         const int dt = tid - 64;
-        tt_mbar_wait(tt_smem_u32(tmem_full), 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // only the four warps that read TMEM poll the accumulator barrier; the other twelve sleep in the named barrier below (a
+        // polling warp re-issues its probe every ~34 cycles: sixteen of them per CTA were a quarter of all issued instructions,
+        // ncu source page)
         if (warp < 6) {
+            tt_mbar_wait_parked(tt_smem_u32(tmem_full), 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int lg = warp & 3, r_local = lg * 32 + lane;     // TMEM lane = output row (time step) of this tile
             const uint32_t tbase = tmem_d + ((uint32_t)(lg * 32) << 16);
             const int ncols_ld = min(TT_BN, (p.N - n0 + 15) & ~15);      // only the columns this tile owns (N = 96: 96 of 128)
@@ -197,6 +231,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
             // convolutions of the vocoder (ncu: 2 TB/s of DRAM traffic on a layer that only moves bytes).
             constexpr int ITEMS = 4;      // per batch; (128 x 128 / 4) / 512 threads = 8 items per thread = two batches (56-register budget)
             const int nc4 = ncols >> 2, n_items = nrows * nc4;
+            const unsigned inv_nc4 = (1u << 20) / (unsigned)nc4 + 1u;       // i / nc4 == (i * inv_nc4) >> 20 for i < 4096, nc4 <= 32
+            const bool plain_c = p.N == p.Cout;                           // every layer but the transposed convs: channel = column
             for (int i0 = dt; i0 < n_items; i0 += ITEMS * TT_EPI_WARPS * 32) {
             float4 res[ITEMS];
             if (p.resid) {
@@ -204,7 +240,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                 for (int q = 0; q < ITEMS; ++q) {
                     const int i = i0 + q * (TT_EPI_WARPS * 32);
                     if (i < n_items) {
-                        const int r = i / nc4, j = (i - r * nc4) << 2;
+                        const int r = (int)(((unsigned)i * inv_nc4) >> 20), j = (i - r * nc4) << 2;
                         res[q] = __ldcs(reinterpret_cast<const float4*>(p.resid + (m_base + r) * p.N + n0 + j));
                     }
                 }
@@ -213,8 +249,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
             for (int q = 0; q < ITEMS; ++q) {
                 const int i = i0 + q * (TT_EPI_WARPS * 32);
                 if (i >= n_items) break;
-                const int r = i / nc4, j = (i - r * nc4) << 2;
-                const int n = n0 + j, c = n % p.Cout;
+                const int r = (int)(((unsigned)i * inv_nc4) >> 20), j = (i - r * nc4) << 2;
+                const int n = n0 + j, c = plain_c ? n : n % p.Cout;
                 const float* sp = stg + r * TT_STG_LD + j;
                 float x[4] = {sp[0], sp[1], sp[2], sp[3]};
                 if (p.bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + c)); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
@@ -228,7 +264,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                         const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.act_a + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.act_b + c));
                         const float aa[4] = {a4.x, a4.y, a4.z, a4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) { const float sn = sinf(x[e] * aa[e]); x[e] = x[e] + bb[e] * (sn * sn); }
+                        for (int e = 0; e < 4; ++e) { const float sn = tt_sin(x[e] * aa[e]); x[e] = x[e] + bb[e] * (sn * sn); }
                     } else if (p.act == Q3T_ACT_GELU) {
 #pragma unroll
                         for (int e = 0; e < 4; ++e) x[e] = tt_gelu_erf(x[e]);
@@ -241,10 +277,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                     }
                     if (p.act_f16) {
                         // fp16 keeps 11 significant bits (TF32: 10); saturate instead of overflowing to inf
-                        __half2 h01 = __floats2half2_rn(fminf(fmaxf(x[0], -65504.f), 65504.f), fminf(fmaxf(x[1], -65504.f), 65504.f));
-                        __half2 h23 = __floats2half2_rn(fminf(fmaxf(x[2], -65504.f), 65504.f), fminf(fmaxf(x[3], -65504.f), 65504.f));
                         uint2 hv;
-                        hv.x = *reinterpret_cast<uint32_t*>(&h01); hv.y = *reinterpret_cast<uint32_t*>(&h23);
+                        hv.x = tt_pack_h2_sat(x[0], x[1]); hv.y = tt_pack_h2_sat(x[2], x[3]);
                         *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_act) + o) = hv;
                     } else {
                         *reinterpret_cast<float4*>(p.out_act + o) = make_float4(tt_round_tf32(x[0]), tt_round_tf32(x[1]), tt_round_tf32(x[2]), tt_round_tf32(x[3]));
