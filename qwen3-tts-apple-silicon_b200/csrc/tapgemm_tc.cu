@@ -30,7 +30,7 @@ constexpr int TT_A_BYTES = TT_BM * 128, TT_B_BYTES = TT_BN * 128;     // 16 KB e
 constexpr int TT_STAGE_BYTES = TT_A_BYTES + TT_B_BYTES;
 constexpr int TT_OFF_BAR = TT_STAGES * TT_STAGE_BYTES;                 // 98 304
 constexpr int TT_SMEM_BYTES = TT_OFF_BAR + 128 + 1024;                 // + barriers + alignment slack
-constexpr int TT_STG_LD = TT_BN + 1;                                   // staging tile [128 rows][129]: conflict-free both ways
+constexpr int TT_STG_LD = TT_BN + 4;                                   // staging tile [128 rows][132]: 16-byte rows, conflict-free for the 128-bit row writes (lane = row) and reads
 static_assert(TT_BM * TT_STG_LD * 4 <= TT_OFF_BAR, "staging tile must fit the operand ring");
 
 struct TapTcParams {
@@ -197,9 +197,10 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                              : "r"(tbase + (uint32_t)c0));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float* d = stg + r_local * TT_STG_LD + c0;
+                float4* d = reinterpret_cast<float4*>(stg + r_local * TT_STG_LD + c0);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) d[c] = __uint_as_float(v[c]);
+                for (int c = 0; c < 4; ++c)
+                    d[c] = make_float4(__uint_as_float(v[4 * c]), __uint_as_float(v[4 * c + 1]), __uint_as_float(v[4 * c + 2]), __uint_as_float(v[4 * c + 3]));
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
@@ -251,8 +252,8 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
                 if (i >= n_items) break;
                 const int r = (int)(((unsigned)i * inv_nc4) >> 20), j = (i - r * nc4) << 2;
                 const int n = n0 + j, c = plain_c ? n : n % p.Cout;
-                const float* sp = stg + r * TT_STG_LD + j;
-                float x[4] = {sp[0], sp[1], sp[2], sp[3]};
+                const float4 s4 = *reinterpret_cast<const float4*>(stg + r * TT_STG_LD + j);
+                float x[4] = {s4.x, s4.y, s4.z, s4.w};
                 if (p.bias) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.bias + c)); x[0] += t4.x; x[1] += t4.y; x[2] += t4.z; x[3] += t4.w; }
                 if (p.scale) { const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.scale + c)); x[0] *= t4.x; x[1] *= t4.y; x[2] *= t4.z; x[3] *= t4.w; }
                 if (p.resid) { x[0] += res[q].x; x[1] += res[q].y; x[2] += res[q].z; x[3] += res[q].w; }
