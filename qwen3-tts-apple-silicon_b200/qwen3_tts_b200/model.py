@@ -251,7 +251,7 @@ class Model:
     def generate(self, text: str, voice: Optional[str] = None, instruct: Optional[str] = None, speed: float = 1.0,
                  lang_code: str = "auto", ref_audio: Optional[str] = None, ref_text: Optional[str] = None,
                  temperature: Optional[float] = None, top_k: int = 50, top_p: float = 1.0,
-                 repetition_penalty: float = 1.05, max_tokens: int = 1200, seed: int = 0, verbose: bool = False,
+                 repetition_penalty: float = 1.05, max_tokens: int = 1200, seed: Optional[int] = None, verbose: bool = False,
                  stream: bool = False, streaming_interval: float = 2.0, max_segment_chars: int = 600,
                  **kwargs) -> Iterator[GenerationResult]:
         """One utterance -> one result (the reference consumes only audio_000.wav, io.py:156); with `stream=True` one
@@ -263,6 +263,10 @@ class Model:
         t0 = time.perf_counter()
         mode = self.cfg.tts_model_type
         greedy = kwargs.pop("greedy", False) or (temperature is not None and temperature <= 0)
+        if seed is None:
+            # like the reference stack's global RNG, two sampled calls with the same text differ; pass `seed` to reproduce one
+            self._auto_seed = (getattr(self, "_auto_seed", None) or int.from_bytes(os.urandom(4), "little")) + 1
+            seed = 0 if greedy else self._auto_seed
         self.engine.set_sampling(do_sample=not greedy, temperature=temperature or 0.9, top_k=top_k, top_p=top_p,
                                  repetition_penalty=repetition_penalty, seed=seed)
         language = None if lang_code in (None, "auto") else lang_code

@@ -386,6 +386,22 @@ def test_bf16_chaining_between_batched_kernels_is_bit_identical(cuda, monkeypatc
     assert _rel(outs[0][3], outs[1][3]) < 4 * max(err[1]) + 1e-4
 
 
+def test_sampled_calls_differ_unless_seeded(small_setup):
+    """The reference stack samples from a global RNG (sessions/custom.py:163-170 never passes a seed): two sampled calls with the same
+    text give different codes; an explicit `seed` reproduces a call; greedy calls are deterministic."""
+    cfg, ws, model, oracle = small_setup
+    kw = dict(voice="ryan", max_tokens=6, temperature=1.0)
+    a = list(model.generate("hello there", **kw))[0].codes
+    b = list(model.generate("hello there", **kw))[0].codes
+    assert a.shape == b.shape and (a != b).any()
+    c = list(model.generate("hello there", seed=7, **kw))[0].codes
+    d = list(model.generate("hello there", seed=7, **kw))[0].codes
+    assert (c == d).all()
+    g1 = list(model.generate("hello there", voice="ryan", max_tokens=6, greedy=True))[0].codes
+    g2 = list(model.generate("hello there", voice="ryan", max_tokens=6, greedy=True))[0].codes
+    assert (g1 == g2).all()
+
+
 def test_streaming_generation_equals_offline_chunked_decode(small_setup):
     """BASELINE config 3 (streaming, frame by frame): the pieces yielded every `interval` frames - codes and audio -
     concatenate to exactly what the offline path gives (same greedy codes; codec chunked with chunk_size = interval and
