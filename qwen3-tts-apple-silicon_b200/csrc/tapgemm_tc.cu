@@ -10,9 +10,11 @@
 //   * operands stay fp32 in HBM/L2 (the codec is fp32 end to end); the tensor core reads them as TF32 (kind::tf32, 10-bit
 //     mantissa, fp32 accumulate in TMEM).  Weights are rounded to TF32 once at load and the epilogue rounds what it stores
 //     (cvt.rna.tf32), so the hardware's truncation never sees low mantissa bits -> unbiased 2^-11 rounding per operand;
-//   * MMA tile 128 rows (time) x 128 columns (channels) x 32 (Cin slice = one 128-byte swizzle row), 3-stage TMA ring,
-//     96 KB of shared memory -> two CTAs per SM, so one CTA's epilogue overlaps the other's MMAs;
-//   * epilogue: 4 warps move the accumulator TMEM -> shared memory, then all 16 epilogue warps apply bias / LayerScale /
+//   * MMA tile 128 rows (time) x 128 columns (channels) x 32 (Cin slice = one 128-byte swizzle row), 2-stage TMA ring,
+//     68 KB of shared memory and 320 threads -> THREE CTAs per SM: a tile is a chain launch -> set-up -> first TMA -> MMAs ->
+//     accumulator -> staging -> stores -> exit, and what hides it is the number of tiles in flight per SM (3 x 8 epilogue warps
+//     measured 3 % faster than 2 x 16 with a 3-stage ring; 3 x 12 spills at 40 registers and is no faster);
+//   * epilogue: 4 warps move the accumulator TMEM -> shared memory, then all 8 epilogue warps apply bias / LayerScale /
 //     residual / SnakeBeta / GELU / SiLU / SwiGLU-pair and store coalesced rows.
 #include <cuda.h>
 #include <stdlib.h>
@@ -22,13 +24,13 @@
 
 namespace q3t {
 
-constexpr int TT_EPI_WARPS = 16;
-constexpr int TT_THREADS = 64 + TT_EPI_WARPS * 32;      // producer warp, MMA warp, 16 epilogue warps
+constexpr int TT_EPI_WARPS = 8;
+constexpr int TT_THREADS = 64 + TT_EPI_WARPS * 32;      // producer warp, MMA warp, 8 epilogue warps
 constexpr int TT_BM = 128, TT_BN = 128, TT_BK = 32;
-constexpr int TT_STAGES = 3;
+constexpr int TT_STAGES = 2;
 constexpr int TT_A_BYTES = TT_BM * 128, TT_B_BYTES = TT_BN * 128;     // 16 KB each
 constexpr int TT_STAGE_BYTES = TT_A_BYTES + TT_B_BYTES;
-constexpr int TT_OFF_BAR = TT_STAGES * TT_STAGE_BYTES;                 // 98 304
+constexpr int TT_OFF_BAR = TT_STAGES * TT_STAGE_BYTES + 2048;          // ring (64 KB) + room for the 67.6 KB staging tile
 constexpr int TT_SMEM_BYTES = TT_OFF_BAR + 128 + 1024;                 // + barriers + alignment slack
 constexpr int TT_STG_LD = TT_BN + 4;                                   // staging tile [128 rows][132]: 16-byte rows, conflict-free for the 128-bit row writes (lane = row) and reads
 static_assert(TT_BM * TT_STG_LD * 4 <= TT_OFF_BAR, "staging tile must fit the operand ring");
@@ -96,7 +98,7 @@ __device__ __forceinline__ float tt_round_tf32(float x) {
     return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcParams p, const __grid_constant__ CUtensorMap tm_a,
+__global__ void __launch_bounds__(TT_THREADS, 3) tapgemm_tc_kernel(const TapTcParams p, const __grid_constant__ CUtensorMap tm_a,
                                                                     const __grid_constant__ CUtensorMap tm_w) {
     extern __shared__ unsigned char tt_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)tt_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(TT_EPI_WARPS * 32) : "memory");
         const int ncols = p.N - n0 < TT_BN ? p.N - n0 : TT_BN;
         const int nrows = p.rows - t0 < TT_BM ? p.rows - t0 : TT_BM;
         const long long m_base = (long long)b * p.rows + t0;       // global output row of local row 0
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(TT_THREADS, 2) tapgemm_tc_kernel(const TapTcPa
             // residual loads of a thread are issued BEFORE its first store: the scalar one-element loop this replaces interleaved a
             // dependent DRAM load with two stores per element - 24 serialized round trips per warp, 34 us per tile for the 1x1
             // convolutions of the vocoder (ncu: 2 TB/s of DRAM traffic on a layer that only moves bytes).
-            constexpr int ITEMS = 4;      // per batch; (128 x 128 / 4) / 512 threads = 8 items per thread = two batches (56-register budget)
+            constexpr int ITEMS = 4;      // per batch; (128 x 128 / 4) / 256 threads = 16 items per thread = four batches
             const int nc4 = ncols >> 2, n_items = nrows * nc4;
             const unsigned inv_nc4 = (1u << 20) / (unsigned)nc4 + 1u;       // i / nc4 == (i * inv_nc4) >> 20 for i < 4096, nc4 <= 32
             const bool plain_c = p.N == p.Cout;                           // every layer but the transposed convs: channel = column
