@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define Q3T_ABI_VERSION 1
+#define Q3T_ABI_VERSION 2   /* 2: round 2 - fields appended to q3t_gemm_args, q3t_tapgemm_args, q3t_frame_args, q3t_prefill_args, q3t_sample_args; new entry points */
 #define Q3T_TILE_BYTES 4352
 #define Q3T_KV_PAGE 16
 

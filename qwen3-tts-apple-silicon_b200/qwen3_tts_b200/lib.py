@@ -158,7 +158,7 @@ def load() -> C.CDLL:
     lib.q3t_eltwise.argtypes = [i32, vp, vp, vp, i64, i32, i64, vp, vp]
     lib.q3t_mel.argtypes = [vp, i64, i32, i32, vp, i32, vp, vp]
     lib.q3t_layernorm.argtypes = [vp, vp, vp, i64, i32, f32, vp, vp]
-    if lib.q3t_abi_version() != 1:
+    if lib.q3t_abi_version() != 2:
         raise Q3TError("libq3tts_b200.so ABI version mismatch")
     _lib = lib
     return lib

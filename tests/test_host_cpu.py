@@ -77,7 +77,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.q3t_abi_version() == 1
+    assert lib.q3t_abi_version() == 2
     # struct mirrors must match the C layout: compile a tiny probe against the header
     probe = r'''
     #include "q3tts_b200.h"
