@@ -2,26 +2,28 @@
 //     Y[m, n] = epilogue( sum_k  X[m, k] * dequant(W8)[n, k] )          M = tokens (batch-64 decode, prefill), N = features
 // Replaces mx.quantized_matmul (qmm path: batched decode and prefill) of the reference stack.
 //
-// Shape of the problem: W is streamed from HBM exactly once per launch, so at M = 64 the kernel is HBM-bound and at
-// prefill sizes tensor-bound.  W plays the MMA "A" operand (128 output features per CTA = eight 16-row W8 tiles), the
-// activations are the "B" operand (up to 256 tokens per CTA), the fp32 accumulator D[128 features x tokens] lives in TMEM.
-//   warp 0      : producer - cp.async.bulk (TMA, no tensor map: W8 tiles are contiguous 4352-byte records) into a 2-stage
-//                 ring of raw tiles, one stage = the eight tiles of one 256-wide K chunk
-//   warp 1      : allocates TMEM; one elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M=128, N=tokens,
-//                 K=16 per instruction, four per 64-wide K block) and commits to mbarriers
-//   warps 2..17 : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout
-//                 (warp w owns row tile w; codes are fragment-ordered in HBM, every lane converts 32 codes per block:
-//                 byte -> fp32 by the 2^23 trick, one FFMA with the group scale/bias, cvt.rn.bf16x2, 8-byte stores),
-//                 then fence.proxy.async + mbarrier arrive; the matching activation block (bf16, prepared by
-//                 act_prep_kernel) is a 2-D TMA tensor-map load with hardware SWIZZLE_128B issued by a second producer lane;
-//                 (c) warps 2..5 run the epilogue: tcgen05.ld (32 lanes x 32
-//                 columns) -> bias / SiLU / SwiGLU pair / residual -> coalesced fp32 stores.
+// Shape of the problem: W is streamed from HBM exactly once per launch.  At M = 64 the kernel is paced by the dequantise -> MMA
+// loop (0.7 us per 128 x 64 weight block, tools/gemm_stamps.py) and by ~4.5 us of fixed cost per launch, at prefill sizes by the
+// tensor pipe.  W plays the MMA "A" operand (128 output features per CTA = eight 16-row W8 tiles), the activations are the "B"
+// operand (up to 128 tokens per CTA), the fp32 accumulator D[128 features x 2 x tokens] lives in TMEM.
+//   warp 0      : lane 0 - cp.async.bulk (TMA, no tensor map: W8 tiles are contiguous 4352-byte records) into a 2-stage ring of
+//                 raw tiles, one stage = the eight tiles of one 256-wide K chunk, starting BEFORE the previous kernel has
+//                 finished (weights do not depend on it); lane 1 - the activation blocks (bf16 split rows) by 2-D TMA tensor map
+//                 with hardware SWIZZLE_128B into a ring of their own (5 stages at 64 tokens)
+//   warp 1      : allocates TMEM; one elected lane issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, M=128, K=16 per
+//                 instruction): per K step W_hi x [x_hi | x_lo] (N = 2 x tokens) and W_lo x x_hi (N = tokens), commits to mbarriers
+//   warps 2..17 : (a) dequantise one 64-wide K block of the raw stage into the bf16 K-major SWIZZLE_128B operand layout, hi and lo
+//                 plane (two warps per 16-row tile; codes are fragment-ordered in HBM: byte -> fp32 by the 2^23 trick, one FFMA
+//                 with the group scale/bias, cvt.rn.bf16x2, 8-byte stores), fence.proxy.async + mbarrier arrive - also ahead of
+//                 the grid dependency; (b) epilogue: warps 2..5 tcgen05.ld both accumulator halves -> staging tile; split-K =
+//                 the CTAs of one output tile are a thread-block CLUSTER, every rank sums its token slice over the ranks'
+//                 staging tiles through distributed shared memory (rank order: deterministic); then bias / SiLU / SwiGLU pair /
+//                 residual / deferred-RMSNorm scale and statistics -> coalesced fp32 or split-bf16 stores.
 // Numerics: SPLIT-bf16 operands, fp32 accumulation.  A 28-layer random-init stack amplifies a single bf16 rounding of the
 // operands (2^-9) to 1.4e-2 of max|logit| (measured against the fp32 CPU oracle at the 1.7B shapes; weights alone 1.7e-2,
 // TF32 operands 6e-3) - outside the 1e-2 BASELINE.json allows.  So every operand is carried as hi + lo, both bf16
-// (hi = rn(v), lo = rn(v - hi): 16 mantissa bits), and a K block costs three MMAs: W_hi.x_hi + W_lo.x_hi + W_hi.x_lo (the
-// lo.lo term is 2^-18 relative).  The tensor pipe is idle at decode sizes anyway (HBM / latency bound); prompt GEMMs pay
-// 3x MMA issue.  Activation rows therefore travel between kernels as "split rows" [hi(K) | lo(K)] of 2K bf16 (the same
+// (hi = rn(v), lo = rn(v - hi): 16 mantissa bits), and a K block costs three products: W_hi.x_hi + W_lo.x_hi + W_hi.x_lo (the
+// lo.lo term is 2^-18 relative) issued as two instructions per K step.  Prompt GEMMs pay 3x the MACs.  Activation rows therefore travel between kernels as "split rows" [hi(K) | lo(K)] of 2K bf16 (the same
 // bytes as the fp32 row).  The batch-1/2 GEMV (w8_gemv.cu, frame_ll.cu) stays exact-integer.
 #include <cuda.h>
 #include "common.cuh"
