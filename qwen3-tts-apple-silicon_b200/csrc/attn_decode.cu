@@ -6,9 +6,11 @@
 //
 // grid = (kv_head, split, batch); 128 threads.  A CTA owns one KV head (its `REP` query heads share every
 // K/V byte it streams) and one contiguous slice of the context, so the KV pages are read exactly once
-// per step.  Each half-warp streams one token at a time with 128-bit loads (16 lanes x 8 bf16 = one
-// 256 B row); scores are reduced with 4 xor-shuffles; softmax is online in fp32.  Slices are merged by
-// the last CTA to arrive (fixed split order => deterministic, no float atomics).
+// per step.  Each half-warp streams two tokens of a page per iteration with 128-bit loads (16 lanes x 8 bf16 =
+// one 256 B row), the next page's loads in flight; scores are reduced with 4 xor-shuffles; softmax is online in
+// fp32.  The slices of one (kv head, sequence) are a thread-block cluster merged by slice 0 through distributed
+// shared memory (more than 8 slices: L2 workspace + last CTA to arrive); fixed slice order => deterministic,
+// no float atomics.
 #include "common.cuh"
 #include "../../include/q3tts_b200.h"
 
