@@ -62,6 +62,29 @@ class Request:
     pages: List[int] = field(default_factory=list)
 
 
+def plan_admissions(pending: Deque["Request"], slots: Sequence[Optional["Request"]], pool: PagePool, pages_per_seq: int,
+                    engine_max_frames: int, sync_every: int) -> List:
+    """Admission policy, first come first served: the head of the queue enters the lowest free slot as soon as the pool holds
+    ceil((prompt + max_frames + sync_every) / 16) pages for it (a finished slot keeps stepping until the next look at the flags, so
+    those frames are budgeted too); a head-of-line request that does not fit makes everybody behind it wait.  Takes the pages and
+    pops the queue; returns [(slot, request)].  Pure host logic (tests/test_serving_cpu.py)."""
+    pairs = []
+    for b in range(len(slots)):
+        if slots[b] is not None or not pending:
+            continue
+        r = pending[0]
+        need = (int(r.prefill.shape[0]) + r.max_frames + sync_every + L.KV_PAGE - 1) // L.KV_PAGE
+        if need > pages_per_seq or r.max_frames > engine_max_frames:
+            raise ValueError(f"request {r.rid}: {need} pages / {r.max_frames} frames exceed the engine's max_ctx / max_frames")
+        pages = pool.alloc(need)
+        if pages is None:
+            break                      # head-of-line request waits for pages
+        r.pages = pages
+        pending.popleft()
+        pairs.append((b, r))
+    return pairs
+
+
 class ContinuousBatcher:
     def __init__(self, engine: TalkerEngine, pool_pages: int, sync_every: int = 8):
         e = self.e = engine
@@ -146,21 +169,7 @@ class ContinuousBatcher:
         per_seq = e.talker_tbl.shape[1]
         while pending or any(s is not None for s in self.slots):
             # admit: first come, first served, while a slot AND enough pages are free
-            pairs = []
-            for b in range(e.B):
-                if self.slots[b] is not None or not pending:
-                    continue
-                r = pending[0]
-                # a finished slot keeps stepping until the next look at the flags: budget those frames too
-                need = (int(r.prefill.shape[0]) + r.max_frames + self.sync_every + L.KV_PAGE - 1) // L.KV_PAGE
-                if need > per_seq or r.max_frames > e.max_frames:
-                    raise ValueError(f"request {r.rid}: {need} pages / {r.max_frames} frames exceed the engine's max_ctx / max_frames")
-                pages = self.pool.alloc(need)
-                if pages is None:
-                    break                      # head-of-line request waits for pages
-                r.pages = pages
-                pending.popleft()
-                pairs.append((b, r))
+            pairs = plan_admissions(pending, self.slots, self.pool, per_seq, e.max_frames, self.sync_every)
             if pairs:
                 self._admit(pairs)
             n_active = sum(s is not None for s in self.slots)
