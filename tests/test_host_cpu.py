@@ -92,6 +92,19 @@ def test_library_exports_every_declared_symbol():
     mirrors = [L.W8, L.GemvArgs, L.AttnArgs, L.Sampling, L.SampleArgs, L.Layer, L.Stack, L.FrameArgs, L.TapGemmArgs,
                L.GemmArgs, L.AttnPrefillArgs, L.PrefillArgs]
     assert sizes == [ctypes.sizeof(m) for m in mirrors]
+    # ... and the fields round 2 appended sit where the C compiler puts them
+    probe2 = r'''
+    #include "q3tts_b200.h"
+    #include <stddef.h>
+    #include <stdio.h>
+    int main(){ printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(q3t_gemm_args, y_norm_w), offsetof(q3t_gemm_args, x_rowss_parts),
+        offsetof(q3t_tapgemm_args, a_f16), offsetof(q3t_tapgemm_args, act_f16), offsetof(q3t_frame_args, active),
+        offsetof(q3t_frame_args, gemm_rowss), offsetof(q3t_prefill_args, rowss), offsetof(q3t_sample_args, step_stride)); return 0; }'''
+    open(src, "w").write(probe2)
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+    offs = list(map(int, subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()))
+    assert offs == [L.GemmArgs.y_norm_w.offset, L.GemmArgs.x_rowss_parts.offset, L.TapGemmArgs.a_f16.offset, L.TapGemmArgs.act_f16.offset,
+                    L.FrameArgs.active.offset, L.FrameArgs.gemm_rowss.offset, L.PrefillArgs.rowss.offset, L.SampleArgs.step_stride.offset]
 
 
 def test_product_path_has_no_cpu_fallback_and_never_imports_the_oracle():
